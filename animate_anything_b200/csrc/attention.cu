@@ -1,0 +1,433 @@
+// Attention kernels of the denoising path.
+//
+// 1. aab_flash_attn_d64 — spatial self-attention and text cross-attention of diffusers' BasicTransformerBlock
+//    (head_dim 64; reference call sites: Transformer2DModel built at models/unet_3d_blocks.py:287-296,446-456,
+//    681-691, processor AttnProcessor2_0 -> F.scaled_dot_product_attention installed by train.py:124-138).
+//    Flash-style: one CTA owns 256 query rows (two 128-row tiles, ping-pong) of one (batch, head);
+//    S = Q.K^T and O_j = P_j.V_j run on tcgen05 with S / O_j in TMEM; two softmax warpgroups do the online
+//    softmax (exp2, fp32 running max / sum), write P (16-bit) into 128B-swizzled shared memory as the A operand of
+//    the second MMA and accumulate O in registers.  K/V tiles are TMA-loaded into a 3-stage ring shared by both
+//    query tiles.  Keys past Lk (e.g. 77 text tokens in a 128-key tile) are masked to -inf.
+//
+// 2. aab_temporal_attn_d64 — self-attention over the frame axis (T <= 32) of TransformerTemporalModel
+//    (models/unet_3d_blocks.py:299-306,459-467,694-701; called without encoder_hidden_states so both attn1 and attn2
+//    are self-attention over T).  Activations stay in [B, T, H*W, C] order; the kernel gathers the T rows of one
+//    (b, position, head) with stride H*W*ld, so no permute to [B*H*W, T, C] is ever materialised.  0.1 % of the
+//    FLOPs: CUDA cores, one warp per (position, head).
+#include "common.cuh"
+#include "igemm.h"
+
+namespace aab {
+
+constexpr int FA_THREADS = 320;       // warp0 TMA, warp1 MMA, warps 2-5 softmax tile A, warps 6-9 softmax tile B
+constexpr int FA_KV_STAGES = 3;
+constexpr int FA_TILE_BYTES = 128 * 64 * 2;   // 16 KiB: one [128 x 64] 16-bit tile
+constexpr int FA_SMEM_BYTES = 2 * FA_TILE_BYTES               /* Q A,B */
+                              + FA_KV_STAGES * 2 * FA_TILE_BYTES /* K,V ring */
+                              + 2 * 2 * FA_TILE_BYTES          /* P A,B: two 64-key halves each */
+                              + 1024 + 256;
+
+struct FaParams {
+  int Lq, Lk, heads, kv_batch_div;
+  int q_col0, k_col0, v_col0;
+  void* out;
+  long ld_out;
+  long out_batch_stride;   // elements between consecutive batches of the output
+  int out_col0;
+  float scale_log2;
+  int is_bf16;
+};
+
+__global__ void __launch_bounds__(FA_THREADS, 1)
+flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const FaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smQ = smem;                                    // [2][16K]
+  uint8_t* smK = smQ + 2 * FA_TILE_BYTES;                 // [ST][16K]
+  uint8_t* smV = smK + FA_KV_STAGES * FA_TILE_BYTES;      // [ST][16K]
+  uint8_t* smP = smV + FA_KV_STAGES * FA_TILE_BYTES;      // [2 tiles][2 halves][16K]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smP + 4 * FA_TILE_BYTES);
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* kv_full = bars + 1;            // ST
+  uint64_t* kv_empty = kv_full + FA_KV_STAGES;
+  uint64_t* s_full = kv_empty + FA_KV_STAGES;   // 2
+  uint64_t* p_ready = s_full + 2;               // 2
+  uint64_t* o_full = p_ready + 2;               // 2
+  uint64_t* o_free = o_full + 2;                // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int q0 = blockIdx.x * 256;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int bkv = b / p.kv_batch_div;
+  const int nkv = (p.Lk + 127) / 128;
+  const bool bf16 = p.is_bf16 != 0;
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      mbar_init(q_full, 1);
+      for (int i = 0; i < FA_KV_STAGES; ++i) {
+        mbar_init(&kv_full[i], 1);
+        mbar_init(&kv_empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&s_full[i], 1);
+        mbar_init(&p_ready[i], 128);
+        mbar_init(&o_full[i], 1);
+        mbar_init(&o_free[i], 128);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384)
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, 2 * FA_TILE_BYTES);
+      tma_load_3d(smQ, &tmQ, q_full, p.q_col0 + head * 64, q0, b);
+      tma_load_3d(smQ + FA_TILE_BYTES, &tmQ, q_full, p.q_col0 + head * 64, q0 + 128, b);
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j % FA_KV_STAGES;
+        const uint32_t ph = (j / FA_KV_STAGES) & 1;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], 2 * FA_TILE_BYTES);
+        tma_load_3d(smK + s * FA_TILE_BYTES, &tmK, &kv_full[s], p.k_col0 + head * 64, j * 128, bkv);
+        tma_load_3d(smV + s * FA_TILE_BYTES, &tmV, &kv_full[s], p.v_col0 + head * 64, j * 128, bkv);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc_s = make_idesc_f16(bf16 ? 1 : 0, 128, 128, 0, 0);
+    const uint32_t idesc_o = make_idesc_f16(bf16 ? 1 : 0, 128, 64, 0, 1);   // B (=V) is MN-major
+    auto issue_s = [&](int tile, int s) {
+      if (elect_one()) {
+        const uint32_t qa = smem_u32(smQ + tile * FA_TILE_BYTES);
+        const uint32_t ka = smem_u32(smK + s * FA_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(tmem_base + tile * 128, make_desc_kmajor_sw128(qa + k * 32), make_desc_kmajor_sw128(ka + k * 32),
+                      idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[tile]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int tile, int s) {
+      if (elect_one()) {
+        const uint32_t pa = smem_u32(smP + tile * 2 * FA_TILE_BYTES);
+        const uint32_t va = smem_u32(smV + s * FA_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_f16_ss(tmem_base + 256 + tile * 64,
+                      make_desc_kmajor_sw128(pa + (k >> 2) * FA_TILE_BYTES + (k & 3) * 32),
+                      make_desc_mnmajor_sw128(va + k * 2048, 8192), idesc_o, k > 0 ? 1u : 0u);
+        umma_commit(&o_full[tile]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    issue_s(0, 0);
+    issue_s(1, 0);
+    for (int j = 0; j < nkv; ++j) {
+      const int s = j % FA_KV_STAGES;
+      const uint32_t jph = j & 1;
+      const int sn = (j + 1) % FA_KV_STAGES;
+      const uint32_t phn = ((j + 1) / FA_KV_STAGES) & 1;
+#pragma unroll
+      for (int tile = 0; tile < 2; ++tile) {
+        mbar_wait(&p_ready[tile], jph);
+        if (j > 0) mbar_wait(&o_free[tile], jph ^ 1);
+        tc_fence_after();
+        issue_pv(tile, s);
+        if (tile == 1 && elect_one()) umma_commit(&kv_empty[s]);
+        __syncwarp();
+        if (j + 1 < nkv) {
+          if (tile == 0) {
+            mbar_wait(&kv_full[sn], phn);
+            tc_fence_after();
+          }
+          issue_s(tile, sn);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax warpgroups
+    const int tile = (warp - 2) >> 2;               // 0: rows q0..q0+127, 1: q0+128..
+    const int qd = warp & 3;                        // TMEM lane quarter
+    const int row = qd * 32 + lane_id();
+    const uint32_t t_s = tmem_base + tile * 128 + (static_cast<uint32_t>(qd * 32) << 16);
+    const uint32_t t_o = tmem_base + 256 + tile * 64 + (static_cast<uint32_t>(qd * 32) << 16);
+    uint8_t* prow = smP + tile * 2 * FA_TILE_BYTES + row * 128;
+    float o_acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
+    float m_run = -INFINITY;
+    float l_run = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      const uint32_t jph = j & 1;
+      mbar_wait(&s_full[tile], jph);
+      tc_fence_after();
+      const int kbase = j * 128;
+      const bool need_mask = (kbase + 128 > p.Lk);
+      // pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_s + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float v = __uint_as_float(r[i]);
+          if (need_mask && (kbase + c * 32 + i >= p.Lk)) v = -INFINITY;
+          mx = fmaxf(mx, v);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const float alpha = exp2f(m_run - m_new);
+      m_run = m_new;
+      // pass 2: probabilities -> shared memory (A operand of P.V), row sum
+      float lsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_s + c * 32, r);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float v = __uint_as_float(r[i]);
+          float e = exp2f(fmaf(v, p.scale_log2, -m_new));
+          if (need_mask && (kbase + c * 32 + i >= p.Lk)) e = 0.f;
+          pv[i] = e;
+          lsum += e;
+        }
+        uint8_t* hp = prow + (c >> 1) * FA_TILE_BYTES;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack2(pv[g * 8 + 0], pv[g * 8 + 1], bf16);
+          u.y = pack2(pv[g * 8 + 2], pv[g * 8 + 3], bf16);
+          u.z = pack2(pv[g * 8 + 4], pv[g * 8 + 5], bf16);
+          u.w = pack2(pv[g * 8 + 6], pv[g * 8 + 7], bf16);
+          const int chunk = (c & 1) * 4 + g;
+          *reinterpret_cast<uint4*>(hp + ((chunk ^ (row & 7)) << 4)) = u;
+        }
+      }
+      l_run = l_run * alpha + lsum;
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&p_ready[tile]);
+      // O_j = P_j . V_j  ->  o_acc = alpha * o_acc + O_j
+      mbar_wait(&o_full[tile], jph);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_o + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha, __uint_as_float(r[i]));
+      }
+      tc_fence_before();
+      mbar_arrive(&o_free[tile]);
+    }
+    const int q = q0 + tile * 128 + row;
+    if (q < p.Lq) {
+      const float inv = 1.0f / l_run;
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) +
+                                           (static_cast<long>(b) * p.out_batch_stride + static_cast<long>(q) * p.ld_out +
+                                            p.out_col0 + head * 64) * 2);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        uint4 u;
+        u.x = pack2(o_acc[g * 8 + 0] * inv, o_acc[g * 8 + 1] * inv, bf16);
+        u.y = pack2(o_acc[g * 8 + 2] * inv, o_acc[g * 8 + 3] * inv, bf16);
+        u.z = pack2(o_acc[g * 8 + 4] * inv, o_acc[g * 8 + 5] * inv, bf16);
+        u.w = pack2(o_acc[g * 8 + 6] * inv, o_acc[g * 8 + 7] * inv, bf16);
+        op[g] = u;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ temporal
+// q/k/v rows of frame t of (b, position pos): base + ((b*T + t)*HW + pos)*ld + col0 + head*64
+template <bool BF16>
+__global__ void __launch_bounds__(128)
+temporal_attn_d64_kernel(const void* __restrict__ qkv, long ld, int q_col0, int k_col0, int v_col0, void* __restrict__ out,
+                         long ld_out, int B, int T, int HW, int heads, float scale) {
+  __shared__ uint32_t sK[4][32][32];   // [warp][frame][channel pair], raw 16-bit pairs
+  __shared__ uint32_t sV[4][32][32];
+  const int w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long item = static_cast<long>(blockIdx.x) * 4 + w;
+  const long total = static_cast<long>(B) * HW * heads;
+  if (item >= total) return;
+  const int head = item % heads;
+  const long bp = item / heads;
+  const int pos = bp % HW;
+  const int b = bp / HW;
+  for (int t = 0; t < T; ++t) {
+    const long rowi = (static_cast<long>(b) * T + t) * HW + pos;
+    sK[w][t][lane] = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(qkv) +
+                                                        (rowi * ld + k_col0 + head * 64 + lane * 2) * 2);
+    sV[w][t][lane] = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(qkv) +
+                                                        (rowi * ld + v_col0 + head * 64 + lane * 2) * 2);
+  }
+  __syncwarp();
+  if (lane < T) {
+    const long rowi = (static_cast<long>(b) * T + lane) * HW + pos;
+    float q[64];
+    const uint4* qp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(qkv) +
+                                                     (rowi * ld + q_col0 + head * 64) * 2);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const uint4 u = qp[g];
+      const uint32_t ws[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack2(ws[e], BF16);
+        q[g * 8 + e * 2] = f.x * scale;
+        q[g * 8 + e * 2 + 1] = f.y * scale;
+      }
+    }
+    float s[32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      s[t] = -INFINITY;
+      if (t < T) {
+        float acc = 0.f;
+#pragma unroll
+        for (int d2 = 0; d2 < 32; ++d2) {
+          const float2 kf = unpack2(sK[w][t][d2], BF16);
+          acc = fmaf(q[d2 * 2], kf.x, acc);
+          acc = fmaf(q[d2 * 2 + 1], kf.y, acc);
+        }
+        s[t] = acc;
+        mx = fmaxf(mx, acc);
+      }
+    }
+    float l = 0.f;
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      s[t] = (t < T) ? __expf(s[t] - mx) : 0.f;
+      l += s[t];
+    }
+    const float inv = 1.f / l;
+    float o[64];
+#pragma unroll
+    for (int d = 0; d < 64; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      if (t < T) {
+        const float pt = s[t] * inv;
+#pragma unroll
+        for (int d2 = 0; d2 < 32; ++d2) {
+          const float2 vf = unpack2(sV[w][t][d2], BF16);
+          o[d2 * 2] = fmaf(pt, vf.x, o[d2 * 2]);
+          o[d2 * 2 + 1] = fmaf(pt, vf.y, o[d2 * 2 + 1]);
+        }
+      }
+    }
+    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out) + (rowi * ld_out + head * 64) * 2);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      uint4 u;
+      u.x = pack2(o[g * 8 + 0], o[g * 8 + 1], BF16);
+      u.y = pack2(o[g * 8 + 2], o[g * 8 + 3], BF16);
+      u.z = pack2(o[g * 8 + 4], o[g * 8 + 5], BF16);
+      u.w = pack2(o[g * 8 + 6], o[g * 8 + 7], BF16);
+      op[g] = u;
+    }
+  }
+}
+
+}  // namespace aab
+
+using namespace aab;
+
+extern "C" int aab_flash_attn_d64(const void* q, long ldq, long q_batch_stride, int q_cols, int q_col0,
+                                  const void* kv, long ldkv, long kv_batch_stride, int kv_cols, int k_col0, int v_col0,
+                                  void* out, long ld_out, long out_batch_stride, int out_col0, int nb, int nb_kv,
+                                  int kv_batch_div, int heads, int lq, int lk, float scale, int is_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!q || !kv || !out || lq < 1 || lk < 1 || heads < 1 || nb < 1 || kv_batch_div < 1) return AAB_ERR_ARG;
+  if ((ldq % 8) || (ldkv % 8) || (ld_out % 8) || (out_col0 % 8)) return AAB_ERR_ARG;
+  CUtensorMap tmQ, tmK, tmV;
+  int box[3] = {64, 128, 1};
+  {
+    long dims[3] = {q_cols, lq, nb};
+    long strides[3] = {1, ldq, q_batch_stride};
+    int r = make_tmap_16(&tmQ, q, 3, dims, strides, box, is_bf16);
+    if (r) return r;
+  }
+  {
+    long dims[3] = {kv_cols, lk, nb_kv};
+    long strides[3] = {1, ldkv, kv_batch_stride};
+    int r = make_tmap_16(&tmK, kv, 3, dims, strides, box, is_bf16);
+    if (r) return r;
+    tmV = tmK;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(flash_attn_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES) !=
+        cudaSuccess)
+      return AAB_ERR_CUDA;
+    attr_set = true;
+  }
+  FaParams p;
+  p.Lq = lq;
+  p.Lk = lk;
+  p.heads = heads;
+  p.kv_batch_div = kv_batch_div;
+  p.q_col0 = q_col0;
+  p.k_col0 = k_col0;
+  p.v_col0 = v_col0;
+  p.out = out;
+  p.ld_out = ld_out;
+  p.out_batch_stride = out_batch_stride;
+  p.out_col0 = out_col0;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.is_bf16 = is_bf16;
+  dim3 grid((lq + 255) / 256, heads, nb);
+  flash_attn_d64_kernel<<<grid, FA_THREADS, FA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
+}
+
+extern "C" int aab_temporal_attn_d64(const void* qkv, long ld, int q_col0, int k_col0, int v_col0, void* out,
+                                     long ld_out, int b, int t, int hw, int heads, float scale, int is_bf16,
+                                     void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!qkv || !out || t < 1 || t > 32 || (ld % 8) || (ld_out % 8)) return AAB_ERR_ARG;
+  const long total = static_cast<long>(b) * hw * heads;
+  const int grid = static_cast<int>((total + 3) / 4);
+  if (is_bf16)
+    temporal_attn_d64_kernel<true><<<grid, 128, 0, stream>>>(qkv, ld, q_col0, k_col0, v_col0, out, ld_out, b, t, hw,
+                                                             heads, scale);
+  else
+    temporal_attn_d64_kernel<false><<<grid, 128, 0, stream>>>(qkv, ld, q_col0, k_col0, v_col0, out, ld_out, b, t, hw,
+                                                              heads, scale);
+  return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
+}

@@ -1,0 +1,443 @@
+// Small HBM/launch-bound kernels that sit between the implicit GEMMs: layout assembly at the model boundaries
+// (reference layouts are [b, c, f, h, w]; internal layout is channels-last [b, t, h, w, c]), sinusoidal timestep
+// embedding, GEGLU (unfused fallback), nearest 2x upsample, the fused classifier-free-guidance + scheduler step, and
+// the VAE boundary ops.  Each cites the reference line it replaces.
+#include "common.cuh"
+
+namespace aab {
+
+// ------------------------------------------------------------------------------------------------
+// UNet input assembly  (models/unet_3d_condition_mask.py:376 cat(condition_latent, sample) on frames;
+// :424-427 mask repeat + cat on channels + permute to (b f) c h w).  Output [B, T, H, W, 8] 16-bit, channel order
+// (mask, c0..c3, 0, 0, 0) when mask != NULL, else (c0..c3, 0...).
+struct Strides5 { long b, c, f, y, x; };
+
+template <bool BF16>
+__global__ void unet_in_assemble_kernel(const void* __restrict__ sample, Strides5 ss, const void* __restrict__ cond,
+                                        Strides5 cs, const void* __restrict__ mask, Strides5 ms, int mask_batch,
+                                        void* __restrict__ out, int B, int T, int H, int W) {
+  const long total = static_cast<long>(B) * T * H * W;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = i % W;
+  long r = i / W;
+  const int y = r % H;
+  r /= H;
+  const int t = r % T;
+  const int b = r / T;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  int o = 0;
+  if (mask != nullptr) {
+    v[0] = load_elem(mask, (b % mask_batch) * ms.b + y * ms.y + x * ms.x, BF16);
+    o = 1;
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    v[o + c] = (t == 0) ? load_elem(cond, b * cs.b + c * cs.c + y * cs.y + x * cs.x, BF16)
+                        : load_elem(sample, b * ss.b + c * ss.c + (t - 1) * ss.f + y * ss.y + x * ss.x, BF16);
+  }
+  uint4 u;
+  u.x = pack2(v[0], v[1], BF16);
+  u.y = pack2(v[2], v[3], BF16);
+  u.z = pack2(v[4], v[5], BF16);
+  u.w = pack2(v[6], v[7], BF16);
+  reinterpret_cast<uint4*>(out)[i] = u;
+}
+
+// UNet output: conv_out result [B, T, H, W, ldc] (fp32, 4 valid channels) -> [B, 4, T-1, H, W] 16-bit, frame 0 dropped
+// (models/unet_3d_condition_mask.py:521-522).
+template <bool BF16>
+__global__ void unet_out_finalize_kernel(const float* __restrict__ y, int ldc, void* __restrict__ out, int B, int T,
+                                         int H, int W) {
+  const int F = T - 1;
+  const long total = static_cast<long>(B) * 4 * F * H * W;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = i % W;
+  long r = i / W;
+  const int yy = r % H;
+  r /= H;
+  const int f = r % F;
+  r /= F;
+  const int c = r % 4;
+  const int b = r / 4;
+  const float v = y[(((static_cast<long>(b) * T + f + 1) * H + yy) * W + x) * ldc + c];
+  store_elem(out, i, v, BF16);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sinusoidal embedding, diffusers Timesteps(num_channels, flip_sin_to_cos=True, downscale_freq_shift=0)
+// (models/unet_3d_condition_mask.py:146,156,408,415): out[b, j] = cos(t * w_j) for j < half, sin(t * w_{j-half}) after.
+template <bool BF16>
+__global__ void timestep_embed_kernel(const float* __restrict__ t, int t_count, void* __restrict__ out, int B, int dim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * dim) return;
+  const int b = i / dim;
+  const int j = i % dim;
+  const int half = dim / 2;
+  const int k = (j < half) ? j : j - half;
+  const float tv = t[t_count == 1 ? 0 : b];
+  const float freq = expf(-9.210340371976184f * static_cast<float>(k) / static_cast<float>(half));
+  const float a = tv * freq;
+  const float v = (j < half) ? cosf(a) : sinf(a);
+  store_elem(out, i, v, BF16);
+}
+
+// GEGLU fallback: out[r, j] = x[r, j] * gelu(x[r, nh + j])   (diffusers GEGLU.forward)
+template <bool BF16>
+__global__ void geglu_kernel(const void* __restrict__ x, long ldx, void* __restrict__ out, long ldo, long rows, int nh) {
+  const long total = rows * (nh / 8);
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long r = i / (nh / 8);
+  const int c = (i % (nh / 8)) * 8;
+  const uint4 a = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(x) + (r * ldx + c) * 2);
+  const uint4 g = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(x) + (r * ldx + nh + c) * 2);
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+  const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 af = unpack2(aw[e], BF16);
+    const float2 gf = unpack2(gw[e], BF16);
+    o[e] = pack2(af.x * gelu_erf_f(gf.x), af.y * gelu_erf_f(gf.y), BF16);
+  }
+  *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out) + (r * ldo + c) * 2) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// nearest-neighbour 2x upsample on channels-last [N, H, W, C] -> [N, 2H, 2W, C]  (diffusers Upsample2D, F.interpolate)
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long n, int H, int W, int V) {
+  const long total = n * 2 * H * 2 * W * V;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int v = i % V;
+  long r = i / V;
+  const int ox = r % (2 * W);
+  r /= (2 * W);
+  const int oy = r % (2 * H);
+  const long nn = r / (2 * H);
+  y[i] = __ldg(&x[((nn * H + (oy >> 1)) * W + (ox >> 1)) * V + v]);
+}
+
+// strided 16-bit copy of a [rows, cols] block (used for K/V^T staging and channel concat fallbacks)
+__global__ void copy2d_kernel(const uint16_t* __restrict__ src, long lds, uint16_t* __restrict__ dst, long ldd, long rows,
+                              int cols) {
+  const long total = rows * cols;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long r = i / cols;
+  const int c = i % cols;
+  dst[r * ldd + c] = src[r * lds + c];
+}
+
+// batched transpose: src [nb][rows][lds] (cols used) -> dst [nb][cols][rows]
+__global__ void transpose_kernel(const uint16_t* __restrict__ src, long lds, long src_batch, uint16_t* __restrict__ dst,
+                                 int rows, int cols) {
+  __shared__ uint16_t tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = src[b * src_batch + static_cast<long>(r) * lds + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[(static_cast<long>(b) * cols + c) * rows + r] = tile[threadIdx.x][j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused classifier-free guidance + scheduler step + layout shuffles (models/pipeline.py:180-192).
+//   eps  = e_u + g * (e_t - e_u)            (or e directly when no CFG)
+//   x0   = k0 * x + k1 * eps
+//   x'   = k2 * x + k3 * eps + k4 * x0 + k5 * x0_prev ;  x0_prev <- x0
+// covers DDIM (k2, k3) and DPM-Solver++(2M) (k0, k1, k2, k4, k5).  `coef` is a device table [steps][6]; the row is
+// selected by *step_idx (device) so the same captured CUDA graph serves every step.
+// eps comes straight from conv_out: fp32 [Bu, T, H, W, ldc]; latents are [n, 4, F, H, W] 16-bit.
+template <bool BF16>
+__global__ void cfg_step_kernel(const float* __restrict__ eps, int ldc, int cfg, float guidance,
+                                const void* __restrict__ x, void* __restrict__ x_out, float* __restrict__ x0_hist,
+                                const float* __restrict__ coef, const int* __restrict__ step_idx, int n, int F, int H,
+                                int W) {
+  const long total = static_cast<long>(n) * 4 * F * H * W;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float* k = coef + (step_idx ? *step_idx : 0) * 6;
+  const int xw = i % W;
+  long r = i / W;
+  const int y = r % H;
+  r /= H;
+  const int f = r % F;
+  r /= F;
+  const int c = r % 4;
+  const int b = r / 4;
+  const int T = F + 1;
+  const long pix = ((static_cast<long>(f + 1)) * H + y) * W + xw;
+  const long per_b = static_cast<long>(T) * H * W;
+  float e;
+  if (cfg) {
+    const float eu = eps[(b * per_b + pix) * ldc + c];
+    const float et = eps[((b + n) * per_b + pix) * ldc + c];
+    e = eu + guidance * (et - eu);
+  } else {
+    e = eps[(b * per_b + pix) * ldc + c];
+  }
+  const float xv = load_elem(x, i, BF16);
+  const float x0 = k[0] * xv + k[1] * e;
+  float xn = k[2] * xv + k[3] * e + k[4] * x0;
+  if (x0_hist != nullptr) {
+    xn += k[5] * x0_hist[i];
+    x0_hist[i] = x0;
+  }
+  store_elem(x_out, i, xn, BF16);
+}
+
+// ------------------------------------------------------------------------------------------------ VAE boundary ops
+// image [N, 3, H, W] (strided, 16-bit) -> channels-last [N, H, W, 8] zero padded   (AutoencoderKL.encode input)
+template <bool BF16>
+__global__ void image_to_nhwc8_kernel(const void* __restrict__ img, long sn, long sc, long sy, long sx,
+                                      void* __restrict__ out, long N, int C, int H, int W) {
+  const long total = N * H * W;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = i % W;
+  long r = i / W;
+  const int y = r % H;
+  const long nn = r / H;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = (j < C) ? load_elem(img, nn * sn + j * sc + y * sy + x * sx, BF16) : 0.f;
+  reinterpret_cast<uint4*>(out)[i] =
+      make_uint4(pack2(v[0], v[1], BF16), pack2(v[2], v[3], BF16), pack2(v[4], v[5], BF16), pack2(v[6], v[7], BF16));
+}
+
+// encoder tail: moments [N, h, w, ldm] (8 ch) -> quant_conv (1x1, 8->8) -> mean (first 4) * scale -> [B, 4, F, h, w]
+// (AutoencoderKL.encode + DiagonalGaussianDistribution.mode(); utils/common.py:16-18 multiplies by 0.18215)
+template <bool BF16>
+__global__ void vae_enc_finalize_kernel(const void* __restrict__ mom, int ldm, const float* __restrict__ wq /*[8][8]*/,
+                                        const float* __restrict__ bq, float scale, void* __restrict__ out, int B, int F,
+                                        int H, int W) {
+  const long total = static_cast<long>(B) * F * H * W;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = i % W;
+  long r = i / W;
+  const int y = r % H;
+  r /= H;
+  const int f = r % F;
+  const int b = r / F;
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = load_elem(mom, i * ldm + j, BF16);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float acc = bq[c];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(wq[c * 8 + j], m[j], acc);
+    // the reference rounds the mean to the model dtype before scaling
+    const float mean = BF16 ? __bfloat162float(__float2bfloat16_rn(acc)) : __half2float(__float2half_rn(acc));
+    store_elem(out, (((static_cast<long>(b) * 4 + c) * F + f) * H + y) * W + x, mean * scale, BF16);
+  }
+}
+
+// decoder head: latents [B, 4, F, h, w] -> z/scaling -> post_quant_conv (1x1, 4->4) -> channels-last [B*F, h, w, 8]
+// (TextToVideoSDPipeline.decode_latents + AutoencoderKL._decode)
+template <bool BF16>
+__global__ void vae_dec_in_kernel(const void* __restrict__ lat, float inv_scale, const float* __restrict__ wp /*[4][4]*/,
+                                  const float* __restrict__ bp, void* __restrict__ out, int B, int F, int H, int W) {
+  const long total = static_cast<long>(B) * F * H * W;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = i % W;
+  long r = i / W;
+  const int y = r % H;
+  r /= H;
+  const int f = r % F;
+  const int b = r / F;
+  float z[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float raw = load_elem(lat, (((static_cast<long>(b) * 4 + c) * F + f) * H + y) * W + x, BF16) * inv_scale;
+    z[c] = BF16 ? __bfloat162float(__float2bfloat16_rn(raw)) : __half2float(__float2half_rn(raw));
+  }
+  float v[8];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float acc = bp[c];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc = fmaf(wp[c * 4 + j], z[j], acc);
+    v[c] = acc;
+  }
+#pragma unroll
+  for (int c = 4; c < 8; ++c) v[c] = 0.f;
+  reinterpret_cast<uint4*>(out)[i] =
+      make_uint4(pack2(v[0], v[1], BF16), pack2(v[2], v[3], BF16), pack2(v[4], v[5], BF16), pack2(v[6], v[7], BF16));
+}
+
+// decoder tail: conv_out result [B*F, H, W, ldc] (3 valid channels, fp32) -> video [B, 3, F, H, W] float32
+// (decode_latents: reshape + permute + .float()).  The value is first rounded to the model dtype like the reference.
+template <bool BF16>
+__global__ void vae_dec_finalize_kernel(const float* __restrict__ y, int ldc, float* __restrict__ out, int B, int F,
+                                        int H, int W) {
+  const long total = static_cast<long>(B) * 3 * F * H * W;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = i % W;
+  long r = i / W;
+  const int yy = r % H;
+  r /= H;
+  const int f = r % F;
+  r /= F;
+  const int c = r % 3;
+  const int b = r / 3;
+  const float v = y[(((static_cast<long>(b) * F + f) * H + yy) * W + x) * ldc + c];
+  out[i] = BF16 ? __bfloat162float(__float2bfloat16_rn(v)) : __half2float(__float2half_rn(v));
+}
+
+// fp32 -> 16-bit convert (weights / small tensors)
+template <bool BF16>
+__global__ void cast_f32_kernel(const float* __restrict__ x, void* __restrict__ y, long n) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) store_elem(y, i, x[i], BF16);
+}
+
+}  // namespace aab
+
+using namespace aab;
+
+#define AAB_GRID(total, threads) static_cast<unsigned>(((total) + (threads)-1) / (threads))
+#define AAB_LAUNCH_RET() return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA
+
+extern "C" int aab_unet_in_assemble(const void* sample, const long* s_strides /*b,c,f,y,x*/, const void* cond,
+                                    const long* c_strides, const void* mask, const long* m_strides, int mask_batch,
+                                    void* out, int b, int t, int h, int w, int is_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!sample || !cond || !out) return AAB_ERR_ARG;
+  Strides5 ss{s_strides[0], s_strides[1], s_strides[2], s_strides[3], s_strides[4]};
+  Strides5 cs{c_strides[0], c_strides[1], c_strides[2], c_strides[3], c_strides[4]};
+  Strides5 ms{0, 0, 0, 0, 0};
+  if (mask) ms = Strides5{m_strides[0], m_strides[1], m_strides[2], m_strides[3], m_strides[4]};
+  const long total = static_cast<long>(b) * t * h * w;
+  if (is_bf16)
+    unet_in_assemble_kernel<true><<<AAB_GRID(total, 256), 256, 0, stream>>>(sample, ss, cond, cs, mask, ms,
+                                                                            mask_batch > 0 ? mask_batch : 1, out, b, t, h, w);
+  else
+    unet_in_assemble_kernel<false><<<AAB_GRID(total, 256), 256, 0, stream>>>(sample, ss, cond, cs, mask, ms,
+                                                                             mask_batch > 0 ? mask_batch : 1, out, b, t, h, w);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_unet_out_finalize(const float* y, int ldc, void* out, int b, int t, int h, int w, int is_bf16,
+                                     void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const long total = static_cast<long>(b) * 4 * (t - 1) * h * w;
+  if (is_bf16) unet_out_finalize_kernel<true><<<AAB_GRID(total, 256), 256, 0, stream>>>(y, ldc, out, b, t, h, w);
+  else unet_out_finalize_kernel<false><<<AAB_GRID(total, 256), 256, 0, stream>>>(y, ldc, out, b, t, h, w);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_timestep_embed(const float* t, int t_count, void* out, int b, int dim, int is_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!t || !out || (dim & 1)) return AAB_ERR_ARG;
+  const long total = static_cast<long>(b) * dim;
+  if (is_bf16) timestep_embed_kernel<true><<<AAB_GRID(total, 128), 128, 0, stream>>>(t, t_count, out, b, dim);
+  else timestep_embed_kernel<false><<<AAB_GRID(total, 128), 128, 0, stream>>>(t, t_count, out, b, dim);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_geglu(const void* x, long ldx, void* out, long ldo, long rows, int nh, int is_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if ((nh % 8) || (ldx % 8) || (ldo % 8)) return AAB_ERR_ARG;
+  const long total = rows * (nh / 8);
+  if (is_bf16) geglu_kernel<true><<<AAB_GRID(total, 256), 256, 0, stream>>>(x, ldx, out, ldo, rows, nh);
+  else geglu_kernel<false><<<AAB_GRID(total, 256), 256, 0, stream>>>(x, ldx, out, ldo, rows, nh);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_upsample2x(const void* x, void* y, long n, int h, int w, int c, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (c % 8) return AAB_ERR_ARG;
+  const long total = n * 2 * h * 2 * w * (c / 8);
+  upsample2x_kernel<<<AAB_GRID(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x),
+                                                               reinterpret_cast<uint4*>(y), n, h, w, c / 8);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_copy2d(const void* src, long lds, void* dst, long ldd, long rows, int cols, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const long total = rows * cols;
+  copy2d_kernel<<<AAB_GRID(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(src), lds,
+                                                          reinterpret_cast<uint16_t*>(dst), ldd, rows, cols);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_transpose(const void* src, long lds, long src_batch, void* dst, int nb, int rows, int cols,
+                             void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32, nb);
+  transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(reinterpret_cast<const uint16_t*>(src), lds, src_batch,
+                                                     reinterpret_cast<uint16_t*>(dst), rows, cols);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_cfg_scheduler_step(const float* eps, int ldc, int cfg, float guidance, const void* x, void* x_out,
+                                      float* x0_hist, const float* coef, const int* step_idx, int n, int f, int h, int w,
+                                      int is_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!eps || !x || !x_out || !coef) return AAB_ERR_ARG;
+  const long total = static_cast<long>(n) * 4 * f * h * w;
+  if (is_bf16)
+    cfg_step_kernel<true><<<AAB_GRID(total, 256), 256, 0, stream>>>(eps, ldc, cfg, guidance, x, x_out, x0_hist, coef,
+                                                                    step_idx, n, f, h, w);
+  else
+    cfg_step_kernel<false><<<AAB_GRID(total, 256), 256, 0, stream>>>(eps, ldc, cfg, guidance, x, x_out, x0_hist, coef,
+                                                                     step_idx, n, f, h, w);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_image_to_nhwc8(const void* img, long sn, long sc, long sy, long sx, void* out, long n, int c, int h,
+                                  int w, int is_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (c > 8) return AAB_ERR_ARG;
+  const long total = n * h * w;
+  if (is_bf16) image_to_nhwc8_kernel<true><<<AAB_GRID(total, 256), 256, 0, stream>>>(img, sn, sc, sy, sx, out, n, c, h, w);
+  else image_to_nhwc8_kernel<false><<<AAB_GRID(total, 256), 256, 0, stream>>>(img, sn, sc, sy, sx, out, n, c, h, w);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_vae_enc_finalize(const void* mom, int ldm, const float* wq, const float* bq, float scale, void* out,
+                                    int b, int f, int h, int w, int is_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const long total = static_cast<long>(b) * f * h * w;
+  if (is_bf16) vae_enc_finalize_kernel<true><<<AAB_GRID(total, 256), 256, 0, stream>>>(mom, ldm, wq, bq, scale, out, b, f, h, w);
+  else vae_enc_finalize_kernel<false><<<AAB_GRID(total, 256), 256, 0, stream>>>(mom, ldm, wq, bq, scale, out, b, f, h, w);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_vae_dec_in(const void* lat, float inv_scale, const float* wp, const float* bp, void* out, int b, int f,
+                              int h, int w, int is_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const long total = static_cast<long>(b) * f * h * w;
+  if (is_bf16) vae_dec_in_kernel<true><<<AAB_GRID(total, 256), 256, 0, stream>>>(lat, inv_scale, wp, bp, out, b, f, h, w);
+  else vae_dec_in_kernel<false><<<AAB_GRID(total, 256), 256, 0, stream>>>(lat, inv_scale, wp, bp, out, b, f, h, w);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_vae_dec_finalize(const float* y, int ldc, float* out, int b, int f, int h, int w, int is_bf16,
+                                    void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const long total = static_cast<long>(b) * 3 * f * h * w;
+  if (is_bf16) vae_dec_finalize_kernel<true><<<AAB_GRID(total, 256), 256, 0, stream>>>(y, ldc, out, b, f, h, w);
+  else vae_dec_finalize_kernel<false><<<AAB_GRID(total, 256), 256, 0, stream>>>(y, ldc, out, b, f, h, w);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_cast_f32(const float* x, void* y, long n, int is_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (is_bf16) cast_f32_kernel<true><<<AAB_GRID(n, 256), 256, 0, stream>>>(x, y, n);
+  else cast_f32_kernel<false><<<AAB_GRID(n, 256), 256, 0, stream>>>(x, y, n);
+  AAB_LAUNCH_RET();
+}

@@ -1,0 +1,502 @@
+// Implicit-GEMM on tcgen05 tensor cores for every dense contraction of the denoising path:
+//   Linear / 1x1 conv (1 tap), conv3x3 (9 taps over H,W), temporal conv (3,1,1) (3 taps over T),
+//   stride-2 conv (9 taps over a space-to-depth view), batched Q.K^T / P.V for the VAE attention.
+//
+//   D[pixels, N] = act( sum_taps A_tap[pixels, Kc] . B[N, tap*Kc : (tap+1)*Kc]^T + bias + bias2[sample] + residual ) * s
+//
+// * A (activations, channels-last) is never im2col'd: every tap is a TMA box load of the same 5-D tensor map at a
+//   shifted pixel coordinate; out-of-bounds pixels are zero-filled by the TMA unit (= conv zero padding).
+// * B (weights, [N, K] K-contiguous) is TMA-loaded; both land in shared memory in the 128B-swizzled K-major layout
+//   that tcgen05.mma consumes directly.  One elected thread issues tcgen05.mma (M=128, N=BN, K=16), accumulators
+//   live in TMEM (double buffered so the epilogue of tile i overlaps the main loop of tile i+1).
+// * Persistent CTAs (one per SM) walk the tile list n-fastest so that the CTAs running concurrently share the same
+//   A rows (L2 hits) while the weights stay L2-resident.
+// * Epilogue warps: tcgen05.ld -> bias / per-sample bias (time embedding) / residual / activation / GEGLU gate ->
+//   16-bit pack -> swizzled smem staging -> TMA store (hardware clips partial tiles).  A direct-store variant handles
+//   N that is not a multiple of 8 (e.g. conv_out, N=4) and fp32 outputs.
+//
+// Replaces, for the reference path: cuDNN conv2d/conv3d and cuBLAS linear calls made by
+// diffusers ResnetBlock2D / TemporalConvLayer / Transformer2DModel / TransformerTemporalModel / AutoencoderKL
+// (models/unet_3d_blocks.py:262-306,425-467,564-583,660-701,794-813).
+#include "common.cuh"
+#include "igemm.h"
+
+namespace aab {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;       // 16 KiB
+constexpr int OUT_CHUNK_BYTES = BM * 64 * 2;     // one 64-column output chunk, 16 KiB
+constexpr int NUM_THREADS = 192;                 // warp0 TMA, warp1 MMA, warps2-5 epilogue
+
+template <int BN>
+struct Cfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator stages
+  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 2 * OUT_CHUNK_BYTES + 1024 /*align*/ +
+                                    256 /*barriers*/;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == AAB_ACT_SILU) return silu_f(x);
+  if (act == AAB_ACT_GELU) return gelu_erf_f(x);
+  return x;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
+             const IgemmParams p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smA = smem;
+  uint8_t* smB = smA + STAGES * A_STAGE_BYTES;
+  uint8_t* smO = smB + STAGES * C::B_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smO + 2 * OUT_CHUNK_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const bool bf16 = (p.flags & AAB_F_BF16) != 0;
+  const bool geglu = (p.flags & AAB_F_GEGLU) != 0;
+  const bool direct = (p.flags & AAB_F_DIRECT) != 0;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int kb_per_tap = p.kb_per_tap;
+  const int k_iters = p.num_taps * kb_per_tap;
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmA2);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmD);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int i = 0; i < STAGES; ++i) {
+        mbar_init(&full_bar[i], 1);
+        mbar_init(&empty_bar[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tfull_bar[i], 1);
+        mbar_init(&tempty_bar[i], 128);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = tile % p.num_n_tiles;
+        int mt = tile / p.num_n_tiles;
+        int cb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          cb[i] = (mt % p.tiles[i]) * p.box[i];
+          mt /= p.tiles[i];
+        }
+        const int bbatch = (p.b_batch_dim >= 0) ? cb[p.b_batch_dim] : 0;
+        const int n0 = geglu ? nt * (BN / 2) : nt * BN;
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          const int o0 = p.tap_off[tap][0], o1 = p.tap_off[tap][1], o2 = p.tap_off[tap][2], o3 = p.tap_off[tap][3],
+                    o4 = p.tap_off[tap][4];
+          for (int kb = 0; kb < kb_per_tap; ++kb, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + C::B_STAGE_BYTES);
+            const int kc = kb * BK;
+            if (kc < p.Kc1)
+              tma_load_5d(smA + s * A_STAGE_BYTES, &tmA, &full_bar[s], kc + o0, cb[0] + o1, cb[1] + o2, cb[2] + o3,
+                          cb[3] + o4);
+            else
+              tma_load_5d(smA + s * A_STAGE_BYTES, &tmA2, &full_bar[s], kc - p.Kc1 + o0, cb[0] + o1, cb[1] + o2,
+                          cb[2] + o3, cb[3] + o4);
+            const int kg = tap * p.Kc + kc;
+            if (!geglu) {
+              tma_load_3d(smB + s * C::B_STAGE_BYTES, &tmB, &full_bar[s], kg, n0, bbatch);
+            } else {
+              tma_load_3d(smB + s * C::B_STAGE_BYTES, &tmB, &full_bar[s], kg, n0, bbatch);
+              tma_load_3d(smB + s * C::B_STAGE_BYTES + (BN / 2) * 128, &tmB, &full_bar[s], kg, p.N / 2 + n0, bbatch);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    const uint32_t idesc = make_idesc_f16(bf16 ? 1 : 0, BM, BN, 0, 0);
+    uint32_t it = 0;
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+      const uint32_t as = tl & 1;
+      const uint32_t aph = (tl >> 1) & 1;
+      mbar_wait(&tempty_bar[as], aph ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BN;
+      for (int ki = 0; ki < k_iters; ++ki, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smA + s * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(smB + s * C::B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = make_desc_kmajor_sw128(a_addr + k * 32);
+            const uint64_t db = make_desc_kmajor_sw128(b_addr + k * 32);
+            umma_f16_ss(tmem_d, da, db, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (ki == k_iters - 1) umma_commit(&tfull_bar[as]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
+    const int q = warp & 3;
+    const int row = q * 32 + lane_id();           // row inside the 128-row tile == TMEM lane
+    const int et = threadIdx.x - 64;              // 0..127
+    const int OUT_BN = geglu ? BN / 2 : BN;
+    uint32_t tl = 0;
+    uint32_t chunk_ctr = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+      const uint32_t as = tl & 1;
+      const uint32_t aph = (tl >> 1) & 1;
+      const int nt = tile % p.num_n_tiles;
+      int mt = tile / p.num_n_tiles;
+      int cb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        cb[i] = (mt % p.tiles[i]) * p.box[i];
+        mt /= p.tiles[i];
+      }
+      // global row of this thread
+      int rr = row;
+      long grow = 0;
+      bool rvalid = true;
+      {
+        int g[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          g[i] = cb[i] + rr % p.box[i];
+          rr /= p.box[i];
+          rvalid = rvalid && (g[i] < p.dimD[i]);
+        }
+        grow = ((static_cast<long>(g[3]) * p.dimD[2] + g[2]) * p.dimD[1] + g[1]) * p.dimD[0] + g[0];
+      }
+      const int n0 = nt * OUT_BN;
+      const float* bias2row =
+          (p.bias2 != nullptr && rvalid) ? p.bias2 + (grow / p.rows_per_bias2) * static_cast<long>(p.ld_bias2) : nullptr;
+
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
+
+      for (int c0 = 0; c0 < OUT_BN; c0 += 64, ++chunk_ctr) {
+        uint8_t* stage_buf = smO + (chunk_ctr & 1) * OUT_CHUNK_BYTES;
+        if (!direct) {
+          // the TMA store that used this staging buffer two chunks ago must have finished reading it
+          if (et == 0) tma_store_wait_read<1>();
+          named_bar_sync(1, 128);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int cc = c0 + h * 32;             // column inside the tile
+          if (cc >= OUT_BN) break;
+          const int col = n0 + cc;                // global output column
+          float v[32];
+          {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_acc + cc, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          }
+          float gte[32];
+          if (geglu) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_acc + BN / 2 + cc, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) gte[j] = __uint_as_float(r[j]);
+          }
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (col + j < p.n_out) {
+                v[j] += __ldg(p.bias + col + j);
+                if (geglu) gte[j] += __ldg(p.bias + p.N / 2 + col + j);
+              }
+            }
+          }
+          if (geglu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] * gelu_erf_f(gte[j]);
+          }
+          if (bias2row != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col + j < p.n_out) v[j] += __ldg(bias2row + col + j);
+          }
+          if (p.residual != nullptr && rvalid) {
+            const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.residual) + (grow * p.ld_res + col) * 2;
+            if (col + 32 <= p.n_out && (p.ld_res % 8) == 0) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + j4);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = unpack2(w[e], bf16);
+                  v[j4 * 8 + e * 2] += f.x;
+                  v[j4 * 8 + e * 2 + 1] += f.y;
+                }
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col + j < p.n_out) v[j] += load_elem(p.residual, grow * p.ld_res + col + j, bf16);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act) * p.out_scale;
+
+          if (!direct) {
+            // 16-bit pack into the 128B-swizzled staging tile: row r, 16-byte chunk c -> r*128 + ((c ^ (r&7))*16)
+            uint8_t* rowp = stage_buf + row * 128;
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              uint4 u;
+              u.x = pack2(v[j4 * 8 + 0], v[j4 * 8 + 1], bf16);
+              u.y = pack2(v[j4 * 8 + 2], v[j4 * 8 + 3], bf16);
+              u.z = pack2(v[j4 * 8 + 4], v[j4 * 8 + 5], bf16);
+              u.w = pack2(v[j4 * 8 + 6], v[j4 * 8 + 7], bf16);
+              const int chunk = h * 4 + j4;
+              *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row & 7)) << 4)) = u;
+            }
+          } else if (rvalid) {
+            if (p.flags & AAB_F_OUT_F32) {
+              float* op = reinterpret_cast<float*>(p.out) + grow * p.ld_out + col;
+              for (int j = 0; j < 32; ++j)
+                if (col + j < p.n_out) op[j] = v[j];
+            } else if (col + 32 <= p.n_out && (p.ld_out % 8) == 0) {
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + (grow * p.ld_out + col) * 2);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                uint4 u;
+                u.x = pack2(v[j4 * 8 + 0], v[j4 * 8 + 1], bf16);
+                u.y = pack2(v[j4 * 8 + 2], v[j4 * 8 + 3], bf16);
+                u.z = pack2(v[j4 * 8 + 4], v[j4 * 8 + 5], bf16);
+                u.w = pack2(v[j4 * 8 + 6], v[j4 * 8 + 7], bf16);
+                op[j4] = u;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col + j < p.n_out) store_elem(p.out, grow * p.ld_out + col + j, v[j], bf16);
+            }
+          }
+        }
+        if (!direct) {
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (et == 0) {
+            tma_store_5d(&tmD, stage_buf, n0 + c0, cb[0], cb[1], cb[2], cb[3]);
+            tma_store_commit();
+          }
+        }
+      }
+      // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+    }
+    if (!direct && et == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  return fn;
+}
+
+// rank-`rank` 16-bit tensor map, dims/strides innermost first (strides in elements, strides[0] must be 1)
+int make_tmap_16(CUtensorMap* out, const void* base, int rank, const long* dims, const long* strides, const int* box,
+                 int is_bf16) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return AAB_ERR_DRIVER;
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = static_cast<cuuint64_t>(dims[i]);
+    bx[i] = static_cast<cuuint32_t>(box[i]);
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = static_cast<cuuint64_t>(strides[i]) * 2;
+  }
+  CUresult r = enc(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                   static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? AAB_OK : AAB_ERR_DRIVER;
+}
+
+static int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN>
+static int launch_bn(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& d,
+                     const IgemmParams& p, int max_ctas, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e =
+        cudaFuncSetAttribute(igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
+    if (e != cudaSuccess) return AAB_ERR_CUDA;
+    attr_set = true;
+  }
+  int tiles = p.num_m_tiles * p.num_n_tiles;
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  igemm_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(a, a2, b, d, p);
+  return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
+}
+
+}  // namespace aab
+
+using namespace aab;
+
+extern "C" int aab_igemm(const AabIgemmDesc* d, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!d || !d->a || !d->b || !d->out) return AAB_ERR_ARG;
+  const int is_bf16 = (d->flags & AAB_F_BF16) ? 1 : 0;
+  const bool geglu = (d->flags & AAB_F_GEGLU) != 0;
+  int bn = d->block_n;
+  if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return AAB_ERR_ARG;
+  bool direct = (d->flags & AAB_F_DIRECT) != 0;
+  const int n_out = geglu ? d->n / 2 : d->n;
+  if (bn == 32 || (d->ld_out % 8) != 0 || (d->flags & AAB_F_OUT_F32)) direct = true;
+  if (geglu && bn < 64) return AAB_ERR_ARG;
+  if (d->num_taps < 1 || d->num_taps > AAB_MAX_TAPS) return AAB_ERR_ARG;
+  if (d->kc % 8 != 0) return AAB_ERR_ARG;
+  if (d->a2 && (d->kc1 % 64 != 0)) return AAB_ERR_ARG;
+
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  long box_prod = 1;
+  p.num_m_tiles = 1;
+  for (int i = 0; i < 4; ++i) {
+    p.dimD[i] = d->dim_d[i];
+    p.box[i] = d->box[i];
+    if (p.box[i] < 1 || p.dimD[i] < 1) return AAB_ERR_ARG;
+    p.tiles[i] = (p.dimD[i] + p.box[i] - 1) / p.box[i];
+    p.num_m_tiles *= p.tiles[i];
+    box_prod *= p.box[i];
+  }
+  if (box_prod != BM) return AAB_ERR_ARG;
+  const int out_bn = geglu ? bn / 2 : bn;
+  p.num_n_tiles = (n_out + out_bn - 1) / out_bn;
+  p.N = d->n;
+  p.n_out = n_out;
+  p.Kc = d->kc;
+  p.Kc1 = d->a2 ? d->kc1 : (1 << 30);
+  p.num_taps = d->num_taps;
+  p.kb_per_tap = (d->kc + BK - 1) / BK;
+  for (int t = 0; t < d->num_taps; ++t)
+    for (int j = 0; j < 5; ++j) p.tap_off[t][j] = d->tap_off[t][j];
+  p.b_batch_dim = d->b_batch_dim;
+  p.bias = d->bias;
+  p.bias2 = d->bias2;
+  p.rows_per_bias2 = d->rows_per_bias2 > 0 ? d->rows_per_bias2 : 1;
+  p.ld_bias2 = d->ld_bias2;
+  p.residual = d->residual;
+  p.ld_res = d->ld_res;
+  p.out = d->out;
+  p.ld_out = d->ld_out;
+  p.out_scale = d->out_scale;
+  p.act = d->act;
+  p.flags = d->flags | (direct ? AAB_F_DIRECT : 0);
+
+  CUtensorMap tmA, tmA2, tmB, tmD;
+  {
+    int box[5] = {BK, d->box[0], d->box[1], d->box[2], d->box[3]};
+    int r = make_tmap_16(&tmA, d->a, 5, d->a_dims, d->a_strides, box, is_bf16);
+    if (r) return r;
+    if (d->a2) {
+      r = make_tmap_16(&tmA2, d->a2, 5, d->a2_dims, d->a2_strides, box, is_bf16);
+      if (r) return r;
+    } else {
+      tmA2 = tmA;
+    }
+  }
+  {
+    long dims[3] = {static_cast<long>(d->num_taps) * d->kc, d->n, d->b_batch > 0 ? d->b_batch : 1};
+    long strides[3] = {1, d->ld_b, d->b_batch_stride > 0 ? d->b_batch_stride : static_cast<long>(d->n) * d->ld_b};
+    int box[3] = {BK, geglu ? bn / 2 : bn, 1};
+    int r = make_tmap_16(&tmB, d->b, 3, dims, strides, box, is_bf16);
+    if (r) return r;
+  }
+  if (!direct) {
+    // D viewed with the same pixel decomposition as the tile grid: [n_out, dimD0..3], contiguous rows of ld_out
+    long dims[5] = {n_out, d->dim_d[0], d->dim_d[1], d->dim_d[2], d->dim_d[3]};
+    long strides[5];
+    strides[0] = 1;
+    strides[1] = d->ld_out;
+    for (int i = 2; i < 5; ++i) strides[i] = strides[i - 1] * d->dim_d[i - 2];
+    int box[5] = {64, d->box[0], d->box[1], d->box[2], d->box[3]};
+    int r = make_tmap_16(&tmD, d->out, 5, dims, strides, box, is_bf16);
+    if (r) return r;
+  } else {
+    tmD = tmB;
+  }
+  switch (bn) {
+    case 32: return launch_bn<32>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
+    case 64: return launch_bn<64>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
+    case 128: return launch_bn<128>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
+    default: return launch_bn<256>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
+  }
+}
+
+extern "C" int aab_num_sms(void) { return aab::num_sms(); }

@@ -1,0 +1,261 @@
+// HBM-bound normalisation kernels on channels-last activations [samples][rows][C]:
+//   * GroupNorm statistics (fp32 partial sums per thread, fp64 atomics per (sample, group)), with the statistics
+//     extent a parameter: rows = H*W gives torch.nn.GroupNorm on [(b t), C, H, W] (ResnetBlock2D / Transformer2DModel
+//     norms), rows = T*H*W gives GroupNorm on [b, C, T, H, W] (TemporalConvLayer / TransformerTemporalModel norms,
+//     reference: diffusers resnet.TemporalConvLayer, transformer_temporal.py; call sites models/unet_3d_blocks.py:276,299).
+//   * GroupNorm apply (+ optional SiLU) writing the 16-bit operand of the following implicit GEMM; the input may be
+//     the *virtual* channel concatenation of two tensors (skip connections, models/unet_3d_blocks.py:731,828), so
+//     torch.cat is never materialised for the norm path.
+//   * LayerNorm over C (one warp per token row, exact two-pass variance in registers).
+// Algorithmic bytes: stats = 1 read of the activation; apply = 1 read + 1 write; layernorm = 1 read + 1 write.
+#include "common.cuh"
+
+namespace aab {
+
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// thread mapping shared by stats/apply: V = C/8 channel octets per row; blockDim = V * rpi (rows per iteration)
+struct GnArgs {
+  const void* x1;
+  const void* x2;     // optional second source (channels C1..C)
+  int C1, C2;         // C = C1 + C2
+  long ld1, ld2;      // row strides (elements)
+  long rows;          // rows per sample (statistics extent)
+  int groups;
+  int rows_per_cta;
+  int bf16;
+};
+
+__global__ void gn_stats_kernel(GnArgs a, double* __restrict__ stats /* [S][G][2] */) {
+  extern __shared__ float sh[];   // [2*groups]
+  const int C = a.C1 + a.C2;
+  const int V = C >> 3;
+  const int oct = threadIdx.x % V;
+  const int rsub = threadIdx.x / V;
+  const int rpi = blockDim.x / V;
+  const int s = blockIdx.y;
+  const long r0 = static_cast<long>(blockIdx.x) * a.rows_per_cta;
+  long r1 = r0 + a.rows_per_cta;
+  if (r1 > a.rows) r1 = a.rows;
+  for (int i = threadIdx.x; i < 2 * a.groups; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  float sum[8], sq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
+  const bool bf = a.bf16 != 0;
+  const int c0 = oct * 8;
+  const uint8_t* base;
+  long ld;
+  int cc;
+  if (c0 < a.C1) { base = reinterpret_cast<const uint8_t*>(a.x1); ld = a.ld1; cc = c0; }
+  else { base = reinterpret_cast<const uint8_t*>(a.x2); ld = a.ld2; cc = c0 - a.C1; }
+  for (long r = r0 + rsub; r < r1; r += rpi) {
+    const long row = static_cast<long>(s) * a.rows + r;
+    const uint4 u = ldg16(base + (row * ld + cc) * 2);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack2(w[e], bf);
+      sum[2 * e] += f.x; sq[2 * e] += f.x * f.x;
+      sum[2 * e + 1] += f.y; sq[2 * e + 1] += f.y * f.y;
+    }
+  }
+  const int cpg = C / a.groups;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c0 + j) / cpg;
+    atomicAdd(&sh[2 * g], sum[j]);
+    atomicAdd(&sh[2 * g + 1], sq[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * a.groups; i += blockDim.x)
+    atomicAdd(&stats[static_cast<long>(s) * 2 * a.groups + i], static_cast<double>(sh[i]));
+}
+
+__global__ void gn_apply_kernel(GnArgs a, const double* __restrict__ stats, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float eps, int silu, void* __restrict__ y, long ldy) {
+  const int C = a.C1 + a.C2;
+  const int V = C >> 3;
+  const int oct = threadIdx.x % V;
+  const int rsub = threadIdx.x / V;
+  const int rpi = blockDim.x / V;
+  const int s = blockIdx.y;
+  const long r0 = static_cast<long>(blockIdx.x) * a.rows_per_cta;
+  long r1 = r0 + a.rows_per_cta;
+  if (r1 > a.rows) r1 = a.rows;
+  const bool bf = a.bf16 != 0;
+  const int c0 = oct * 8;
+  const int cpg = C / a.groups;
+  const double n = static_cast<double>(a.rows) * cpg;
+  float sc[8], sf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c0 + j) / cpg;
+    const double m = stats[(static_cast<long>(s) * a.groups + g) * 2] / n;
+    double var = stats[(static_cast<long>(s) * a.groups + g) * 2 + 1] / n - m * m;
+    if (var < 0) var = 0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float gm = gamma[c0 + j];
+    sc[j] = rstd * gm;
+    sf[j] = beta[c0 + j] - static_cast<float>(m) * rstd * gm;
+  }
+  const uint8_t* base;
+  long ld;
+  int cc;
+  if (c0 < a.C1) { base = reinterpret_cast<const uint8_t*>(a.x1); ld = a.ld1; cc = c0; }
+  else { base = reinterpret_cast<const uint8_t*>(a.x2); ld = a.ld2; cc = c0 - a.C1; }
+  for (long r = r0 + rsub; r < r1; r += rpi) {
+    const long row = static_cast<long>(s) * a.rows + r;
+    const uint4 u = ldg16(base + (row * ld + cc) * 2);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack2(w[e], bf);
+      float v0 = fmaf(f.x, sc[2 * e], sf[2 * e]);
+      float v1 = fmaf(f.y, sc[2 * e + 1], sf[2 * e + 1]);
+      if (silu) { v0 = silu_f(v0); v1 = silu_f(v1); }
+      o[e] = pack2(v0, v1, bf);
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y) + (row * ldy + c0) * 2) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// one warp per row; C % 8 == 0, C <= 2048
+__global__ void layernorm_kernel(const void* __restrict__ x, long ldx, void* __restrict__ y, long ldy,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, long rows, int C,
+                                 float eps, int bf16) {
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const bool bf = bf16 != 0;
+  const int V = C >> 3;
+  float v[8][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int o = lane + i * 32;
+    if (o < V) {
+      const uint4 u = ldg16(reinterpret_cast<const uint8_t*>(x) + (row * ldx + o * 8) * 2);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack2(w[e], bf);
+        v[i][2 * e] = f.x; v[i][2 * e + 1] = f.y;
+        sum += f.x + f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  const float mean = sum / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int o = lane + i * 32;
+    if (o < V) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; sq += d * d; }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+  const float rstd = rsqrtf(sq / C + eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int o = lane + i * 32;
+    if (o < V) {
+      uint32_t ow[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = o * 8 + 2 * e;
+        const float a0 = (v[i][2 * e] - mean) * rstd * gamma[c] + beta[c];
+        const float a1 = (v[i][2 * e + 1] - mean) * rstd * gamma[c + 1] + beta[c + 1];
+        ow[e] = pack2(a0, a1, bf);
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y) + (row * ldy + o * 8) * 2) =
+          make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+  }
+}
+
+// row softmax: fp32 scores [rows][L] -> 16-bit probabilities (VAE mid-block attention, upcast_softmax semantics)
+__global__ void softmax_rows_kernel(const float* __restrict__ s, long lds, void* __restrict__ p, long ldp, int L,
+                                    int bf16) {
+  __shared__ float red[32];
+  const long row = blockIdx.x;
+  const float* sr = s + row * lds;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) mx = fmaxf(mx, sr[i]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < (blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) sum += __expf(sr[i] - mx);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) sum += red[i];
+  const float inv = 1.f / sum;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) store_elem(p, row * ldp + i, __expf(sr[i] - mx) * inv, bf16 != 0);
+}
+
+}  // namespace aab
+
+using namespace aab;
+
+static int gn_launch_cfg(int C, int* threads, int* rows_per_cta) {
+  if (C % 8) return AAB_ERR_ARG;
+  const int V = C / 8;
+  if (V > 1024) return AAB_ERR_ARG;
+  int rpi = 256 / V;
+  if (rpi < 1) rpi = 1;
+  *threads = V * rpi;
+  *rows_per_cta = rpi * 16;
+  return AAB_OK;
+}
+
+// stats must hold samples*groups*2 doubles; it is zeroed here.
+extern "C" int aab_groupnorm(const void* x1, long ld1, int c1, const void* x2, long ld2, int c2, long samples, long rows,
+                             int groups, const float* gamma, const float* beta, float eps, int silu, void* y, long ldy,
+                             double* stats, int is_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int C = c1 + c2;
+  if (!x1 || !y || !stats || groups < 1 || C % groups || (c1 % 8) || (c2 % 8) || (ld1 % 8) || (ldy % 8)) return AAB_ERR_ARG;
+  if (c2 > 0 && (!x2 || (ld2 % 8))) return AAB_ERR_ARG;
+  int threads, rpc;
+  int r = gn_launch_cfg(C, &threads, &rpc);
+  if (r) return r;
+  GnArgs a;
+  a.x1 = x1; a.x2 = x2; a.C1 = c1; a.C2 = c2; a.ld1 = ld1; a.ld2 = ld2; a.rows = rows; a.groups = groups;
+  a.rows_per_cta = rpc; a.bf16 = is_bf16;
+  if (cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * samples, stream) != cudaSuccess) return AAB_ERR_CUDA;
+  dim3 grid(static_cast<unsigned>((rows + rpc - 1) / rpc), static_cast<unsigned>(samples));
+  gn_stats_kernel<<<grid, threads, 2 * groups * sizeof(float), stream>>>(a, stats);
+  gn_apply_kernel<<<grid, threads, 0, stream>>>(a, stats, gamma, beta, eps, silu, y, ldy);
+  return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
+}
+
+extern "C" int aab_layernorm(const void* x, long ldx, void* y, long ldy, const float* gamma, const float* beta,
+                             long rows, int c, float eps, int is_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !y || (c % 8) || c > 2048 || (ldx % 8) || (ldy % 8)) return AAB_ERR_ARG;
+  const int wpb = 8;
+  layernorm_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(x, ldx, y, ldy, gamma, beta,
+                                                                                         rows, c, eps, is_bf16);
+  return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
+}
+
+extern "C" int aab_softmax_rows(const float* s, long lds, void* p, long ldp, long rows, int l, int is_bf16,
+                                void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!s || !p) return AAB_ERR_ARG;
+  softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(s, lds, p, ldp, l, is_bf16);
+  return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
+}

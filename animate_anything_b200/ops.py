@@ -1,0 +1,393 @@
+"""Tensor-level wrappers over the C-ABI (`_lib.call`).  Activations are channels-last 16-bit torch tensors; torch only
+provides memory and the current stream.  Every function here launches hand-written sm_100a kernels — nothing falls back
+to torch compute.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, ACT_SILU, F_BF16, F_DIRECT, F_GEGLU, F_OUT_F32, IgemmDesc
+
+NUM_SMS = 148
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _is_bf16(t: torch.Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return 1
+    if t.dtype == torch.float16:
+        return 0
+    raise TypeError(f"16-bit activations required, got {t.dtype}")
+
+
+def _np2(x: int) -> int:
+    return 1 << max(0, (int(x) - 1).bit_length())
+
+
+def pick_box(dims: Sequence[int], fixed_one: Sequence[int] = ()) -> list:
+    """Pixels-per-tile along each (innermost-first) output dim; powers of two with product 128."""
+    box = [1, 1, 1, 1]
+    rem = 128
+    for i, d in enumerate(dims):
+        if i in fixed_one:
+            continue
+        b = min(rem, _np2(d))
+        box[i] = b
+        rem //= b
+        if rem == 1:
+            break
+    if rem > 1:
+        for i in range(4):
+            if i not in fixed_one:
+                box[i] *= rem
+                break
+    return box
+
+
+def pick_block_n(n_out: int, m_tiles: int, geglu: bool = False) -> int:
+    cands = [256, 128, 64]
+    best = None
+    for bn in cands:
+        obn = bn // 2 if geglu else bn
+        if obn > 2 * _np2(n_out) and bn > 64:
+            continue
+        n_tiles = -(-n_out // obn)
+        waste = n_tiles * obn / n_out
+        if best is None:
+            best = (bn, n_tiles, waste)
+        if m_tiles * n_tiles >= NUM_SMS and waste <= 1.25:
+            return bn
+    # nothing fills the machine / low waste: take the candidate with least padding, preferring larger tiles
+    scored = []
+    for bn in cands:
+        obn = bn // 2 if geglu else bn
+        n_tiles = -(-n_out // obn)
+        scored.append((n_tiles * obn / n_out + (0.0 if m_tiles * n_tiles >= NUM_SMS else 0.3), -bn, bn))
+    scored.sort()
+    return scored[0][2]
+
+
+def _fix_strides(dims, strides):
+    """TMA wants non-zero, 16-byte-multiple strides even for extent-1 dims."""
+    st = list(strides)
+    for i in range(1, 5):
+        if st[i] == 0:
+            st[i] = st[i - 1] * max(1, dims[i - 1])
+    return st
+
+
+def igemm(a: torch.Tensor, a_dims, a_strides, w: torch.Tensor, n: int, kc: int, dim_d, box, taps,
+          out: Optional[torch.Tensor] = None, ld_out: Optional[int] = None, *, bias=None, bias2=None, rows_per_bias2=1,
+          residual=None, ld_res=None, act=ACT_NONE, out_scale=1.0, geglu=False, out_f32=False, a2=None, a2_dims=None,
+          a2_strides=None, kc1=0, ld_b=None, b_batch=0, b_batch_stride=0, b_batch_dim=-1, block_n=None, direct=False,
+          max_ctas=0, out_rows=None):
+    """Generic launch of the implicit-GEMM kernel. `taps` is a list of 5-int offsets (channel, pix0..pix3)."""
+    bf = _is_bf16(a)
+    n_out = n // 2 if geglu else n
+    rows = 1
+    for d in dim_d:
+        rows *= d
+    if out is None:
+        out = torch.empty((rows if out_rows is None else out_rows, n_out), device=a.device,
+                          dtype=torch.float32 if out_f32 else a.dtype)
+    if ld_out is None:
+        ld_out = out.stride(-2) if out.dim() >= 2 else n_out
+    d = IgemmDesc()
+    d.a = a.data_ptr()
+    a_strides = _fix_strides(a_dims, a_strides)
+    for i in range(5):
+        d.a_dims[i] = a_dims[i]
+        d.a_strides[i] = a_strides[i]
+    if a2 is not None:
+        d.a2 = a2.data_ptr()
+        a2_strides = _fix_strides(a2_dims, a2_strides)
+        for i in range(5):
+            d.a2_dims[i] = a2_dims[i]
+            d.a2_strides[i] = a2_strides[i]
+        d.kc1 = kc1
+    else:
+        d.a2 = None
+    d.kc = kc
+    d.num_taps = len(taps)
+    for t, off in enumerate(taps):
+        for j in range(5):
+            d.tap_off[t][j] = off[j]
+    d.b = w.data_ptr()
+    d.ld_b = ld_b if ld_b is not None else w.stride(-2)
+    d.b_batch = b_batch
+    d.b_batch_stride = b_batch_stride
+    d.b_batch_dim = b_batch_dim
+    d.n = n
+    m_tiles = 1
+    for i in range(4):
+        d.dim_d[i] = dim_d[i]
+        d.box[i] = box[i]
+        m_tiles *= -(-dim_d[i] // box[i])
+    d.out = out.data_ptr()
+    d.ld_out = ld_out
+    d.bias = None if bias is None else bias.data_ptr()
+    if bias is not None:
+        assert bias.dtype == torch.float32
+    if bias2 is not None:
+        assert bias2.dtype == torch.float32
+        d.bias2 = bias2.data_ptr()
+        d.rows_per_bias2 = rows_per_bias2
+        d.ld_bias2 = bias2.stride(0)
+    else:
+        d.bias2 = None
+        d.rows_per_bias2 = 1
+    if residual is not None:
+        d.residual = residual.data_ptr()
+        d.ld_res = ld_res if ld_res is not None else residual.stride(-2)
+    else:
+        d.residual = None
+    d.out_scale = out_scale
+    d.act = act
+    flags = (F_BF16 if bf else 0) | (F_GEGLU if geglu else 0) | (F_OUT_F32 if out_f32 else 0) | (F_DIRECT if direct else 0)
+    d.flags = flags
+    if block_n is None:
+        if n_out < 64 and not geglu:
+            block_n = 32 if n_out <= 32 else 64
+        else:
+            block_n = pick_block_n(n_out, m_tiles, geglu)
+    d.block_n = block_n
+    d.max_ctas = max_ctas
+    _lib.call("aab_igemm", C.byref(d), _stream())
+    return out
+
+
+_NO_TAP = [[0, 0, 0, 0, 0]]
+TAPS_3X3 = [[0, s - 1, r - 1, 0, 0] for r in range(3) for s in range(3)]
+TAPS_T3 = [[0, 0, dt - 1, 0, 0] for dt in range(3)]
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias=None, **kw) -> torch.Tensor:
+    """x [M, K] (row stride arbitrary, multiple of 8) @ w[N, K]^T."""
+    m, k = x.shape
+    n = w.shape[0]
+    return igemm(x, (k, m, 1, 1, 1), (1, x.stride(0), 0, 0, 0), w, n, k, (m, 1, 1, 1), (128, 1, 1, 1), _NO_TAP,
+                 bias=bias, **kw)
+
+
+def conv3x3(x: torch.Tensor, w: torch.Tensor, bias=None, x2: Optional[torch.Tensor] = None, **kw) -> torch.Tensor:
+    """x [N, H, W, C] channels-last (optionally virtually concatenated with x2 on channels), w [Cout, 9*(C+C2)]
+    tap-major (r, s, c).  stride 1, zero padding 1.  Returns [N*H*W, Cout]."""
+    nb, h, wd, c = x.shape
+    dims = (c, wd, h, nb, 1)
+    strides = (1, c, wd * c, h * wd * c, nb * h * wd * c)
+    dim_d = (wd, h, nb, 1)
+    box = pick_box(dim_d)
+    if x2 is not None:
+        c2 = x2.shape[-1]
+        return igemm(x, dims, strides, w, w.shape[0], c + c2, dim_d, box, TAPS_3X3, bias=bias, a2=x2,
+                     a2_dims=(c2, wd, h, nb, 1), a2_strides=(1, c2, wd * c2, h * wd * c2, nb * h * wd * c2), kc1=c, **kw)
+    return igemm(x, dims, strides, w, w.shape[0], c, dim_d, box, TAPS_3X3, bias=bias, **kw)
+
+
+def conv1x1_cat(x: torch.Tensor, x2: Optional[torch.Tensor], w: torch.Tensor, bias=None, **kw) -> torch.Tensor:
+    """1x1 conv / linear over the virtual channel concat of x [M, C1] and x2 [M, C2]."""
+    m, c = x.shape
+    if x2 is None:
+        return linear(x, w, bias, **kw)
+    c2 = x2.shape[1]
+    return igemm(x, (c, m, 1, 1, 1), (1, x.stride(0), 0, 0, 0), w, w.shape[0], c + c2, (m, 1, 1, 1), (128, 1, 1, 1),
+                 _NO_TAP, bias=bias, a2=x2, a2_dims=(c2, m, 1, 1, 1), a2_strides=(1, x2.stride(0), 0, 0, 0), kc1=c, **kw)
+
+
+def conv3x3_stride2(x: torch.Tensor, w: torch.Tensor, bias=None, pad_mode: str = "sym", **kw) -> torch.Tensor:
+    """3x3 stride-2 conv on x [N, H, W, C] (H, W even) through a space-to-depth view (no gather kernel).
+    pad_mode "sym": padding 1 (UNet Downsample2D); "br": F.pad(0,1,0,1) + padding 0 (VAE encoder Downsample2D)."""
+    nb, h, wd, c = x.shape
+    assert h % 2 == 0 and wd % 2 == 0 and c % 64 == 0
+    h2, w2 = h // 2, wd // 2
+    dims = (2 * c, w2, 2, h2, nb)
+    strides = (1, 2 * c, wd * c, 2 * wd * c, h * wd * c)
+    dim_d = (w2, 1, h2, nb)
+    box = pick_box(dim_d, fixed_one=(1,))
+    if pad_mode == "sym":
+        m = {0: (1, -1), 1: (0, 0), 2: (1, 0)}      # kernel index -> (parity, coarse offset)
+    else:
+        m = {0: (0, 0), 1: (1, 0), 2: (0, 1)}
+    taps = []
+    for r in range(3):
+        hp, dh = m[r]
+        for s in range(3):
+            wp, dw = m[s]
+            taps.append([wp * c, dw, hp, dh, 0])
+    return igemm(x, dims, strides, w, w.shape[0], c, dim_d, box, taps, bias=bias, **kw)
+
+
+def tconv3(x: torch.Tensor, b: int, t: int, hw: int, w: torch.Tensor, bias=None, **kw) -> torch.Tensor:
+    """Conv3d kernel (3,1,1), padding (1,0,0) on x [B*T*HW, C] in (b, t, hw) row order; w [Cout, 3*C] tap-major."""
+    c = x.shape[-1]
+    dims = (c, hw, t, b, 1)
+    strides = (1, c, hw * c, t * hw * c, b * t * hw * c)
+    dim_d = (hw, t, b, 1)
+    box = pick_box(dim_d)
+    return igemm(x, dims, strides, w, w.shape[0], c, dim_d, box, TAPS_T3, bias=bias, **kw)
+
+
+# ---------------------------------------------------------------------------------------------- attention
+def flash_attn_d64(q: torch.Tensor, q_col0: int, kv: torch.Tensor, k_col0: int, v_col0: int, nb: int, lq: int, lk: int,
+                   heads: int, kv_batch_div: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q: [nb*lq, q_cols]; kv: [nb_kv*lk, kv_cols]; head h uses columns col0 + 64*h.  Returns [nb*lq, heads*64]."""
+    bf = _is_bf16(q)
+    if out is None:
+        out = torch.empty((nb * lq, heads * 64), device=q.device, dtype=q.dtype)
+    nb_kv = kv.shape[0] // lk
+    _lib.call("aab_flash_attn_d64", _ptr(q), q.stride(0), lq * q.stride(0), q.shape[1], q_col0,
+              _ptr(kv), kv.stride(0), lk * kv.stride(0), kv.shape[1], k_col0, v_col0,
+              _ptr(out), out.stride(0), lq * out.stride(0), 0, nb, nb_kv, kv_batch_div, heads, lq, lk,
+              1.0 / math.sqrt(64.0), bf, _stream())
+    return out
+
+
+def temporal_attn_d64(qkv: torch.Tensor, b: int, t: int, hw: int, heads: int, q_col0: int, k_col0: int, v_col0: int):
+    bf = _is_bf16(qkv)
+    out = torch.empty((qkv.shape[0], heads * 64), device=qkv.device, dtype=qkv.dtype)
+    _lib.call("aab_temporal_attn_d64", _ptr(qkv), qkv.stride(0), q_col0, k_col0, v_col0, _ptr(out), out.stride(0), b, t,
+              hw, heads, 1.0 / math.sqrt(64.0), bf, _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- norms
+_stats_cache = {}
+
+
+def _stats_buf(device, n):
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    buf = _stats_cache.get(key)
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(n, 4096), device=device, dtype=torch.float64)
+        _stats_cache[key] = buf
+    return buf
+
+
+def groupnorm(x: torch.Tensor, samples: int, rows: int, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+              silu: bool, groups: int = 32, x2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [samples*rows, C] (+ optional x2 [.., C2] virtual concat).  Statistics per (sample, group) over rows x C/groups."""
+    bf = _is_bf16(x)
+    c1 = x.shape[1]
+    c2 = 0 if x2 is None else x2.shape[1]
+    y = torch.empty((x.shape[0], c1 + c2), device=x.device, dtype=x.dtype)
+    stats = _stats_buf(x.device, samples * groups * 2)
+    _lib.call("aab_groupnorm", _ptr(x), x.stride(0), c1, _ptr(x2), 0 if x2 is None else x2.stride(0), c2, samples, rows,
+              groups, _ptr(gamma), _ptr(beta), eps, int(silu), _ptr(y), y.stride(0), _ptr(stats), bf, _stream())
+    return y
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    bf = _is_bf16(x)
+    y = torch.empty_like(x)
+    _lib.call("aab_layernorm", _ptr(x), x.stride(0), _ptr(y), y.stride(0), _ptr(gamma), _ptr(beta), x.shape[0], x.shape[1],
+              eps, bf, _stream())
+    return y
+
+
+def softmax_rows(s: torch.Tensor, dtype) -> torch.Tensor:
+    p = torch.empty(s.shape, device=s.device, dtype=dtype)
+    _lib.call("aab_softmax_rows", _ptr(s), s.stride(0), _ptr(p), p.stride(0), s.shape[0], s.shape[1],
+              1 if dtype == torch.bfloat16 else 0, _stream())
+    return p
+
+
+# ---------------------------------------------------------------------------------------------- elementwise
+def _strides5(t: torch.Tensor):
+    arr = (C.c_long * 5)(*t.stride())
+    return arr
+
+
+def unet_in_assemble(sample, cond, mask, t_frames) -> torch.Tensor:
+    """sample [B,4,F,h,w], cond [B,4,1,h,w], mask [Bm,1,1,h,w] or None -> [B, T, h, w, 8]."""
+    bf = _is_bf16(sample)
+    b, _, f, h, w = sample.shape
+    out = torch.empty((b, f + 1, h, w, 8), device=sample.device, dtype=sample.dtype)
+    ms = _strides5(mask) if mask is not None else None
+    _lib.call("aab_unet_in_assemble", _ptr(sample), _strides5(sample), _ptr(cond), _strides5(cond), _ptr(mask), ms,
+              0 if mask is None else mask.shape[0], _ptr(out), b, f + 1, h, w, bf, _stream())
+    return out
+
+
+def unet_out_finalize(y: torch.Tensor, b, t, h, w, dtype) -> torch.Tensor:
+    out = torch.empty((b, 4, t - 1, h, w), device=y.device, dtype=dtype)
+    _lib.call("aab_unet_out_finalize", _ptr(y), y.stride(0), _ptr(out), b, t, h, w, 1 if dtype == torch.bfloat16 else 0,
+              _stream())
+    return out
+
+
+def timestep_embed(t: torch.Tensor, b: int, dim: int, dtype) -> torch.Tensor:
+    assert t.dtype == torch.float32 and t.is_cuda
+    out = torch.empty((b, dim), device=t.device, dtype=dtype)
+    _lib.call("aab_timestep_embed", _ptr(t), t.numel(), _ptr(out), b, dim, 1 if dtype == torch.bfloat16 else 0, _stream())
+    return out
+
+
+def geglu(x: torch.Tensor) -> torch.Tensor:
+    nh = x.shape[1] // 2
+    out = torch.empty((x.shape[0], nh), device=x.device, dtype=x.dtype)
+    _lib.call("aab_geglu", _ptr(x), x.stride(0), _ptr(out), out.stride(0), x.shape[0], nh, _is_bf16(x), _stream())
+    return out
+
+
+def upsample2x(x: torch.Tensor) -> torch.Tensor:
+    n, h, w, c = x.shape
+    y = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=x.dtype)
+    _lib.call("aab_upsample2x", _ptr(x), _ptr(y), n, h, w, c, _stream())
+    return y
+
+
+def transpose_batched(src: torch.Tensor, col0: int, nb: int, rows: int, cols: int) -> torch.Tensor:
+    """src [nb*rows, ld] -> dst [nb, cols, rows] taking columns col0..col0+cols."""
+    dst = torch.empty((nb, cols, rows), device=src.device, dtype=src.dtype)
+    base = C.c_void_p(src.data_ptr() + col0 * 2)
+    _lib.call("aab_transpose", base, src.stride(0), rows * src.stride(0), _ptr(dst), nb, rows, cols, _stream())
+    return dst
+
+
+def cfg_scheduler_step(eps: torch.Tensor, ldc: int, cfg: bool, guidance: float, x: torch.Tensor, x_out: torch.Tensor,
+                       x0_hist: Optional[torch.Tensor], coef: torch.Tensor, step_idx: Optional[torch.Tensor]):
+    n, _, f, h, w = x.shape
+    _lib.call("aab_cfg_scheduler_step", _ptr(eps), ldc, int(cfg), float(guidance), _ptr(x), _ptr(x_out), _ptr(x0_hist),
+              _ptr(coef), _ptr(step_idx), n, f, h, w, _is_bf16(x), _stream())
+    return x_out
+
+
+def image_to_nhwc8(img: torch.Tensor) -> torch.Tensor:
+    n, c, h, w = img.shape
+    out = torch.empty((n, h, w, 8), device=img.device, dtype=img.dtype)
+    _lib.call("aab_image_to_nhwc8", _ptr(img), img.stride(0), img.stride(1), img.stride(2), img.stride(3), _ptr(out), n, c,
+              h, w, _is_bf16(img), _stream())
+    return out
+
+
+def vae_enc_finalize(mom: torch.Tensor, wq, bq, scale, b, f, h, w) -> torch.Tensor:
+    out = torch.empty((b, 4, f, h, w), device=mom.device, dtype=mom.dtype)
+    _lib.call("aab_vae_enc_finalize", _ptr(mom), mom.stride(0), _ptr(wq), _ptr(bq), float(scale), _ptr(out), b, f, h, w,
+              _is_bf16(mom), _stream())
+    return out
+
+
+def vae_dec_in(lat: torch.Tensor, inv_scale, wp, bp) -> torch.Tensor:
+    b, _, f, h, w = lat.shape
+    out = torch.empty((b * f, h, w, 8), device=lat.device, dtype=lat.dtype)
+    _lib.call("aab_vae_dec_in", _ptr(lat), float(inv_scale), _ptr(wp), _ptr(bp), _ptr(out), b, f, h, w, _is_bf16(lat),
+              _stream())
+    return out
+
+
+def vae_dec_finalize(y: torch.Tensor, b, f, h, w, bf16: bool) -> torch.Tensor:
+    out = torch.empty((b, 3, f, h, w), device=y.device, dtype=torch.float32)
+    _lib.call("aab_vae_dec_finalize", _ptr(y), y.stride(0), _ptr(out), b, f, h, w, int(bf16), _stream())
+    return out

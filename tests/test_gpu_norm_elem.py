@@ -1,0 +1,155 @@
+"""GPU parity of the normalisation / elementwise / boundary kernels vs plain PyTorch fp32."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import check
+
+pytestmark = pytest.mark.gpu
+TOL = {torch.float16: (1e-3, 1e-3), torch.bfloat16: (8e-3, 8e-3)}
+
+
+def _rand(shape, dtype, scale=1.0, seed=0, shift=0.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, device="cuda", generator=g) * scale + shift).to(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("samples,rows,c,silu", [(4, 256, 320, True), (2, 17 * 64, 640, False), (3, 100, 1280, True),
+                                                 (2, 4096, 128, True), (1, 64, 1920, True)])
+def test_groupnorm(dtype, samples, rows, c, silu):
+    from animate_anything_b200 import ops
+    x = _rand((samples * rows, c), dtype, 1.5, 1, shift=0.3)
+    gamma = _rand((c,), torch.float32, 0.2, 2, shift=1.0)
+    beta = _rand((c,), torch.float32, 0.2, 3)
+    y = ops.groupnorm(x, samples, rows, gamma, beta, 1e-5, silu)
+    xr = x.float().reshape(samples, rows, c).permute(0, 2, 1)
+    ref = F.group_norm(xr, 32, gamma, beta, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1).reshape(samples * rows, c)
+    check(f"groupnorm s{samples} r{rows} c{c} {dtype}", y, ref, *TOL[dtype])
+
+
+def test_groupnorm_concat():
+    from animate_anything_b200 import ops
+    dtype = torch.float16
+    samples, rows, c1, c2 = 3, 256, 1280, 640
+    x1 = _rand((samples * rows, c1), dtype, 1.0, 1)
+    x2 = _rand((samples * rows, c2), dtype, 2.0, 2, shift=-0.5)
+    gamma = _rand((c1 + c2,), torch.float32, 0.2, 3, shift=1.0)
+    beta = _rand((c1 + c2,), torch.float32, 0.2, 4)
+    y = ops.groupnorm(x1, samples, rows, gamma, beta, 1e-5, True, x2=x2)
+    xc = torch.cat([x1, x2], dim=1).float().reshape(samples, rows, c1 + c2).permute(0, 2, 1)
+    ref = F.silu(F.group_norm(xc, 32, gamma, beta, 1e-5)).permute(0, 2, 1).reshape(samples * rows, c1 + c2)
+    check("groupnorm virtual concat 1280+640", y, ref, *TOL[dtype])
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("rows,c", [(1000, 320), (77, 1280), (4096, 512), (10, 640)])
+def test_layernorm(dtype, rows, c):
+    from animate_anything_b200 import ops
+    x = _rand((rows, c), dtype, 2.0, 1, shift=0.5)
+    gamma = _rand((c,), torch.float32, 0.2, 2, shift=1.0)
+    beta = _rand((c,), torch.float32, 0.2, 3)
+    y = ops.layernorm(x, gamma, beta, 1e-5)
+    ref = F.layer_norm(x.float(), (c,), gamma, beta, 1e-5)
+    check(f"layernorm {rows}x{c} {dtype}", y, ref, *TOL[dtype])
+
+
+def test_softmax_rows_and_transpose():
+    from animate_anything_b200 import ops
+    s = _rand((300, 1000), torch.float32, 3.0, 1)
+    p = ops.softmax_rows(s, torch.float16)
+    check("softmax rows", p, torch.softmax(s, dim=-1), 1e-3, 1e-5)
+    src = _rand((3 * 100, 96), torch.float16, 1.0, 2)
+    dst = ops.transpose_batched(src, 32, 3, 100, 64)
+    ref = src[:, 32:96].reshape(3, 100, 64).permute(0, 2, 1)
+    assert torch.equal(dst, ref.contiguous())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_unet_boundary_kernels(dtype):
+    from animate_anything_b200 import ops
+    b, f, h, w = 2, 5, 8, 16
+    sample = _rand((1, 4, f, h, w), dtype, 1.0, 1).expand(b, 4, f, h, w)      # batch-stride-0 view (CFG duplicate)
+    cond = _rand((b, 4, 1, h, w), dtype, 1.0, 2)
+    mask = (_rand((1, 1, 1, h, w), torch.float32, 1.0, 3) > 0).to(dtype)
+    out = ops.unet_in_assemble(sample, cond, mask, f + 1)
+    full = torch.cat([cond, sample], dim=2)                                      # b 4 T h w
+    m = mask.expand(b, 1, f + 1, h, w)
+    ref = torch.cat([m, full], dim=1).permute(0, 2, 3, 4, 1)                     # b T h w 5
+    assert torch.equal(out[..., :5], ref.contiguous())
+    assert torch.all(out[..., 5:] == 0)
+    out2 = ops.unet_in_assemble(sample, cond, None, f + 1)
+    assert torch.equal(out2[..., :4], full.permute(0, 2, 3, 4, 1).contiguous())
+    # output finalize
+    y = _rand((b * (f + 1) * h * w, 4), torch.float32, 1.0, 4)
+    o = ops.unet_out_finalize(y, b, f + 1, h, w, dtype)
+    ref = y.reshape(b, f + 1, h, w, 4).permute(0, 4, 1, 2, 3)[:, :, 1:].to(dtype)
+    assert torch.equal(o, ref.contiguous())
+    # timestep embedding
+    t = torch.tensor([981.0], device="cuda")
+    e = ops.timestep_embed(t, b, 320, dtype)
+    half = 160
+    freq = torch.exp(-math.log(10000) * torch.arange(half, device="cuda", dtype=torch.float32) / half)
+    a = t[:, None] * freq[None]
+    ref = torch.cat([torch.cos(a), torch.sin(a)], dim=-1).expand(b, 320)
+    check(f"timestep embed {dtype}", e, ref, *TOL[dtype])
+    # geglu + upsample
+    x = _rand((100, 256), dtype, 1.0, 5)
+    g = ops.geglu(x)
+    check("geglu", g, x[:, :128].float() * F.gelu(x[:, 128:].float()), *TOL[dtype])
+    xi = _rand((3, 4, 6, 16), dtype, 1.0, 6)
+    up = ops.upsample2x(xi)
+    ref = F.interpolate(xi.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1).to(dtype)
+    assert torch.equal(up, ref.contiguous())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_cfg_scheduler_step(dtype):
+    from animate_anything_b200 import ops
+    n, f, h, w = 1, 4, 8, 8
+    t = f + 1
+    eps = _rand((2 * n * t * h * w, 4), torch.float32, 1.0, 1)
+    x = _rand((n, 4, f, h, w), dtype, 1.0, 2)
+    hist = _rand((n, 4, f, h, w), torch.float32, 1.0, 3)
+    hist0 = hist.clone()
+    coef = torch.tensor([[0.0] * 6, [1.1, -0.3, 0.7, 0.2, -0.4, 0.15]], device="cuda", dtype=torch.float32)
+    step = torch.tensor([1], device="cuda", dtype=torch.int32)
+    out = torch.empty_like(x)
+    ops.cfg_scheduler_step(eps, 4, True, 9.0, x, out, hist, coef, step)
+    e = eps.reshape(2 * n, t, h, w, 4).permute(0, 4, 1, 2, 3)[:, :, 1:]
+    e = e[:n] + 9.0 * (e[n:] - e[:n])
+    k = coef[1]
+    x0 = k[0] * x.float() + k[1] * e
+    ref = k[2] * x.float() + k[3] * e + k[4] * x0 + k[5] * hist0
+    check(f"cfg+scheduler step {dtype}", out, ref, *TOL[dtype])
+    check("x0 history", hist, x0, 1e-5, 1e-5)
+
+
+def test_vae_boundary_kernels():
+    from animate_anything_b200 import ops
+    dtype = torch.float16
+    img = _rand((2, 3, 16, 24), dtype, 1.0, 1)
+    o = ops.image_to_nhwc8(img)
+    assert torch.equal(o[..., :3], img.permute(0, 2, 3, 1).contiguous()) and torch.all(o[..., 3:] == 0)
+    b, f, h, w = 1, 3, 8, 8
+    mom = _rand((b * f * h * w, 8), dtype, 1.0, 2)
+    wq = _rand((8, 8), torch.float32, 0.3, 3)
+    bq = _rand((8,), torch.float32, 0.3, 4)
+    lat = ops.vae_enc_finalize(mom, wq, bq, 0.18215, b, f, h, w)
+    ref = ((mom.float() @ wq.t() + bq)[:, :4].to(dtype).float() * 0.18215).reshape(b, f, h, w, 4).permute(0, 4, 1, 2, 3)
+    check("vae enc finalize", lat, ref, 1e-3, 1e-4)
+    latents = _rand((b, 4, f, h, w), dtype, 1.0, 5)
+    wp = _rand((4, 4), torch.float32, 0.5, 6)
+    bp = _rand((4,), torch.float32, 0.5, 7)
+    z = ops.vae_dec_in(latents, 1 / 0.18215, wp, bp)
+    zr = (latents.float() / 0.18215).to(dtype).float().permute(0, 2, 3, 4, 1).reshape(-1, 4) @ wp.t() + bp
+    check("vae dec in", z.reshape(-1, 8)[:, :4], zr, 2e-3, 2e-3)
+    y = _rand((b * f * 16 * 16, 16), torch.float32, 1.0, 8)
+    vid = ops.vae_dec_finalize(y, b, f, 16, 16, False)
+    ref = y[:, :3].to(dtype).float().reshape(b, f, 16, 16, 3).permute(0, 4, 1, 2, 3)
+    assert torch.equal(vid, ref.contiguous())
