@@ -418,7 +418,7 @@ extern "C" int aab_igemm(const AabIgemmDesc* d, void* stream_) {
   bool direct = (d->flags & AAB_F_DIRECT) != 0;
   const int n_out = geglu ? d->n / 2 : d->n;
   if (bn == 32 || (d->ld_out % 8) != 0 || (d->flags & AAB_F_OUT_F32)) direct = true;
-  if (geglu && bn < 64) return AAB_ERR_ARG;
+  if (geglu && bn < 128) return AAB_ERR_ARG;   // output tile must cover whole 64-column store boxes
   if (d->num_taps < 1 || d->num_taps > AAB_MAX_TAPS) return AAB_ERR_ARG;
   if (d->kc % 8 != 0) return AAB_ERR_ARG;
   if (d->a2 && (d->kc1 % 64 != 0)) return AAB_ERR_ARG;

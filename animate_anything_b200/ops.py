@@ -57,7 +57,7 @@ def pick_box(dims: Sequence[int], fixed_one: Sequence[int] = ()) -> list:
 
 
 def pick_block_n(n_out: int, m_tiles: int, geglu: bool = False) -> int:
-    cands = [256, 128, 64]
+    cands = [256, 128] if geglu else [256, 128, 64]
     best = None
     for bn in cands:
         obn = bn // 2 if geglu else bn

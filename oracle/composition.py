@@ -1,0 +1,248 @@
+"""ORACLE (test infrastructure, not product): plain-PyTorch restatement of the reference's *composition* of the hot
+path, written on top of the diffusers shim (`oracle/shim/diffusers/_impl.py`, parity unpinned — see its header).
+
+  OracleUNet3D          <- models/unet_3d_condition_mask.py:54-526  (UNet3DConditionModel)
+  _OBlock               <- models/unet_3d_blocks.py:234-842         (the five block classes, one table-driven class)
+  oracle_sampling_loop  <- models/pipeline.py:14-214                (LatentToVideoPipeline.__call__)
+
+It travels to the GPU box (where /root/reference does not exist) and is pinned in THIS container against the verbatim
+reference files: `tests/golden/make_golden.py` imports /root/reference/models/*.py over the shim, runs both on the same
+seeded weights/inputs and stores the reference outputs as fixtures; `tests/test_oracle_golden.py` re-checks the
+restatement against those fixtures everywhere.  Sub-module names equal the reference's, so one state_dict fits both.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shim")
+if _SHIM not in sys.path:
+    sys.path.insert(0, _SHIM)
+
+from diffusers._impl import (AutoencoderKL, DDIMScheduler, DPMSolverMultistepScheduler, Downsample2D,  # noqa: E402
+                             ResnetBlock2D, TemporalConvLayer, TimestepEmbedding, Timesteps, Transformer2DModel,
+                             TransformerTemporalModel, Upsample2D, tensor2vid)
+
+
+class _OBlock(nn.Module):
+    """One UNet stage.  kind: 'down' | 'mid' | 'up'; cross=True adds the (spatial, temporal) transformer pair."""
+
+    def __init__(self, kind, cross, resnet_io, temb_ch, eps, groups, head_ch, cross_dim, scale=1.0, resample_ch=None,
+                 down_padding=1):
+        super().__init__()
+        self.kind, self.cross = kind, cross
+        self.resnets = nn.ModuleList([ResnetBlock2D(in_channels=i, out_channels=o, temb_channels=temb_ch, eps=eps,
+                                                    groups=groups, output_scale_factor=scale) for i, o in resnet_io])
+        self.temp_convs = nn.ModuleList([TemporalConvLayer(o, o, dropout=0.1) for _, o in resnet_io])
+        if cross:
+            n_attn = len(resnet_io) - (1 if kind == "mid" else 0)
+            ch = resnet_io[-1][1]
+            self.attentions = nn.ModuleList([
+                Transformer2DModel(ch // head_ch, head_ch, in_channels=ch, num_layers=1, cross_attention_dim=cross_dim,
+                                   norm_num_groups=groups, use_linear_projection=True) for _ in range(n_attn)])
+            self.temp_attentions = nn.ModuleList([
+                TransformerTemporalModel(ch // head_ch, head_ch, in_channels=ch, num_layers=1,
+                                         cross_attention_dim=cross_dim, norm_num_groups=groups) for _ in range(n_attn)])
+        if kind == "down":
+            self.downsamplers = (nn.ModuleList([Downsample2D(resample_ch, use_conv=True, out_channels=resample_ch,
+                                                             padding=down_padding, name="op")])
+                                 if resample_ch else None)
+        if kind == "up":
+            self.upsamplers = (nn.ModuleList([Upsample2D(resample_ch, use_conv=True, out_channels=resample_ch)])
+                               if resample_ch else None)
+
+    def _spatio_temporal(self, i, h, ehs, nf):
+        h = self.attentions[i](h, encoder_hidden_states=ehs).sample
+        if nf > 1:
+            h = self.temp_attentions[i](h, num_frames=nf).sample
+        return h
+
+    def forward(self, h, temb, ehs, nf, skips: Optional[List[torch.Tensor]] = None):
+        if self.kind == "mid":
+            h = self.resnets[0](h, temb)
+            h = self.temp_convs[0](h, num_frames=nf)
+            for i in range(len(self.attentions)):
+                h = self._spatio_temporal(i, h, ehs, nf)
+                h = self.resnets[i + 1](h, temb)
+                if nf > 1:
+                    h = self.temp_convs[i + 1](h, num_frames=nf)
+            return h
+        produced = []
+        for i, (res, tconv) in enumerate(zip(self.resnets, self.temp_convs)):
+            if self.kind == "up":
+                h = torch.cat([h, skips.pop()], dim=1)
+            h = res(h, temb)
+            if nf > 1:
+                h = tconv(h, num_frames=nf)
+            if self.cross:
+                h = self._spatio_temporal(i, h, ehs, nf)
+            produced.append(h)
+        if self.kind == "down":
+            if self.downsamplers is not None:
+                h = self.downsamplers[0](h)
+                produced.append(h)
+            return h, produced
+        if self.upsamplers is not None:
+            h = self.upsamplers[0](h)
+        return h
+
+
+class OracleUNet3D(nn.Module):
+    def __init__(self, sample_size=None, in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280, 1280),
+                 layers_per_block=2, downsample_padding=1, mid_block_scale_factor=1, norm_num_groups=32, norm_eps=1e-5,
+                 cross_attention_dim=1024, attention_head_dim=64, motion_mask=False, motion_strength=False,
+                 cross_stages=(True, True, True, False)):
+        super().__init__()
+        self.motion_mask, self.motion_strength = motion_mask, motion_strength
+        ch = list(block_out_channels)
+        c0, temb_ch, g, e = ch[0], ch[0] * 4, norm_num_groups, norm_eps
+        self.conv_in = nn.Conv2d(in_channels, c0, 3, padding=1)
+        self.conv_in2 = nn.Conv2d(5, c0, 3, padding=1)
+        self.time_proj = Timesteps(c0, True, 0)
+        self.time_embedding = TimestepEmbedding(c0, temb_ch, act_fn="silu", cond_proj_dim=c0)
+        self.motion_proj = Timesteps(c0, True, 0)
+        self.motion_embedding = nn.Sequential(nn.Linear(c0, temb_ch), nn.SiLU(), nn.Linear(temb_ch, temb_ch))
+        nn.init.zeros_(self.motion_embedding[-1].weight)
+        nn.init.zeros_(self.motion_embedding[-1].bias)
+        self.transformer_in = TransformerTemporalModel(num_attention_heads=8, attention_head_dim=attention_head_dim,
+                                                       in_channels=c0, num_layers=1)
+        hd = attention_head_dim
+        nst = len(ch)
+        self.down_blocks = nn.ModuleList()
+        prev = c0
+        for i in range(nst):
+            io = [(prev if j == 0 else ch[i], ch[i]) for j in range(layers_per_block)]
+            self.down_blocks.append(_OBlock("down", cross_stages[i], io, temb_ch, e, g, hd, cross_attention_dim,
+                                            resample_ch=ch[i] if i < nst - 1 else None,
+                                            down_padding=downsample_padding))
+            prev = ch[i]
+        self.mid_block = _OBlock("mid", True, [(ch[-1], ch[-1])] * 2, temb_ch, e, g, hd, cross_attention_dim,
+                                 scale=mid_block_scale_factor)
+        self.up_blocks = nn.ModuleList()
+        rev = ch[::-1]
+        rev_cross = list(cross_stages)[::-1]
+        prev_out = rev[0]
+        for i in range(nst):
+            out_c = rev[i]
+            in_c = rev[min(i + 1, nst - 1)]
+            nl = layers_per_block + 1
+            io = [((prev_out if j == 0 else out_c) + (in_c if j == nl - 1 else out_c), out_c) for j in range(nl)]
+            self.up_blocks.append(_OBlock("up", rev_cross[i], io, temb_ch, e, g, hd, cross_attention_dim,
+                                          resample_ch=out_c if i < nst - 1 else None))
+            prev_out = out_c
+        self.conv_norm_out = nn.GroupNorm(g, c0, eps=e)
+        self.conv_act = nn.SiLU()
+        self.conv_out = nn.Conv2d(c0, out_channels, 3, padding=1)
+
+    @property
+    def dtype(self):
+        return self.conv_out.weight.dtype
+
+    def forward(self, sample, timestep, encoder_hidden_states, condition_latent, mask, motion=None):
+        x = torch.cat([condition_latent, sample], dim=2)                      # b c T h w, T = F + 1
+        b, _, nf, hh, ww = x.shape
+        ts = timestep if torch.is_tensor(timestep) else torch.tensor([timestep], device=x.device)
+        ts = ts.reshape(-1).to(x.device).expand(b)
+        t_emb = self.time_proj(ts).to(self.dtype)
+        cond = None
+        if self.motion_strength and motion is not None:
+            cond = self.motion_proj(motion).to(self.dtype)
+        emb = self.time_embedding(t_emb, cond).repeat_interleave(nf, dim=0)
+        ehs = encoder_hidden_states.repeat_interleave(nf, dim=0)
+        if self.motion_mask and mask is not None:
+            rep = b // mask.shape[0]
+            m = mask.repeat(rep, 1, nf, 1, 1)                                # '(t b) 1 f h w'
+            x = torch.cat([m, x], dim=1)
+            x = self.conv_in2(x.permute(0, 2, 1, 3, 4).reshape(b * nf, -1, hh, ww))
+        else:
+            x = self.conv_in(x.permute(0, 2, 1, 3, 4).reshape(b * nf, -1, hh, ww))
+        if nf > 1:
+            x = self.transformer_in(x, num_frames=nf).sample
+        skips = [x]
+        for blk in self.down_blocks:
+            x, produced = blk(x, emb, ehs, nf)
+            skips.extend(produced)
+        x = self.mid_block(x, emb, ehs, nf)
+        for blk in self.up_blocks:
+            x = blk(x, emb, ehs, nf, skips)
+        x = self.conv_out(self.conv_act(self.conv_norm_out(x)))
+        x = x.reshape(b, nf, -1, hh, ww).permute(0, 2, 1, 3, 4)
+        return x[:, :, 1:]
+
+
+def oracle_decode_latents(vae, latents):
+    """diffusers TextToVideoSDPipeline.decode_latents (called at models/pipeline.py:200)."""
+    z = latents / vae.config.scaling_factor
+    b, c, f, h, w = z.shape
+    img = vae.decode(z.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)).sample
+    return img.reshape(b, f, -1, img.shape[-2], img.shape[-1]).permute(0, 2, 1, 3, 4).float()
+
+
+def oracle_encode_image(vae, frames):
+    """utils/common.py:12-20 tensor_to_vae_latent: frames [b, f, 3, H, W] -> latents [b, 4, f, h, w] * 0.18215."""
+    b, f = frames.shape[:2]
+    lat = vae.encode(frames.reshape(b * f, *frames.shape[2:])).latent_dist.mode()
+    return lat.reshape(b, f, *lat.shape[1:]).permute(0, 2, 1, 3, 4) * 0.18215
+
+
+@torch.no_grad()
+def oracle_sampling_loop(unet, scheduler, latents, prompt_embeds, negative_prompt_embeds, condition_latent, mask,
+                         motion, guidance_scale=9.0, num_inference_steps=50, timesteps=None, vae=None,
+                         output_type="pt"):
+    """Restates LatentToVideoPipeline.__call__ (models/pipeline.py:107-212) for pre-computed prompt embeddings."""
+    cfg = guidance_scale > 1.0
+    ehs = torch.cat([negative_prompt_embeds, prompt_embeds]) if cfg else prompt_embeds
+    scheduler.set_timesteps(num_inference_steps, device=latents.device)
+    if timesteps is None:
+        timesteps = scheduler.timesteps
+    cond = torch.cat([condition_latent, condition_latent]) if cfg else condition_latent
+    mot = None if motion is None else torch.tensor(motion, device=latents.device)
+    for t in timesteps:
+        inp = torch.cat([latents] * 2) if cfg else latents
+        inp = scheduler.scale_model_input(inp, t)
+        eps = unet(inp, t, ehs, condition_latent=cond, mask=mask, motion=mot)
+        if cfg:
+            eu, et = eps.chunk(2)
+            eps = eu + guidance_scale * (et - eu)
+        b, c, f, h, w = latents.shape
+        flat = latents.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
+        eflat = eps.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
+        flat = scheduler.step(eflat, t, flat).prev_sample
+        latents = flat.reshape(b, f, c, h, w).permute(0, 2, 1, 3, 4)
+    if vae is None:
+        return None, latents
+    video = oracle_decode_latents(vae, latents)
+    if output_type != "pt":
+        video = tensor2vid(video)
+    return video, latents
+
+
+# ---------------------------------------------------------------------------------------------- shared test helper
+def fill_deterministic(model: nn.Module, seed: int = 0, scale: float = 0.05):
+    """Key-order-independent deterministic weights so that the verbatim reference model, this oracle and the product
+    model (all sharing state_dict keys) hold identical parameters without shipping checkpoints.  Zero-initialised layers
+    are re-drawn too so that they are exercised."""
+    import hashlib
+    sd = model.state_dict()
+    new = {}
+    for k, v in sd.items():
+        if not torch.is_floating_point(v):
+            new[k] = v
+            continue
+        h = int.from_bytes(hashlib.sha256(f"{seed}:{k}".encode()).digest()[:8], "little") % (2 ** 31)
+        g = torch.Generator().manual_seed(h)
+        t = torch.randn(v.shape, generator=g, dtype=torch.float32)
+        if v.dim() == 1 and (("norm" in k and k.endswith("weight")) or ".0.weight" in k and v.dim() == 1):
+            t = 1.0 + 0.1 * t                                     # norm gains
+        elif v.dim() == 1:
+            t = 0.1 * t                                           # biases
+        else:
+            fan_in = v[0].numel()
+            t = t * (1.0 / fan_in) ** 0.5
+        new[k] = t.to(v.dtype)
+    model.load_state_dict(new)
+    return model

@@ -1,0 +1,84 @@
+"""Generates the golden fixtures in this directory by running the VERBATIM reference files
+(/root/reference/models/unet_3d_condition_mask.py, unet_3d_blocks.py, pipeline.py) on top of the diffusers shim
+(oracle/shim, parity unpinned: see its header).  Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+Weights are not stored: `oracle.composition.fill_deterministic` regenerates them from the state_dict keys.
+"""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "shim"))
+sys.path.insert(0, "/root/reference")
+
+from oracle.composition import fill_deterministic  # noqa: E402
+
+TINY = dict(sample_size=16, block_out_channels=(32, 64, 64, 64), attention_head_dim=8, cross_attention_dim=32,
+            motion_mask=True, motion_strength=True)
+TINY_VAE = dict(block_out_channels=(32, 32, 64, 64), layers_per_block=1, norm_num_groups=32, sample_size=64)
+
+
+def tiny_inputs(seed=1, b=2, f=4, hw=16, lk=7, cdim=32):
+    g = torch.Generator().manual_seed(seed)
+    return dict(
+        sample=torch.randn(b, 4, f, hw, hw, generator=g),
+        cond=torch.randn(b, 4, 1, hw, hw, generator=g),
+        ehs=torch.randn(b, lk, cdim, generator=g),
+        mask=(torch.rand(1, 1, 1, hw, hw, generator=g) > 0.5).float(),
+        timestep=500,
+        motion=torch.tensor([4.0]),
+    )
+
+
+def main():
+    import diffusers  # the shim
+    from models.unet_3d_condition_mask import UNet3DConditionModel            # verbatim reference
+    from models.pipeline import LatentToVideoPipeline                         # verbatim reference
+    torch.manual_seed(0)
+    ref = UNet3DConditionModel(**TINY).eval()
+    fill_deterministic(ref, seed=0)
+    inp = tiny_inputs()
+    with torch.no_grad():
+        out = ref(inp["sample"], inp["timestep"], inp["ehs"], condition_latent=inp["cond"], mask=inp["mask"],
+                  motion=inp["motion"]).sample
+        out_nomask = ref(inp["sample"], 37, inp["ehs"], condition_latent=inp["cond"], mask=None, motion=None).sample
+        out_1f = ref(inp["sample"][:, :, :0], 999, inp["ehs"], condition_latent=inp["cond"], mask=inp["mask"],
+                     motion=inp["motion"]).sample if False else None
+    torch.save({"config": TINY, "out": out, "out_nomask_t37": out_nomask, "keys": sorted(ref.state_dict().keys())},
+               os.path.join(HERE, "unet_tiny_ref.pt"))
+    print("unet golden:", out.shape, float(out.abs().mean()))
+
+    # full pipeline: tiny UNet + tiny VAE, DDIM 3 steps, CFG 9, via the verbatim LatentToVideoPipeline.__call__
+    vae = diffusers.AutoencoderKL(**TINY_VAE).eval()
+    fill_deterministic(vae, seed=1)
+    sched = diffusers.DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                                    clip_sample=False, set_alpha_to_one=False, steps_offset=1)
+    pipe = LatentToVideoPipeline(vae=vae, text_encoder=None, tokenizer=None, unet=ref, scheduler=sched)
+    g = torch.Generator().manual_seed(5)
+    lat = torch.randn(1, 4, 4, 16, 16, generator=g)
+    cond = torch.randn(1, 4, 1, 16, 16, generator=g)
+    pe = torch.randn(1, 7, 32, generator=g)
+    ne = torch.randn(1, 7, 32, generator=g)
+    mask = torch.ones(1, 1, 1, 16, 16)
+    video, latents = pipe(prompt_embeds=pe, negative_prompt_embeds=ne, latents=lat, condition_latent=cond, mask=mask,
+                          motion=[4], guidance_scale=9.0, num_inference_steps=3, output_type="pt", return_dict=False)
+    # same loop with DPM-Solver++ (what train.py:806 installs)
+    dpm = diffusers.DPMSolverMultistepScheduler.from_config(sched.config)
+    pipe.scheduler = dpm
+    video_dpm, latents_dpm = pipe(prompt_embeds=pe, negative_prompt_embeds=ne, latents=lat, condition_latent=cond,
+                                  mask=mask, motion=[4], guidance_scale=9.0, num_inference_steps=4, output_type="pt",
+                                  return_dict=False)
+    torch.save({"vae_config": TINY_VAE, "latents_in": lat, "cond": cond, "pe": pe, "ne": ne, "video": video.half(),
+                "latents": latents, "latents_dpm": latents_dpm,
+                "vae_keys": sorted(vae.state_dict().keys())}, os.path.join(HERE, "pipeline_tiny_ref.pt"))
+    print("pipeline golden:", video.shape, latents.shape, float(latents.abs().mean()), float(latents_dpm.abs().mean()))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,109 @@
+"""GPU parity of the B200 UNet3DConditionModel.forward against the oracle (fp32, same 16-bit-rounded weights/inputs).
+
+Three error levels are reported separately (SURVEY.md section 7 'fp16 tolerance'): per kernel (test_gpu_igemm/attention/
+norm_elem: rtol=1e-3 fp16), single forward (here), full loop (test_gpu_pipeline).  For a whole forward the yard-stick is
+the stock PyTorch fp16 execution of the same op sequence (oracle.half() on cuDNN/cuBLAS): our error vs the fp32 oracle
+must not exceed 1.5x that of the stock fp16 stack (+ a small floor)."""
+import os
+import sys
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+from util import report  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _models(cfg, dtype):
+    from oracle.composition import OracleUNet3D, fill_deterministic
+    from animate_anything_b200.unet_3d_condition_mask import UNet3DConditionModel
+    ocfg = {k: v for k, v in cfg.items() if k != "sample_size"}
+    oracle = fill_deterministic(OracleUNet3D(**ocfg).eval(), seed=0)
+    sd16 = {k: v.to(dtype) for k, v in oracle.state_dict().items()}
+    oracle.load_state_dict({k: v.float() for k, v in sd16.items()})      # fp32 math on 16-bit-rounded weights
+    ours = UNet3DConditionModel(**cfg).eval()
+    missing, unexpected = ours.load_state_dict(sd16, strict=True)
+    return oracle.cuda(), ours.to(dtype).cuda()
+
+
+def _inputs(b, f, hw, lk, cdim, dtype, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    d = dict(sample=torch.randn(b, 4, f, hw, hw, generator=g), cond=torch.randn(b, 4, 1, hw, hw, generator=g),
+             ehs=torch.randn(b, lk, cdim, generator=g), mask=(torch.rand(1, 1, 1, hw, hw, generator=g) > 0.5).float())
+    return {k: v.to(dtype).cuda() for k, v in d.items()}
+
+
+def _to_nchw(x, g):
+    return x.float().reshape(g.n, g.h, g.w, -1).permute(0, 3, 1, 2)
+
+
+def _run_case(cfg, dtype, b, f, hw, lk, timestep=500, motion=4.0, trace=True):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    oracle, ours = _models(cfg, dtype)
+    inp = _inputs(b, f, hw, lk, cfg["cross_attention_dim"], dtype)
+    mot = torch.tensor([motion], device="cuda")
+    captured = {}
+    hooks = []
+    if trace:
+        def mk(name):
+            def hook(mod, args, out):
+                o = out[0] if isinstance(out, tuple) else out
+                captured[name] = (o.sample if hasattr(o, "sample") else o).detach().float()
+            return hook
+        for name in (["conv_in2", "transformer_in", "mid_block"] + [f"down_blocks.{i}" for i in range(4)] +
+                     [f"up_blocks.{i}" for i in range(4)]):
+            hooks.append(oracle.get_submodule(name).register_forward_hook(mk(name)))
+    with torch.no_grad():
+        ref = oracle(inp["sample"].float(), timestep, inp["ehs"].float(), inp["cond"].float(), inp["mask"].float(),
+                     motion=mot)
+    for h in hooks:
+        h.remove()
+    ours._trace = [] if trace else None
+    ours.__dict__["_trace"] = ours._trace
+    out = ours(inp["sample"], timestep, inp["ehs"], condition_latent=inp["cond"], mask=inp["mask"], motion=mot).sample
+    torch.cuda.synchronize()
+    if trace:
+        for name, x, g in ours.__dict__["_trace"]:
+            key = "conv_in2" if name == "conv_in" else name
+            if key in captured:
+                report(f"  stage {name}", _to_nchw(x, g), captured[key], 1e-2, 1e-2)
+    # stock fp16/bf16 torch execution of the same op sequence = the yard-stick
+    with torch.no_grad():
+        stock = oracle.to(dtype)(inp["sample"], timestep, inp["ehs"], inp["cond"], inp["mask"], motion=mot).float()
+    e_ours = (out.float() - ref).abs()
+    e_stock = (stock - ref).abs()
+    scale = ref.abs().mean().item()
+    print(f"forward {dtype}: ref|mean|={scale:.4f}  ours: max={e_ours.max().item():.4e} mean={e_ours.mean().item():.4e}"
+          f"  stock-torch: max={e_stock.max().item():.4e} mean={e_stock.mean().item():.4e}")
+    assert torch.isfinite(out).all()
+    assert e_ours.mean().item() <= 1.5 * e_stock.mean().item() + 2e-4 * scale
+    assert e_ours.max().item() <= 2.0 * e_stock.max().item() + 2e-3 * scale
+    return e_ours, e_stock
+
+
+SMALL = dict(sample_size=16, block_out_channels=(64, 128, 256, 256), attention_head_dim=64, cross_attention_dim=128,
+             motion_mask=True, motion_strength=True)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_unet_small(dtype):
+    _run_case(SMALL, dtype, b=2, f=4, hw=16, lk=77)
+
+
+def test_unet_small_no_mask_single_frame_paths():
+    """conv_in (4-ch) branch and motion=None branch (reference :414-419,:429-431)."""
+    from oracle.composition import OracleUNet3D
+    dtype = torch.float16
+    cfg = dict(SMALL, motion_mask=False, motion_strength=False)
+    _run_case(cfg, dtype, b=1, f=3, hw=16, lk=10, trace=False)
+
+
+def test_unet_config1_fullsize():
+    """BASELINE config 1 shapes on the full-size architecture: sample [1,4,8,32,32], text [1,77,1024], t=500, motion 4."""
+    cfg = dict(sample_size=32, motion_mask=True, motion_strength=True)
+    _run_case(cfg, torch.float16, b=1, f=8, hw=32, lk=77, trace=True)

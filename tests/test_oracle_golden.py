@@ -1,0 +1,79 @@
+"""CPU: pins the oracle restatement (oracle/composition.py) against fixtures produced by the VERBATIM reference files
+run over the diffusers shim (tests/golden/make_golden.py).  The shim itself is 'parity unpinned' (no real diffusers
+available); these tests pin the *composition* (reference models/*.py) and the self-consistency of the shim."""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+from oracle.composition import (AutoencoderKL, DDIMScheduler, DPMSolverMultistepScheduler, OracleUNet3D,  # noqa: E402
+                                fill_deterministic, oracle_sampling_loop)
+from make_golden import tiny_inputs  # noqa: E402
+
+
+def _tiny_unet(gold):
+    cfg = dict(gold["config"])
+    cfg.pop("sample_size")
+    m = OracleUNet3D(**cfg).eval()
+    assert sorted(m.state_dict().keys()) == gold["keys"], "state_dict keys differ from the reference model"
+    return fill_deterministic(m, seed=0)
+
+
+def test_unet_composition_matches_reference_files():
+    gold = torch.load(os.path.join(HERE, "golden", "unet_tiny_ref.pt"))
+    m = _tiny_unet(gold)
+    inp = tiny_inputs()
+    with torch.no_grad():
+        out = m(inp["sample"], inp["timestep"], inp["ehs"], inp["cond"], inp["mask"], motion=inp["motion"])
+        out2 = m(inp["sample"], 37, inp["ehs"], inp["cond"], None, motion=None)
+    assert torch.allclose(out, gold["out"], rtol=1e-5, atol=1e-6), float((out - gold["out"]).abs().max())
+    assert torch.allclose(out2, gold["out_nomask_t37"], rtol=1e-5, atol=1e-6)
+
+
+def test_sampling_loop_matches_reference_pipeline():
+    gold_u = torch.load(os.path.join(HERE, "golden", "unet_tiny_ref.pt"))
+    gold = torch.load(os.path.join(HERE, "golden", "pipeline_tiny_ref.pt"))
+    unet = _tiny_unet(gold_u)
+    vae = AutoencoderKL(**gold["vae_config"]).eval()
+    assert sorted(vae.state_dict().keys()) == gold["vae_keys"]
+    fill_deterministic(vae, seed=1)
+    sched = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
+                          set_alpha_to_one=False, steps_offset=1)
+    mask = torch.ones(1, 1, 1, 16, 16)
+    video, lat = oracle_sampling_loop(unet, sched, gold["latents_in"], gold["pe"], gold["ne"], gold["cond"], mask, [4],
+                                      guidance_scale=9.0, num_inference_steps=3, vae=vae)
+    assert torch.allclose(lat, gold["latents"], rtol=1e-4, atol=1e-5), float((lat - gold["latents"]).abs().max())
+    assert torch.allclose(video, gold["video"].float(), rtol=2e-3, atol=2e-3)
+    dpm = DPMSolverMultistepScheduler.from_config(sched.config)
+    _, lat2 = oracle_sampling_loop(unet, dpm, gold["latents_in"], gold["pe"], gold["ne"], gold["cond"], mask, [4],
+                                   guidance_scale=9.0, num_inference_steps=4)
+    assert torch.allclose(lat2, gold["latents_dpm"], rtol=1e-4, atol=1e-5)
+
+
+def test_shim_recalled_facts():
+    """One assertion per RECALLED diffusers-0.24 fact that SURVEY.md 8(c) lists as most likely to be wrong."""
+    from diffusers._impl import GEGLU, TemporalConvLayer, Timesteps, TimestepEmbedding, Upsample2D, ResnetBlock2D
+    import torch.nn.functional as F
+    g = GEGLU(4, 6)
+    x = torch.randn(3, 4)
+    full = g.proj(x)
+    assert torch.allclose(g(x), full[:, :6] * F.gelu(full[:, 6:]))                 # chunk order (value, gate)
+    t = Timesteps(8, True, 0)(torch.tensor([3.0]))
+    freq = torch.exp(-torch.log(torch.tensor(10000.0)) * torch.arange(4) / 4)
+    assert torch.allclose(t[0, :4], torch.cos(3.0 * freq), atol=1e-6)              # flip_sin_to_cos -> cos first
+    assert torch.allclose(t[0, 4:], torch.sin(3.0 * freq), atol=1e-6)
+    te = TimestepEmbedding(8, 16, cond_proj_dim=8)
+    assert te.cond_proj.bias is None                                                # cond_proj is bias-free
+    tc = TemporalConvLayer(32, 32).eval()
+    y = torch.randn(6, 32, 4, 4)
+    assert torch.equal(tc(y, num_frames=3), y)                                      # zero-init conv4 => identity
+    up = Upsample2D(4, use_conv=True).eval()
+    z = torch.randn(1, 4, 3, 3)
+    assert torch.allclose(up(z), up.conv(F.interpolate(z, scale_factor=2.0, mode="nearest")))
+    r = ResnetBlock2D(in_channels=32, out_channels=32, temb_channels=8).eval()
+    assert r.conv_shortcut is None and r.norm1.eps == 1e-6
