@@ -78,6 +78,7 @@ _SIGS = {
 EXPORTS = tuple(_SIGS.keys())
 
 _launch_count = 0
+_KERNELS_PER_CALL = {"aab_groupnorm": 2}     # stats + apply (plus a memset node)
 
 
 def load():
@@ -104,7 +105,7 @@ def call(name, *args):
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise AabError(f"{name} failed with status {rc} (1=bad argument, 2=CUDA launch error, 3=driver/TMA encode)")
-    _launch_count += 1
+    _launch_count += _KERNELS_PER_CALL.get(name, 1)
     return rc
 
 

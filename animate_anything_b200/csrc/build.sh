@@ -13,5 +13,5 @@ for f in igemm attention norm elementwise; do
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o ../libaab200.so ../_build/igemm.o ../_build/attention.o ../_build/norm.o ../_build/elementwise.o -lcudart
+$NVCC -arch=sm_100a -shared -o ../libaab200.so ../_build/igemm.o ../_build/attention.o ../_build/norm.o ../_build/elementwise.o -lcudart
 echo "built $(realpath ../libaab200.so)"

@@ -214,8 +214,8 @@ __global__ void image_to_nhwc8_kernel(const void* __restrict__ img, long sn, lon
       make_uint4(pack2(v[0], v[1], BF16), pack2(v[2], v[3], BF16), pack2(v[4], v[5], BF16), pack2(v[6], v[7], BF16));
 }
 
-// encoder tail: moments [N, h, w, ldm] (8 ch) -> quant_conv (1x1, 8->8) -> mean (first 4) * scale -> [B, 4, F, h, w]
-// (AutoencoderKL.encode + DiagonalGaussianDistribution.mode(); utils/common.py:16-18 multiplies by 0.18215)
+// encoder tail: conv_out result [N, h, w, ldm] (8 ch) -> quant_conv (1x1, 8->8) -> moments [N, 8, h, w] (NCHW, 16-bit)
+// (AutoencoderKL.encode: `moments = self.quant_conv(h)`; DiagonalGaussianDistribution.mode() is channels 0..3)
 template <bool BF16>
 __global__ void vae_enc_finalize_kernel(const void* __restrict__ mom, int ldm, const float* __restrict__ wq /*[8][8]*/,
                                         const float* __restrict__ bq, float scale, void* __restrict__ out, int B, int F,
@@ -233,13 +233,11 @@ __global__ void vae_enc_finalize_kernel(const void* __restrict__ mom, int ldm, c
 #pragma unroll
   for (int j = 0; j < 8; ++j) m[j] = load_elem(mom, i * ldm + j, BF16);
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 8; ++c) {
     float acc = bq[c];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc = fmaf(wq[c * 8 + j], m[j], acc);
-    // the reference rounds the mean to the model dtype before scaling
-    const float mean = BF16 ? __bfloat162float(__float2bfloat16_rn(acc)) : __half2float(__float2half_rn(acc));
-    store_elem(out, (((static_cast<long>(b) * 4 + c) * F + f) * H + y) * W + x, mean * scale, BF16);
+    store_elem(out, (((static_cast<long>(b) * 8 + c) * F + f) * H + y) * W + x, acc * scale, BF16);
   }
 }
 

@@ -14,6 +14,7 @@ from . import _lib
 from ._lib import ACT_GELU, ACT_NONE, ACT_SILU, F_BF16, F_DIRECT, F_GEGLU, F_OUT_F32, IgemmDesc
 
 NUM_SMS = 148
+IGEMM_PROFILE = None     # bench.py sets this to a list to time every implicit-GEMM launch with CUDA events
 
 
 def _stream():
@@ -164,7 +165,16 @@ def igemm(a: torch.Tensor, a_dims, a_strides, w: torch.Tensor, n: int, kc: int, 
             block_n = pick_block_n(n_out, m_tiles, geglu)
     d.block_n = block_n
     d.max_ctas = max_ctas
-    _lib.call("aab_igemm", C.byref(d), _stream())
+    if IGEMM_PROFILE is not None:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        _lib.call("aab_igemm", C.byref(d), _stream())
+        ev1.record()
+        IGEMM_PROFILE.append({"rows": rows, "n": n, "k": kc * len(taps), "taps": len(taps), "block_n": block_n,
+                              "flops": 2.0 * rows * n * kc * len(taps), "ev": (ev0, ev1)})
+    else:
+        _lib.call("aab_igemm", C.byref(d), _stream())
     return out
 
 
@@ -373,7 +383,8 @@ def image_to_nhwc8(img: torch.Tensor) -> torch.Tensor:
 
 
 def vae_enc_finalize(mom: torch.Tensor, wq, bq, scale, b, f, h, w) -> torch.Tensor:
-    out = torch.empty((b, 4, f, h, w), device=mom.device, dtype=mom.dtype)
+    """conv_out output [b*f*h*w, >=8] -> quant_conv -> moments [b, 8, f, h, w]."""
+    out = torch.empty((b, 8, f, h, w), device=mom.device, dtype=mom.dtype)
     _lib.call("aab_vae_enc_finalize", _ptr(mom), mom.stride(0), _ptr(wq), _ptr(bq), float(scale), _ptr(out), b, f, h, w,
               _is_bf16(mom), _stream())
     return out

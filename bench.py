@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path named by BASELINE.json: `LatentToVideoPipeline.__call__` for one 16-frame 512x512 clip,
+50 DDIM steps, CFG 9, random-init full-size UNet3D (1.41 B params) + SD VAE, bf16, synthetic inputs (config 2).
+
+  python bench.py --gpus N --steps K --warmup W          # this repo (sm_100a kernels)
+  python bench.py --impl reference --gpus N ...          # the reference's CPU path (oracle port) on the host cores
+
+A "step" of this bench = one whole pipeline call (50 denoising steps + VAE decode) = 16 denoised frames per rank.
+N > 1 (torchrun, one rank per GPU): weak scaling — every rank generates its own clip (prompts / CFG pairs are sharded
+with both halves of a pair co-located), decoded frames are all-gathered with ONE NCCL collective.
+
+JSON line: `value` = frames/s with inputs resident in HBM (CUDA events, max over ranks); `e2e` = the same through the
+public API with pinned HOST inputs copied H2D every step and the decoded video read back D2H; `roofline` = achieved
+tensor TFLOP/s of the dominant kernel (tcgen05 implicit GEMM, all launches of one UNet forward timed with CUDA events)
+against the measured bf16 peak; `cpu_baseline` = the oracle timed on the host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "denoised_frames_per_sec_16f_512x512_50ddim"
+UNIT = "frames/s"
+FRAMES, HW, LAT, STEPS_DDIM, GUIDANCE = 16, 512, 64, 50, 9.0
+SCHED = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
+             set_alpha_to_one=False, steps_offset=1)
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p["bf16_tflops_sustained"], p["hbm_gbs"], "measured (MEASURED_PEAKS.json, sustained)"
+    except Exception:
+        return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(float(s[0])) for s in self.samples)
+        reasons = []
+        for name, col in (("hw_slowdown", 2), ("hw_thermal_slowdown", 3), ("sw_thermal_slowdown", 4), ("sw_power_cap", 5)):
+            if any(s[col].lower().startswith("active") for s in self.samples):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def _oracle_unet_sample(threads):
+    """Bounded CPU sample of the workload: one oracle UNet3D forward (fp32) for ONE batch element of the CFG pair.
+    Returns (seconds_per_full_forward_B1_T17, description)."""
+    import torch
+    from oracle.composition import OracleUNet3D
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    unet = OracleUNet3D(motion_mask=True, motion_strength=True).eval()
+    g = torch.Generator().manual_seed(1)
+
+    def fwd(f, hw):
+        s = torch.randn(1, 4, f, hw, hw, generator=g)
+        c = torch.randn(1, 4, 1, hw, hw, generator=g)
+        e = torch.randn(1, 77, 1024, generator=g)
+        m = torch.ones(1, 1, 1, hw, hw)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            unet(s, 500, e, c, m, motion=torch.tensor([4.0]))
+        return time.perf_counter() - t0
+    cal = fwd(2, 32)                                    # calibration: T=3 at 32x32 (0.9 TFLOP)
+    est_full = cal * (17 / 3) * 4
+    if est_full <= 40:
+        return unet, fwd, 16, "1 oracle UNet3D forward, fp32, B=1 (one CFG half), T=17, 64x64 latents"
+    f_small = 4
+    return unet, fwd, f_small, (f"1 oracle UNet3D forward, fp32, B=1, T={f_small + 1} of 17 frames, 64x64 latents; "
+                                f"scaled linearly in T (all ops but the 0.1%-FLOP temporal attention are linear in T)")
+
+
+def cpu_frames_per_sec(sample_s, f_sample):
+    per_fwd_b1 = sample_s * (17.0 / (f_sample + 1))
+    clip_s = per_fwd_b1 * 2 * STEPS_DDIM                    # CFG pair x 50 steps; VAE decode (1.8 % of FLOPs) ignored
+    return FRAMES / clip_s
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    unet, fwd, f_sample, desc = _oracle_unet_sample(threads)
+    for _ in range(min(args.warmup, 1)):
+        fwd(f_sample, LAT)
+    times = [fwd(f_sample, LAT) for _ in range(max(1, args.steps))]
+    t = sum(times) / len(times)
+    v = cpu_frames_per_sec(t, f_sample)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": FRAMES / v * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config2: pipeline.__call__ 16x512x512, 50 DDIM steps, CFG 9 (CPU: extrapolated from "
+                                   "a bounded sample)", "sample_seconds": t},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ product arm
+def build_models(device, dtype):
+    import torch
+    from animate_anything_b200.autoencoder_kl import AutoencoderKL
+    from animate_anything_b200.pipeline import LatentToVideoPipeline
+    from animate_anything_b200.schedulers import DDIMScheduler
+    from animate_anything_b200.unet_3d_condition_mask import UNet3DConditionModel
+    torch.manual_seed(0)
+    with torch.device(device):
+        unet = UNet3DConditionModel(sample_size=LAT, motion_mask=True, motion_strength=True)
+        vae = AutoencoderKL()
+    # the reference zero-inits these; re-draw so they are exercised
+    with torch.no_grad():
+        for n, p in unet.named_parameters():
+            if p.abs().max() == 0:
+                p.normal_(0.0, 0.02)
+    unet = unet.to(dtype).eval()
+    vae = vae.to(dtype).eval()
+    pipe = LatentToVideoPipeline(vae=vae, text_encoder=None, tokenizer=None, unet=unet, scheduler=DDIMScheduler(**SCHED))
+    return pipe
+
+
+def synth_inputs(rank, pinned=True):
+    import torch
+    g = torch.Generator().manual_seed(100 + rank)
+    d = {"latents": torch.randn(1, 4, FRAMES, LAT, LAT, generator=g),
+         "condition_latent": torch.randn(1, 4, 1, LAT, LAT, generator=g),
+         "prompt_embeds": torch.randn(1, 77, 1024, generator=g),
+         "negative_prompt_embeds": torch.randn(1, 77, 1024, generator=g),
+         "mask": torch.ones(1, 1, 1, LAT, LAT)}
+    d = {k: v.to(torch.bfloat16) for k, v in d.items()}
+    if pinned:
+        d = {k: v.pin_memory() for k, v in d.items()}
+    return d
+
+
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+    from animate_anything_b200 import _lib, ops
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dtype = torch.bfloat16
+    pipe = build_models(dev, dtype)
+    pipe.use_cuda_graph = not args.no_graph
+    host = synth_inputs(rank)
+    devin = {k: v.to(dev) for k, v in host.items()}
+    kw = dict(motion=[4], guidance_scale=GUIDANCE, num_inference_steps=STEPS_DDIM, output_type="pt", return_dict=False)
+    gather_buf = None
+    if world > 1:
+        gather_buf = torch.empty((world, 3, FRAMES, HW, HW), dtype=torch.uint8, device=dev)
+
+    def one_clip(inp):
+        video, lat = pipe(prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
+                          latents=inp["latents"], condition_latent=inp["condition_latent"], mask=inp["mask"], **kw)
+        if world > 1:     # the one collective of the path: all-gather of the decoded frames (uint8, 12.6 MB per clip)
+            u8 = video[0].mul(127.5).add_(127.5).clamp_(0, 255).to(torch.uint8)
+            dist.all_gather_into_tensor(gather_buf, u8.unsqueeze(0).contiguous())
+        return video, lat
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_clip(devin)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        video, lat = one_clip(devin)
+    e1.record()
+    barrier()
+    t_dev = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev, dtype=torch.float64)
+    launches = _lib.launch_count() - l0
+    if pipe.use_cuda_graph:            # python-side calls happen once at capture; every replay re-launches them
+        per_step = getattr(pipe, "graph_kernels_per_step", None)
+        launches = launches + (per_step or 0) * STEPS_DDIM * args.steps
+    finite = bool(torch.isfinite(lat.float()).all().item())
+
+    # ---- e2e: host inputs (pinned) copied in every step, decoded video read back to the host every step
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    host_out = torch.empty((1, 3, FRAMES, HW, HW), dtype=torch.float32).pin_memory()
+    d2h = host_out.numel() * host_out.element_size()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        video, _ = one_clip(inp)
+        host_out.copy_(video, non_blocking=True)
+    e3.record()
+    barrier()
+    sampler.stop_flag = True
+    t_e2e = torch.tensor([e2.elapsed_time(e3) / 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    total_frames = FRAMES * world * args.steps
+    value = total_frames / t_dev.item()
+    e2e_v = total_frames / t_e2e.item()
+
+    roof = None
+    unet_ms = None
+    cpu_base = None
+    if rank == 0:
+        # ---- per-kernel timing of one eager UNet forward: every tcgen05 implicit-GEMM launch with CUDA events
+        peak_tf, peak_hbm, peak_src = _peaks()
+        pipe.use_cuda_graph = False
+        sample = devin["latents"].expand(2, -1, -1, -1, -1)
+        cond2 = torch.cat([devin["condition_latent"]] * 2)
+        ehs = torch.cat([devin["negative_prompt_embeds"], devin["prompt_embeds"]])
+        tt = torch.tensor([500.0], device=dev)
+        mot = torch.tensor([4.0], device=dev)
+        for _ in range(2):
+            pipe.unet(sample, tt, ehs, condition_latent=cond2, mask=devin["mask"], motion=mot, _raw_eps=True)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(3):
+            pipe.unet(sample, tt, ehs, condition_latent=cond2, mask=devin["mask"], motion=mot, _raw_eps=True)
+        f1.record()
+        torch.cuda.synchronize()
+        unet_ms = f0.elapsed_time(f1) / 3
+        ops.IGEMM_PROFILE = []
+        pipe.unet(sample, tt, ehs, condition_latent=cond2, mask=devin["mask"], motion=mot, _raw_eps=True)
+        torch.cuda.synchronize()
+        prof = ops.IGEMM_PROFILE
+        ops.IGEMM_PROFILE = None
+        tot_ms = sum(p["ev"][0].elapsed_time(p["ev"][1]) for p in prof)
+        tot_fl = sum(p["flops"] for p in prof)
+        achieved = tot_fl / (tot_ms * 1e-3) / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("igemm_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roof = {"bound": "tensor", "kernel": "aab::igemm_kernel (tcgen05 implicit GEMM, all launches of one UNet forward)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                "peak_source": peak_src, "launches": len(prof), "algorithmic_tflop_per_forward": tot_fl / 1e12,
+                "igemm_ms_per_forward": tot_ms, "avg_launch_us": tot_ms * 1e3 / max(1, len(prof))}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                threads = os.cpu_count() or 1
+                _, fwd, f_sample, desc = _oracle_unet_sample(threads)
+                ts = fwd(f_sample, LAT)
+                cpu_base = {"value": cpu_frames_per_sec(ts, f_sample), "unit": UNIT, "cores": threads, "kind": "port",
+                            "sample": desc + f" ({ts:.1f} s); x(17/T) x 2 (CFG) x 50 steps, extrapolated"}
+            except Exception as ex:      # the oracle is a checker; never let it break the bench line
+                cpu_base = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": t_dev.item() / args.steps * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "config2: LatentToVideoPipeline.__call__ 16x512x512, 50 DDIM steps, CFG 9, "
+                                       "random-init UNet3D (1.41B) + SD VAE, 1 clip per GPU",
+                           "l2_policy": "working set per UNet forward (2.8 GB weights + activations) >> 126 MB L2",
+                           "cuda_graph": not args.no_graph, "finite_output": finite,
+                           "parallelism": f"clips x{world} (prompt-sharded), 1 NCCL all-gather of frames" if world > 1
+                           else "single GPU"},
+                "unet_fwd_ms_per_step": unet_ms, "clocks": sampler.summary(),
+                "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_base}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="disable CUDA-graph replay of the denoising step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

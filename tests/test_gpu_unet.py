@@ -45,7 +45,7 @@ def _run_case(cfg, dtype, b, f, hw, lk, timestep=500, motion=4.0, trace=True):
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     oracle, ours = _models(cfg, dtype)
-    inp = _inputs(b, f, hw, lk, cfg["cross_attention_dim"], dtype)
+    inp = _inputs(b, f, hw, lk, cfg.get("cross_attention_dim", 1024), dtype)
     mot = torch.tensor([motion], device="cuda")
     captured = {}
     hooks = []
