@@ -94,6 +94,8 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = C.c_int
+    lib.aab_groupnorm_workspace_bytes.argtypes = [C.c_long, C.c_long, C.c_int, C.c_int]
+    lib.aab_groupnorm_workspace_bytes.restype = C.c_long
     _lib = lib
     return lib
 

@@ -26,19 +26,24 @@ struct GnArgs {
   int bf16;
 };
 
-__global__ void gn_stats_kernel(GnArgs a, double* __restrict__ stats /* [S][G][2] */) {
-  extern __shared__ float sh[];   // [2*groups]
+// Deterministic (bitwise reproducible) statistics: fixed-order reductions only.  Each CTA reduces its row chunk to one
+// (sum, sumsq) pair per group and stores it to `partial`; the last CTA of a sample (atomic ticket, self-resetting)
+// adds the chunk partials in index order and publishes mean / rstd.
+__global__ void gn_stats_kernel(GnArgs a, double* __restrict__ partial /* [S][chunks][G][2] */,
+                                float* __restrict__ mean_rstd /* [S][G][2] */, unsigned int* __restrict__ ticket /* [S] */,
+                                float eps) {
+  extern __shared__ float sh[];   // [rpi][C] sums, [rpi][C] squares
+  __shared__ bool is_last;
   const int C = a.C1 + a.C2;
   const int V = C >> 3;
   const int oct = threadIdx.x % V;
   const int rsub = threadIdx.x / V;
   const int rpi = blockDim.x / V;
   const int s = blockIdx.y;
+  const int chunks = gridDim.x;
   const long r0 = static_cast<long>(blockIdx.x) * a.rows_per_cta;
   long r1 = r0 + a.rows_per_cta;
   if (r1 > a.rows) r1 = a.rows;
-  for (int i = threadIdx.x; i < 2 * a.groups; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
   float sum[8], sq[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
@@ -60,20 +65,55 @@ __global__ void gn_stats_kernel(GnArgs a, double* __restrict__ stats /* [S][G][2
       sum[2 * e + 1] += f.y; sq[2 * e + 1] += f.y * f.y;
     }
   }
-  const int cpg = C / a.groups;
+  float* shs = sh;
+  float* shq = sh + rpi * C;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int g = (c0 + j) / cpg;
-    atomicAdd(&sh[2 * g], sum[j]);
-    atomicAdd(&sh[2 * g + 1], sq[j]);
+    shs[rsub * C + c0 + j] = sum[j];
+    shq[rsub * C + c0 + j] = sq[j];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * a.groups; i += blockDim.x)
-    atomicAdd(&stats[static_cast<long>(s) * 2 * a.groups + i], static_cast<double>(sh[i]));
+  const int cpg = C / a.groups;
+  if (threadIdx.x < a.groups) {
+    const int g = threadIdx.x;
+    double ds = 0.0, dq = 0.0;
+    for (int r = 0; r < rpi; ++r)
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        ds += static_cast<double>(shs[r * C + c]);
+        dq += static_cast<double>(shq[r * C + c]);
+      }
+    double* pp = partial + ((static_cast<long>(s) * chunks + blockIdx.x) * a.groups + g) * 2;
+    pp[0] = ds;
+    pp[1] = dq;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&ticket[s], 1u);
+    is_last = (t == static_cast<unsigned int>(chunks - 1));
+    if (is_last) ticket[s] = 0;          // self-reset for the next launch
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x < a.groups) {
+    __threadfence();
+    const int g = threadIdx.x;
+    double ds = 0.0, dq = 0.0;
+    const volatile double* pp = partial + (static_cast<long>(s) * chunks * a.groups + g) * 2;
+    for (int ch = 0; ch < chunks; ++ch) {
+      ds += pp[static_cast<long>(ch) * a.groups * 2];
+      dq += pp[static_cast<long>(ch) * a.groups * 2 + 1];
+    }
+    const double n = static_cast<double>(a.rows) * cpg;
+    const double m = ds / n;
+    double var = dq / n - m * m;
+    if (var < 0) var = 0;
+    mean_rstd[(static_cast<long>(s) * a.groups + g) * 2] = static_cast<float>(m);
+    mean_rstd[(static_cast<long>(s) * a.groups + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
 }
 
-__global__ void gn_apply_kernel(GnArgs a, const double* __restrict__ stats, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, float eps, int silu, void* __restrict__ y, long ldy) {
+__global__ void gn_apply_kernel(GnArgs a, const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, int silu, void* __restrict__ y, long ldy) {
   const int C = a.C1 + a.C2;
   const int V = C >> 3;
   const int oct = threadIdx.x % V;
@@ -86,18 +126,15 @@ __global__ void gn_apply_kernel(GnArgs a, const double* __restrict__ stats, cons
   const bool bf = a.bf16 != 0;
   const int c0 = oct * 8;
   const int cpg = C / a.groups;
-  const double n = static_cast<double>(a.rows) * cpg;
   float sc[8], sf[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int g = (c0 + j) / cpg;
-    const double m = stats[(static_cast<long>(s) * a.groups + g) * 2] / n;
-    double var = stats[(static_cast<long>(s) * a.groups + g) * 2 + 1] / n - m * m;
-    if (var < 0) var = 0;
-    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float m = mean_rstd[(static_cast<long>(s) * a.groups + g) * 2];
+    const float rstd = mean_rstd[(static_cast<long>(s) * a.groups + g) * 2 + 1];
     const float gm = gamma[c0 + j];
     sc[j] = rstd * gm;
-    sf[j] = beta[c0 + j] - static_cast<float>(m) * rstd * gm;
+    sf[j] = beta[c0 + j] - m * rstd * gm;
   }
   const uint8_t* base;
   long ld;
@@ -210,35 +247,63 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, long lds, void*
 
 using namespace aab;
 
-static int gn_launch_cfg(int C, int* threads, int* rows_per_cta) {
+static int gn_launch_cfg(int C, long samples, long rows, int* threads, int* rows_per_cta, int* chunks) {
   if (C % 8) return AAB_ERR_ARG;
   const int V = C / 8;
   if (V > 1024) return AAB_ERR_ARG;
   int rpi = 256 / V;
   if (rpi < 1) rpi = 1;
   *threads = V * rpi;
-  *rows_per_cta = rpi * 16;
+  // ~4 CTAs per SM in total, at least 4 row-iterations per CTA
+  long want = (4L * 148 + samples - 1) / samples;
+  long maxc = (rows + 4L * rpi - 1) / (4L * rpi);
+  if (want > maxc) want = maxc;
+  if (want < 1) want = 1;
+  long rpc = (rows + want - 1) / want;
+  rpc = ((rpc + rpi - 1) / rpi) * rpi;
+  *rows_per_cta = static_cast<int>(rpc);
+  *chunks = static_cast<int>((rows + rpc - 1) / rpc);
   return AAB_OK;
 }
 
-// stats must hold samples*groups*2 doubles; it is zeroed here.
+// Workspace layout (bytes): [0, 4*samples) tickets (must be zero before the first use; self-resetting afterwards),
+// then mean/rstd floats [samples*groups*2], then double partials [samples*chunks*groups*2].
+extern "C" long aab_groupnorm_workspace_bytes(long samples, long rows, int c, int groups) {
+  int threads, rpc, chunks;
+  if (gn_launch_cfg(c, samples, rows, &threads, &rpc, &chunks)) return -1;
+  long off = ((samples * 4 + 255) / 256) * 256;
+  off += ((samples * groups * 2 * 4 + 255) / 256) * 256;
+  off += samples * chunks * groups * 2 * 8;
+  return off;
+}
+
 extern "C" int aab_groupnorm(const void* x1, long ld1, int c1, const void* x2, long ld2, int c2, long samples, long rows,
                              int groups, const float* gamma, const float* beta, float eps, int silu, void* y, long ldy,
-                             double* stats, int is_bf16, void* stream_) {
+                             void* workspace, int is_bf16, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int C = c1 + c2;
-  if (!x1 || !y || !stats || groups < 1 || C % groups || (c1 % 8) || (c2 % 8) || (ld1 % 8) || (ldy % 8)) return AAB_ERR_ARG;
+  if (!x1 || !y || !workspace || groups < 1 || groups > 256 || C % groups || (c1 % 8) || (c2 % 8) || (ld1 % 8) ||
+      (ldy % 8))
+    return AAB_ERR_ARG;
   if (c2 > 0 && (!x2 || (ld2 % 8))) return AAB_ERR_ARG;
-  int threads, rpc;
-  int r = gn_launch_cfg(C, &threads, &rpc);
+  int threads, rpc, chunks;
+  int r = gn_launch_cfg(C, samples, rows, &threads, &rpc, &chunks);
   if (r) return r;
   GnArgs a;
   a.x1 = x1; a.x2 = x2; a.C1 = c1; a.C2 = c2; a.ld1 = ld1; a.ld2 = ld2; a.rows = rows; a.groups = groups;
   a.rows_per_cta = rpc; a.bf16 = is_bf16;
-  if (cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * samples, stream) != cudaSuccess) return AAB_ERR_CUDA;
-  dim3 grid(static_cast<unsigned>((rows + rpc - 1) / rpc), static_cast<unsigned>(samples));
-  gn_stats_kernel<<<grid, threads, 2 * groups * sizeof(float), stream>>>(a, stats);
-  gn_apply_kernel<<<grid, threads, 0, stream>>>(a, stats, gamma, beta, eps, silu, y, ldy);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(ws);
+  long off = ((samples * 4 + 255) / 256) * 256;
+  float* mean_rstd = reinterpret_cast<float*>(ws + off);
+  off += ((samples * groups * 2 * 4 + 255) / 256) * 256;
+  double* partial = reinterpret_cast<double*>(ws + off);
+  const int rpi = threads / (C / 8);
+  const size_t smem = static_cast<size_t>(2) * rpi * C * sizeof(float);
+  if (smem > 48 * 1024) return AAB_ERR_ARG;
+  dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(samples));
+  gn_stats_kernel<<<grid, threads, smem, stream>>>(a, partial, mean_rstd, ticket, eps);
+  gn_apply_kernel<<<grid, threads, 0, stream>>>(a, mean_rstd, gamma, beta, silu, y, ldy);
   return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }
 

@@ -273,15 +273,16 @@ def temporal_attn_d64(qkv: torch.Tensor, b: int, t: int, hw: int, heads: int, q_
 
 
 # ---------------------------------------------------------------------------------------------- norms
-_stats_cache = {}
+_gn_ws = {}
 
 
-def _stats_buf(device, n):
+def _gn_workspace(device, nbytes):
+    """Zero-initialised (tickets!) workspace per (device, stream); the kernel leaves the tickets at zero."""
     key = (device, torch.cuda.current_stream().cuda_stream)
-    buf = _stats_cache.get(key)
-    if buf is None or buf.numel() < n:
-        buf = torch.empty(max(n, 4096), device=device, dtype=torch.float64)
-        _stats_cache[key] = buf
+    buf = _gn_ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.zeros(max(int(nbytes), 1 << 20), device=device, dtype=torch.uint8)
+        _gn_ws[key] = buf
     return buf
 
 
@@ -292,9 +293,12 @@ def groupnorm(x: torch.Tensor, samples: int, rows: int, gamma: torch.Tensor, bet
     c1 = x.shape[1]
     c2 = 0 if x2 is None else x2.shape[1]
     y = torch.empty((x.shape[0], c1 + c2), device=x.device, dtype=x.dtype)
-    stats = _stats_buf(x.device, samples * groups * 2)
+    need = _lib.load().aab_groupnorm_workspace_bytes(samples, rows, c1 + c2, groups)
+    if need < 0:
+        raise _lib.AabError("aab_groupnorm: unsupported channel count")
+    ws = _gn_workspace(x.device, need)
     _lib.call("aab_groupnorm", _ptr(x), x.stride(0), c1, _ptr(x2), 0 if x2 is None else x2.stride(0), c2, samples, rows,
-              groups, _ptr(gamma), _ptr(beta), eps, int(silu), _ptr(y), y.stride(0), _ptr(stats), bf, _stream())
+              groups, _ptr(gamma), _ptr(beta), eps, int(silu), _ptr(y), y.stride(0), _ptr(ws), bf, _stream())
     return y
 
 
