@@ -44,13 +44,21 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
-template <int BN>
+// EPI: 0 = 16-bit output through swizzled smem staging + TMA store (n_out % 32 == 0);
+//      1 = same with the GEGLU gate (B tile = [values | gates], out = value * gelu(gate));
+//      2 = generic direct-to-global store (any n_out, fp32 or 16-bit output, masked).
+// The epilogue is written as compact loops (no full unrolling): its instruction footprint is executed once per tile by
+// four warps, and a bloated epilogue thrashes the instruction cache when K is small.
+template <int BN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
              const IgemmParams p) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
+  constexpr bool GEGLU = (EPI == 1);
+  constexpr bool DIRECT = (EPI == 2);
+  constexpr int OUT_BN = GEGLU ? BN / 2 : BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;
@@ -65,8 +73,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5;
   const bool bf16 = (p.flags & AAB_F_BF16) != 0;
-  const bool geglu = (p.flags & AAB_F_GEGLU) != 0;
-  const bool direct = (p.flags & AAB_F_DIRECT) != 0;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int kb_per_tap = p.kb_per_tap;
   const int k_iters = p.num_taps * kb_per_tap;
@@ -112,7 +118,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           mt /= p.tiles[i];
         }
         const int bbatch = (p.b_batch_dim >= 0) ? cb[p.b_batch_dim] : 0;
-        const int n0 = geglu ? nt * (BN / 2) : nt * BN;
+        const int n0 = nt * OUT_BN;
         for (int tap = 0; tap < p.num_taps; ++tap) {
           const int o0 = p.tap_off[tap][0], o1 = p.tap_off[tap][1], o2 = p.tap_off[tap][2], o3 = p.tap_off[tap][3],
                     o4 = p.tap_off[tap][4];
@@ -129,12 +135,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               tma_load_5d(smA + s * A_STAGE_BYTES, &tmA2, &full_bar[s], kc - p.Kc1 + o0, cb[0] + o1, cb[1] + o2,
                           cb[2] + o3, cb[3] + o4);
             const int kg = tap * p.Kc + kc;
-            if (!geglu) {
-              tma_load_3d(smB + s * C::B_STAGE_BYTES, &tmB, &full_bar[s], kg, n0, bbatch);
-            } else {
-              tma_load_3d(smB + s * C::B_STAGE_BYTES, &tmB, &full_bar[s], kg, n0, bbatch);
+            tma_load_3d(smB + s * C::B_STAGE_BYTES, &tmB, &full_bar[s], kg, n0, bbatch);
+            if (GEGLU)
               tma_load_3d(smB + s * C::B_STAGE_BYTES + (BN / 2) * 128, &tmB, &full_bar[s], kg, p.N / 2 + n0, bbatch);
-            }
           }
         }
       }
@@ -175,7 +178,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int q = warp & 3;
     const int row = q * 32 + lane_id();           // row inside the 128-row tile == TMEM lane
     const int et = threadIdx.x - 64;              // 0..127
-    const int OUT_BN = geglu ? BN / 2 : BN;
     uint32_t tl = 0;
     uint32_t chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
@@ -189,11 +191,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         cb[i] = (mt % p.tiles[i]) * p.box[i];
         mt /= p.tiles[i];
       }
-      // global row of this thread
-      int rr = row;
       long grow = 0;
       bool rvalid = true;
       {
+        int rr = row;
         int g[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -206,23 +207,25 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int n0 = nt * OUT_BN;
       const float* bias2row =
           (p.bias2 != nullptr && rvalid) ? p.bias2 + (grow / p.rows_per_bias2) * static_cast<long>(p.ld_bias2) : nullptr;
+      const uint8_t* resrow = (p.residual != nullptr && rvalid)
+                                  ? reinterpret_cast<const uint8_t*>(p.residual) + grow * p.ld_res * 2
+                                  : nullptr;
 
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
 
-      for (int c0 = 0; c0 < OUT_BN; c0 += 64, ++chunk_ctr) {
+#pragma unroll 1
+      for (int cc = 0; cc < OUT_BN; cc += 32) {
+        const int col = n0 + cc;                  // global output column of this 32-wide group
+        const int half = (cc >> 5) & 1;
         uint8_t* stage_buf = smO + (chunk_ctr & 1) * OUT_CHUNK_BYTES;
-        if (!direct) {
+        if (!DIRECT && half == 0) {
           // the TMA store that used this staging buffer two chunks ago must have finished reading it
           if (et == 0) tma_store_wait_read<1>();
           named_bar_sync(1, 128);
         }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int cc = c0 + h * 32;             // column inside the tile
-          if (cc >= OUT_BN) break;
-          const int col = n0 + cc;                // global output column
+        if (col < p.n_out) {                      // warp-uniform
           float v[32];
           {
             uint32_t r[32];
@@ -231,38 +234,44 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           }
-          float gte[32];
-          if (geglu) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_acc + BN / 2 + cc, r);
-            tmem_ld_wait();
+          if (!DIRECT) {
+            // ---------------- fast path: n_out % 32 == 0, everything vectorised
+            if (p.bias != nullptr) {
+              const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) gte[j] = __uint_as_float(r[j]);
-          }
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (col + j < p.n_out) {
-                v[j] += __ldg(p.bias + col + j);
-                if (geglu) gte[j] += __ldg(p.bias + p.N / 2 + col + j);
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 b = __ldg(bp + j4);
+                v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
               }
             }
-          }
-          if (geglu) {
+            if (GEGLU) {
+              uint32_t r[32];
+              tmem_ld_32x32(tmem_acc + BN / 2 + cc, r);
+              tmem_ld_wait();
+              const float4* gp = reinterpret_cast<const float4*>(p.bias + p.N / 2 + col);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] * gelu_erf_f(gte[j]);
-          }
-          if (bias2row != nullptr) {
+              for (int j4 = 0; j4 < 8; ++j4) {
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias != nullptr) b = __ldg(gp + j4);
+                v[j4 * 4 + 0] *= gelu_erf_f(__uint_as_float(r[j4 * 4 + 0]) + b.x);
+                v[j4 * 4 + 1] *= gelu_erf_f(__uint_as_float(r[j4 * 4 + 1]) + b.y);
+                v[j4 * 4 + 2] *= gelu_erf_f(__uint_as_float(r[j4 * 4 + 2]) + b.z);
+                v[j4 * 4 + 3] *= gelu_erf_f(__uint_as_float(r[j4 * 4 + 3]) + b.w);
+              }
+            }
+            if (bias2row != nullptr) {
+              const float4* bp = reinterpret_cast<const float4*>(bias2row + col);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col + j < p.n_out) v[j] += __ldg(bias2row + col + j);
-          }
-          if (p.residual != nullptr && rvalid) {
-            const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.residual) + (grow * p.ld_res + col) * 2;
-            if (col + 32 <= p.n_out && (p.ld_res % 8) == 0) {
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 b = __ldg(bp + j4);
+                v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
+              }
+            }
+            if (resrow != nullptr) {
+              const uint4* rp = reinterpret_cast<const uint4*>(resrow + col * 2);
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + j4);
+                const uint4 u = __ldg(rp + j4);
                 const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -271,15 +280,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                   v[j4 * 8 + e * 2 + 1] += f.y;
                 }
               }
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (col + j < p.n_out) v[j] += load_elem(p.residual, grow * p.ld_res + col + j, bf16);
             }
-          }
+            if (p.act == AAB_ACT_SILU) {          // (GELU as a plain activation takes the generic path)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act) * p.out_scale;
-
-          if (!direct) {
+              for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+            }
+            if (p.out_scale != 1.0f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
+            }
             // 16-bit pack into the 128B-swizzled staging tile: row r, 16-byte chunk c -> r*128 + ((c ^ (r&7))*16)
             uint8_t* rowp = stage_buf + row * 128;
 #pragma unroll
@@ -289,45 +298,44 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               u.y = pack2(v[j4 * 8 + 2], v[j4 * 8 + 3], bf16);
               u.z = pack2(v[j4 * 8 + 4], v[j4 * 8 + 5], bf16);
               u.w = pack2(v[j4 * 8 + 6], v[j4 * 8 + 7], bf16);
-              const int chunk = h * 4 + j4;
+              const int chunk = half * 4 + j4;
               *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row & 7)) << 4)) = u;
             }
-          } else if (rvalid) {
-            if (p.flags & AAB_F_OUT_F32) {
-              float* op = reinterpret_cast<float*>(p.out) + grow * p.ld_out + col;
-              for (int j = 0; j < 32; ++j)
-                if (col + j < p.n_out) op[j] = v[j];
-            } else if (col + 32 <= p.n_out && (p.ld_out % 8) == 0) {
-              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + (grow * p.ld_out + col) * 2);
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                uint4 u;
-                u.x = pack2(v[j4 * 8 + 0], v[j4 * 8 + 1], bf16);
-                u.y = pack2(v[j4 * 8 + 2], v[j4 * 8 + 3], bf16);
-                u.z = pack2(v[j4 * 8 + 4], v[j4 * 8 + 5], bf16);
-                u.w = pack2(v[j4 * 8 + 6], v[j4 * 8 + 7], bf16);
-                op[j4] = u;
+          } else {
+            // ---------------- generic path: masked, any n_out, fp32 or 16-bit output, straight to global memory
+            const int nv = (p.n_out - col < 32) ? (p.n_out - col) : 32;
+#pragma unroll 1
+            for (int j = 0; j < 32; ++j) {
+              // v[] is indexed dynamically here on purpose (compact code); it lives in local memory on this path
+              if (j < nv) {
+                float x = v[j];
+                if (p.bias != nullptr) x += __ldg(p.bias + col + j);
+                if (bias2row != nullptr) x += __ldg(bias2row + col + j);
+                if (resrow != nullptr) x += load_elem(resrow, col + j, bf16);
+                x = apply_act(x, p.act) * p.out_scale;
+                if (rvalid) {
+                  if (p.flags & AAB_F_OUT_F32) reinterpret_cast<float*>(p.out)[grow * p.ld_out + col + j] = x;
+                  else store_elem(p.out, grow * p.ld_out + col + j, x, bf16);
+                }
               }
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (col + j < p.n_out) store_elem(p.out, grow * p.ld_out + col + j, v[j], bf16);
             }
           }
         }
-        if (!direct) {
+        if (!DIRECT && (half == 1 || cc + 32 >= OUT_BN)) {
           fence_proxy_async_smem();
           named_bar_sync(1, 128);
-          if (et == 0) {
-            tma_store_5d(&tmD, stage_buf, n0 + c0, cb[0], cb[1], cb[2], cb[3]);
+          if (et == 0 && (col - half * 32) < p.n_out) {
+            tma_store_5d(&tmD, stage_buf, col - half * 32, cb[0], cb[1], cb[2], cb[3]);
             tma_store_commit();
           }
+          ++chunk_ctr;
         }
       }
       // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
     }
-    if (!direct && et == 0) tma_store_wait_all<0>();
+    if (!DIRECT && et == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -387,20 +395,20 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int BN>
+template <int BN, int EPI>
 static int launch_bn(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& d,
                      const IgemmParams& p, int max_ctas, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg<BN>::SMEM_BYTES);
     if (e != cudaSuccess) return AAB_ERR_CUDA;
     attr_set = true;
   }
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  igemm_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(a, a2, b, d, p);
+  igemm_kernel<BN, EPI><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(a, a2, b, d, p);
   return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }
 
@@ -417,8 +425,10 @@ extern "C" int aab_igemm(const AabIgemmDesc* d, void* stream_) {
   if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return AAB_ERR_ARG;
   bool direct = (d->flags & AAB_F_DIRECT) != 0;
   const int n_out = geglu ? d->n / 2 : d->n;
-  if (bn == 32 || (d->ld_out % 8) != 0 || (d->flags & AAB_F_OUT_F32)) direct = true;
-  if (geglu && bn < 128) return AAB_ERR_ARG;   // output tile must cover whole 64-column store boxes
+  if (bn == 32 || (d->ld_out % 8) != 0 || (n_out % 32) != 0 || (d->flags & AAB_F_OUT_F32)) direct = true;
+  if (geglu && (bn < 128 || direct)) return AAB_ERR_ARG;   // output tile must cover whole 64-column store boxes
+  if (d->residual && (d->ld_res % 8) != 0 && !direct) direct = true;
+  if (d->act == AAB_ACT_GELU && !geglu) direct = true;
   if (d->num_taps < 1 || d->num_taps > AAB_MAX_TAPS) return AAB_ERR_ARG;
   if (d->kc % 8 != 0) return AAB_ERR_ARG;
   if (d->a2 && (d->kc1 % 64 != 0)) return AAB_ERR_ARG;
@@ -491,11 +501,22 @@ extern "C" int aab_igemm(const AabIgemmDesc* d, void* stream_) {
   } else {
     tmD = tmB;
   }
+  if (direct) {
+    switch (bn) {
+      case 32: return launch_bn<32, 2>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
+      case 64: return launch_bn<64, 2>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
+      case 128: return launch_bn<128, 2>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
+      default: return launch_bn<256, 2>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
+    }
+  }
+  if (geglu) {
+    if (bn == 128) return launch_bn<128, 1>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
+    return launch_bn<256, 1>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
+  }
   switch (bn) {
-    case 32: return launch_bn<32>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
-    case 64: return launch_bn<64>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
-    case 128: return launch_bn<128>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
-    default: return launch_bn<256>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
+    case 64: return launch_bn<64, 0>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
+    case 128: return launch_bn<128, 0>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
+    default: return launch_bn<256, 0>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
   }
 }
 

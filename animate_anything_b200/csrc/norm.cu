@@ -158,60 +158,77 @@ __global__ void gn_apply_kernel(GnArgs a, const float* __restrict__ mean_rstd, c
   }
 }
 
-// one warp per row; C % 8 == 0, C <= 2048
-__global__ void layernorm_kernel(const void* __restrict__ x, long ldx, void* __restrict__ y, long ldy,
-                                 const float* __restrict__ gamma, const float* __restrict__ beta, long rows, int C,
-                                 float eps, int bf16) {
+// One warp handles R consecutive rows at a time (all loads of the R rows are issued before any reduction, so that
+// enough bytes are in flight per SM); OPL = 16-byte octets per lane = ceil(C/8/32).  C % 8 == 0, C <= 2048.
+template <int OPL, int R>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const void* __restrict__ x, long ldx, void* __restrict__ y, long ldy, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, long rows, int C, float eps, int bf16) {
   const int lane = threadIdx.x & 31;
-  const long row = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const long warp_global = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long row0 = warp_global * R;
+  if (row0 >= rows) return;
   const bool bf = bf16 != 0;
   const int V = C >> 3;
-  float v[8][8];
-  float sum = 0.f;
+  uint4 raw[R][OPL];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int o = lane + i * 32;
-    if (o < V) {
-      const uint4 u = ldg16(reinterpret_cast<const uint8_t*>(x) + (row * ldx + o * 8) * 2);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  for (int r = 0; r < R; ++r) {
+#pragma unroll
+    for (int i = 0; i < OPL; ++i) {
+      const int o = lane + i * 32;
+      raw[r][i] = make_uint4(0, 0, 0, 0);
+      if (o < V && row0 + r < rows)
+        raw[r][i] = ldg16(reinterpret_cast<const uint8_t*>(x) + ((row0 + r) * ldx + o * 8) * 2);
+    }
+  }
+  const float invc = 1.0f / C;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (row0 + r >= rows) break;
+    float v[OPL][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < OPL; ++i) {
+      const uint32_t w[4] = {raw[r][i].x, raw[r][i].y, raw[r][i].z, raw[r][i].w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 f = unpack2(w[e], bf);
         v[i][2 * e] = f.x; v[i][2 * e + 1] = f.y;
-        sum += f.x + f.y;
+        sum += f.x + f.y;                 // lanes beyond V hold zeros
       }
     }
-  }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-  const float mean = sum / C;
-  float sq = 0.f;
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const float mean = sum * invc;
+    float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int o = lane + i * 32;
-    if (o < V) {
+    for (int i = 0; i < OPL; ++i) {
+      if (lane + i * 32 < V) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; sq += d * d; }
-    }
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
-  const float rstd = rsqrtf(sq / C + eps);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int o = lane + i * 32;
-    if (o < V) {
-      uint32_t ow[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int c = o * 8 + 2 * e;
-        const float a0 = (v[i][2 * e] - mean) * rstd * gamma[c] + beta[c];
-        const float a1 = (v[i][2 * e + 1] - mean) * rstd * gamma[c + 1] + beta[c + 1];
-        ow[e] = pack2(a0, a1, bf);
+        for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; sq += d * d; }
       }
-      *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y) + (row * ldy + o * 8) * 2) =
-          make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    const float rstd = rsqrtf(sq * invc + eps);
+#pragma unroll
+    for (int i = 0; i < OPL; ++i) {
+      const int o = lane + i * 32;
+      if (o < V) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + o * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + o * 8) + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + o * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + o * 8) + 1);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          ow[e] = pack2((v[i][2 * e] - mean) * rstd * gg[2 * e] + bb[2 * e],
+                        (v[i][2 * e + 1] - mean) * rstd * gg[2 * e + 1] + bb[2 * e + 1], bf);
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y) + ((row0 + r) * ldy + o * 8) * 2) =
+            make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
     }
   }
 }
@@ -307,13 +324,24 @@ extern "C" int aab_groupnorm(const void* x1, long ld1, int c1, const void* x2, l
   return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }
 
+template <int OPL, int R>
+static void launch_ln(const void* x, long ldx, void* y, long ldy, const float* gamma, const float* beta, long rows, int c,
+                      float eps, int is_bf16, cudaStream_t stream) {
+  const int wpb = 8;
+  const long warps = (rows + R - 1) / R;
+  layernorm_kernel<OPL, R><<<static_cast<unsigned>((warps + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+      x, ldx, y, ldy, gamma, beta, rows, c, eps, is_bf16);
+}
+
 extern "C" int aab_layernorm(const void* x, long ldx, void* y, long ldy, const float* gamma, const float* beta,
                              long rows, int c, float eps, int is_bf16, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!x || !y || (c % 8) || c > 2048 || (ldx % 8) || (ldy % 8)) return AAB_ERR_ARG;
-  const int wpb = 8;
-  layernorm_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(x, ldx, y, ldy, gamma, beta,
-                                                                                         rows, c, eps, is_bf16);
+  const int V = c / 8;
+  if (V <= 64) launch_ln<2, 4>(x, ldx, y, ldy, gamma, beta, rows, c, eps, is_bf16, stream);
+  else if (V <= 96) launch_ln<3, 4>(x, ldx, y, ldy, gamma, beta, rows, c, eps, is_bf16, stream);
+  else if (V <= 160) launch_ln<5, 2>(x, ldx, y, ldy, gamma, beta, rows, c, eps, is_bf16, stream);
+  else launch_ln<8, 1>(x, ldx, y, ldy, gamma, beta, rows, c, eps, is_bf16, stream);
   return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }
 
