@@ -171,19 +171,23 @@ class LatentToVideoPipeline:
             mask = mask.to(dtype)
         motion_dev = None if motion is None else torch.tensor(motion, dtype=torch.float32, device=device).reshape(-1)
         x0_hist = torch.zeros(latents.shape, dtype=torch.float32, device=device) if needs_hist else None
-        buf = [latents, torch.empty_like(latents)]
         kv_cache = {}
 
         if self.use_cuda_graph:
-            latents = self._run_graphed(buf, t_table, ehs, cond2, mask, motion_dev, cfg, float(guidance_scale), coef,
-                                        x0_hist, kv_cache, callback, callback_steps, ts_list)
+            latents = self._run_graphed([latents], t_table, ehs, cond2, mask, motion_dev, cfg, float(guidance_scale),
+                                        coef, x0_hist, kv_cache, callback, callback_steps, ts_list)
         else:
+            # ping-pong between two scratch buffers; the caller's `latents` tensor is only ever read
+            buf = [torch.empty_like(latents), torch.empty_like(latents)]
+            src = latents
             for i, t in enumerate(ts_list):
-                self._one_step(buf[i & 1], buf[(i + 1) & 1], t_table[i: i + 1], ehs, cond2, mask, motion_dev, cfg,
+                dst = buf[i & 1]
+                self._one_step(src, dst, t_table[i: i + 1], ehs, cond2, mask, motion_dev, cfg,
                                float(guidance_scale), coef[i], None, x0_hist, kv_cache)
+                src = dst
                 if callback is not None and i % callback_steps == 0:
-                    callback(i, t, buf[(i + 1) & 1])
-            latents = buf[len(ts_list) & 1]
+                    callback(i, t, dst)
+            latents = src
 
         video_tensor = self.decode_latents(latents)
         video = video_tensor if output_type == "pt" else tensor2vid(video_tensor)
