@@ -27,6 +27,12 @@ constexpr int FA_SMEM_BYTES = 2 * FA_TILE_BYTES               /* Q A,B */
                               + 2 * 2 * FA_TILE_BYTES          /* P A,B: two 64-key halves each */
                               + 1024 + 256;
 
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct FaParams {
   int Lq, Lk, heads, kv_batch_div;
   int q_col0, k_col0, v_col0;
@@ -182,50 +188,83 @@ flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       mbar_wait(&s_full[tile], jph);
       tc_fence_after();
       const int kbase = j * 128;
-      const bool need_mask = (kbase + 128 > p.Lk);
-      // pass 1: row maximum
-      float mx = -INFINITY;
+      const int valid = p.Lk - kbase;               // keys of this block that exist (>= 128: no masking needed)
+      float alpha, lsum = 0.f;
+      if (valid >= 128) {
+        // ---------------- common case: no per-element predicates
+        float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_s + c * 32, r);
-        tmem_ld_wait();
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_s + c * 32, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float v = __uint_as_float(r[i]);
-          if (need_mask && (kbase + c * 32 + i >= p.Lk)) v = -INFINITY;
-          mx = fmaxf(mx, v);
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
         }
-      }
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float alpha = exp2f(m_run - m_new);
-      m_run = m_new;
-      // pass 2: probabilities -> shared memory (A operand of P.V), row sum
-      float lsum = 0.f;
+        const float m_new = fmaxf(m_run, mx * p.scale_log2);
+        alpha = fast_exp2(m_run - m_new);
+        m_run = m_new;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_s + c * 32, r);
-        tmem_ld_wait();
-        float pv[32];
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_s + c * 32, r);
+          tmem_ld_wait();
+          uint8_t* hp = prow + (c >> 1) * FA_TILE_BYTES;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float v = __uint_as_float(r[i]);
-          float e = exp2f(fmaf(v, p.scale_log2, -m_new));
-          if (need_mask && (kbase + c * 32 + i >= p.Lk)) e = 0.f;
-          pv[i] = e;
-          lsum += e;
+          for (int g = 0; g < 4; ++g) {
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              e[i] = fast_exp2(fmaf(__uint_as_float(r[g * 8 + i]), p.scale_log2, -m_new));
+              lsum += e[i];
+            }
+            uint4 u;
+            u.x = pack2(e[0], e[1], bf16);
+            u.y = pack2(e[2], e[3], bf16);
+            u.z = pack2(e[4], e[5], bf16);
+            u.w = pack2(e[6], e[7], bf16);
+            const int chunk = (c & 1) * 4 + g;
+            *reinterpret_cast<uint4*>(hp + ((chunk ^ (row & 7)) << 4)) = u;
+          }
         }
-        uint8_t* hp = prow + (c >> 1) * FA_TILE_BYTES;
+      } else {
+        // ---------------- tail block: keys >= valid are masked to -inf / 0
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_s + c * 32, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 u;
-          u.x = pack2(pv[g * 8 + 0], pv[g * 8 + 1], bf16);
-          u.y = pack2(pv[g * 8 + 2], pv[g * 8 + 3], bf16);
-          u.z = pack2(pv[g * 8 + 4], pv[g * 8 + 5], bf16);
-          u.w = pack2(pv[g * 8 + 6], pv[g * 8 + 7], bf16);
-          const int chunk = (c & 1) * 4 + g;
-          *reinterpret_cast<uint4*>(hp + ((chunk ^ (row & 7)) << 4)) = u;
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
+        const float m_new = fmaxf(m_run, mx * p.scale_log2);
+        alpha = fast_exp2(m_run - m_new);
+        m_run = m_new;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_s + c * 32, r);
+          tmem_ld_wait();
+          uint8_t* hp = prow + (c >> 1) * FA_TILE_BYTES;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float x = fast_exp2(fmaf(__uint_as_float(r[g * 8 + i]), p.scale_log2, -m_new));
+              e[i] = (c * 32 + g * 8 + i < valid) ? x : 0.f;
+              lsum += e[i];
+            }
+            uint4 u;
+            u.x = pack2(e[0], e[1], bf16);
+            u.y = pack2(e[2], e[3], bf16);
+            u.z = pack2(e[4], e[5], bf16);
+            u.w = pack2(e[6], e[7], bf16);
+            const int chunk = (c & 1) * 4 + g;
+            *reinterpret_cast<uint4*>(hp + ((chunk ^ (row & 7)) << 4)) = u;
+          }
         }
       }
       l_run = l_run * alpha + lsum;
@@ -273,27 +312,36 @@ flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
 // ------------------------------------------------------------------------------------------------ temporal
 // q/k/v rows of frame t of (b, position pos): base + ((b*T + t)*HW + pos)*ld + col0 + head*64
+// K and V of one (b, position, head) are unpacked to fp32 in shared memory once (T x 64 each); lane i < T owns query
+// row i: scores, softmax and P.V stay in registers, K/V reads are warp-wide broadcasts (LDS.128, no bank conflicts).
 template <bool BF16>
 __global__ void __launch_bounds__(128)
 temporal_attn_d64_kernel(const void* __restrict__ qkv, long ld, int q_col0, int k_col0, int v_col0, void* __restrict__ out,
                          long ld_out, int B, int T, int HW, int heads, float scale) {
-  __shared__ uint32_t sK[4][32][32];   // [warp][frame][channel pair], raw 16-bit pairs
-  __shared__ uint32_t sV[4][32][32];
+  extern __shared__ float4 sm4[];          // [4 warps][2 (K,V)][T][16 float4]
   const int w = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const long item = static_cast<long>(blockIdx.x) * 4 + w;
   const long total = static_cast<long>(B) * HW * heads;
   if (item >= total) return;
+  float4* sK = sm4 + static_cast<size_t>(w) * 2 * T * 16;
+  float4* sV = sK + static_cast<size_t>(T) * 16;
   const int head = item % heads;
   const long bp = item / heads;
   const int pos = bp % HW;
   const int b = bp / HW;
-  for (int t = 0; t < T; ++t) {
+  // 16 lanes cover one 128-byte row (8 bytes = 4 channels per lane); two rows (frames) per iteration
+  const int sub = lane & 15;
+  for (int t = lane >> 4; t < T; t += 2) {
     const long rowi = (static_cast<long>(b) * T + t) * HW + pos;
-    sK[w][t][lane] = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(qkv) +
-                                                        (rowi * ld + k_col0 + head * 64 + lane * 2) * 2);
-    sV[w][t][lane] = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(qkv) +
-                                                        (rowi * ld + v_col0 + head * 64 + lane * 2) * 2);
+    const uint2 ku = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(qkv) +
+                                                     (rowi * ld + k_col0 + head * 64 + sub * 4) * 2);
+    const uint2 vu = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(qkv) +
+                                                     (rowi * ld + v_col0 + head * 64 + sub * 4) * 2);
+    const float2 k0 = unpack2(ku.x, BF16), k1 = unpack2(ku.y, BF16);
+    const float2 v0 = unpack2(vu.x, BF16), v1 = unpack2(vu.y, BF16);
+    sK[t * 16 + sub] = make_float4(k0.x, k0.y, k1.x, k1.y);
+    sV[t * 16 + sub] = make_float4(v0.x, v0.y, v1.x, v1.y);
   }
   __syncwarp();
   if (lane < T) {
@@ -320,10 +368,12 @@ temporal_attn_d64_kernel(const void* __restrict__ qkv, long ld, int q_col0, int 
       if (t < T) {
         float acc = 0.f;
 #pragma unroll
-        for (int d2 = 0; d2 < 32; ++d2) {
-          const float2 kf = unpack2(sK[w][t][d2], BF16);
-          acc = fmaf(q[d2 * 2], kf.x, acc);
-          acc = fmaf(q[d2 * 2 + 1], kf.y, acc);
+        for (int d4 = 0; d4 < 16; ++d4) {
+          const float4 kf = sK[t * 16 + d4];
+          acc = fmaf(q[d4 * 4], kf.x, acc);
+          acc = fmaf(q[d4 * 4 + 1], kf.y, acc);
+          acc = fmaf(q[d4 * 4 + 2], kf.z, acc);
+          acc = fmaf(q[d4 * 4 + 3], kf.w, acc);
         }
         s[t] = acc;
         mx = fmaxf(mx, acc);
@@ -336,7 +386,7 @@ temporal_attn_d64_kernel(const void* __restrict__ qkv, long ld, int q_col0, int 
       l += s[t];
     }
     const float inv = 1.f / l;
-    float o[64];
+    float* o = q;                          // reuse the query registers for the output row
 #pragma unroll
     for (int d = 0; d < 64; ++d) o[d] = 0.f;
 #pragma unroll
@@ -344,10 +394,12 @@ temporal_attn_d64_kernel(const void* __restrict__ qkv, long ld, int q_col0, int 
       if (t < T) {
         const float pt = s[t] * inv;
 #pragma unroll
-        for (int d2 = 0; d2 < 32; ++d2) {
-          const float2 vf = unpack2(sV[w][t][d2], BF16);
-          o[d2 * 2] = fmaf(pt, vf.x, o[d2 * 2]);
-          o[d2 * 2 + 1] = fmaf(pt, vf.y, o[d2 * 2 + 1]);
+        for (int d4 = 0; d4 < 16; ++d4) {
+          const float4 vf = sV[t * 16 + d4];
+          o[d4 * 4] = fmaf(pt, vf.x, o[d4 * 4]);
+          o[d4 * 4 + 1] = fmaf(pt, vf.y, o[d4 * 4 + 1]);
+          o[d4 * 4 + 2] = fmaf(pt, vf.z, o[d4 * 4 + 2]);
+          o[d4 * 4 + 3] = fmaf(pt, vf.w, o[d4 * 4 + 3]);
         }
       }
     }
@@ -423,11 +475,18 @@ extern "C" int aab_temporal_attn_d64(const void* qkv, long ld, int q_col0, int k
   if (!qkv || !out || t < 1 || t > 32 || (ld % 8) || (ld_out % 8)) return AAB_ERR_ARG;
   const long total = static_cast<long>(b) * hw * heads;
   const int grid = static_cast<int>((total + 3) / 4);
+  const size_t smem = static_cast<size_t>(4) * 2 * t * 64 * sizeof(float);     // 34 KiB at T = 17, 64 KiB at T = 32
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(temporal_attn_d64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    cudaFuncSetAttribute(temporal_attn_d64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    attr_set = true;
+  }
   if (is_bf16)
-    temporal_attn_d64_kernel<true><<<grid, 128, 0, stream>>>(qkv, ld, q_col0, k_col0, v_col0, out, ld_out, b, t, hw,
-                                                             heads, scale);
+    temporal_attn_d64_kernel<true><<<grid, 128, smem, stream>>>(qkv, ld, q_col0, k_col0, v_col0, out, ld_out, b, t, hw,
+                                                                heads, scale);
   else
-    temporal_attn_d64_kernel<false><<<grid, 128, 0, stream>>>(qkv, ld, q_col0, k_col0, v_col0, out, ld_out, b, t, hw,
-                                                              heads, scale);
+    temporal_attn_d64_kernel<false><<<grid, 128, smem, stream>>>(qkv, ld, q_col0, k_col0, v_col0, out, ld_out, b, t, hw,
+                                                                 heads, scale);
   return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }

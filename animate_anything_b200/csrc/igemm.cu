@@ -26,7 +26,8 @@ namespace aab {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;       // 16 KiB
-constexpr int OUT_CHUNK_BYTES = BM * 64 * 2;     // one 64-column output chunk, 16 KiB
+constexpr int OUT_CHUNK_BYTES = BM * 32 * 2;     // one 32-column output chunk (64-byte rows, SWIZZLE_64B), 8 KiB
+constexpr int NUM_OUT_BUFS = 4;                  // staging ring: residual prefetch (TMA load) + output (TMA store)
 constexpr int NUM_THREADS = 192;                 // warp0 TMA, warp1 MMA, warps2-5 epilogue
 
 template <int BN>
@@ -34,8 +35,8 @@ struct Cfg {
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator stages
-  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 2 * OUT_CHUNK_BYTES + 1024 /*align*/ +
-                                    256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + NUM_OUT_BUFS * OUT_CHUNK_BYTES +
+                                    1024 /*align*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -53,7 +54,7 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
-             const IgemmParams p) {
+             const __grid_constant__ CUtensorMap tmR, const IgemmParams p) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   constexpr bool GEGLU = (EPI == 1);
@@ -64,12 +65,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* smA = smem;
   uint8_t* smB = smA + STAGES * A_STAGE_BYTES;
   uint8_t* smO = smB + STAGES * C::B_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smO + 2 * OUT_CHUNK_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smO + NUM_OUT_BUFS * OUT_CHUNK_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* res_bar = bars + 2 * STAGES + 4;     // [NUM_OUT_BUFS] residual chunk landed in staging buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + NUM_OUT_BUFS);
 
   const int warp = threadIdx.x >> 5;
   const bool bf16 = (p.flags & AAB_F_BF16) != 0;
@@ -82,6 +84,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     prefetch_tmap(&tmA2);
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmD);
+    prefetch_tmap(&tmR);
   }
   if (warp == 1) {
     if (elect_one()) {
@@ -93,6 +96,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_init(&tfull_bar[i], 1);
         mbar_init(&tempty_bar[i], 128);
       }
+      for (int i = 0; i < NUM_OUT_BUFS; ++i) mbar_init(&res_bar[i], 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -175,11 +179,42 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else {
     // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
+    // Output leaves in 32-column chunks through a ring of 4 staging buffers (64-byte rows, SWIZZLE_64B).  When a
+    // residual is added, its chunk is TMA-loaded into the SAME staging buffer two chunks ahead (also across tile
+    // boundaries), so each thread finds its residual piece exactly where it will write its output piece: no
+    // latency-exposed global loads in the epilogue, one named barrier per chunk.
     const int q = warp & 3;
     const int row = q * 32 + lane_id();           // row inside the 128-row tile == TMEM lane
     const int et = threadIdx.x - 64;              // 0..127
+    constexpr int CPT = OUT_BN / 32;              // chunks per tile
+    const bool has_res = !DIRECT && (p.residual != nullptr);
     uint32_t tl = 0;
-    uint32_t chunk_ctr = 0;
+    uint32_t gch = 0;                             // global chunk counter of this CTA
+    uint32_t res_phase = 0;                       // per staging buffer phase bits
+
+    auto issue_res_load = [&](uint32_t gg) {      // called by et == 0 only
+      const uint32_t tseq = gg / CPT;
+      const long tile2 = static_cast<long>(blockIdx.x) + static_cast<long>(tseq) * gridDim.x;
+      if (tile2 >= num_tiles) return;
+      const int nt2 = static_cast<int>(tile2 % p.num_n_tiles);
+      int mt2 = static_cast<int>(tile2 / p.num_n_tiles);
+      int c2[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        c2[i] = (mt2 % p.tiles[i]) * p.box[i];
+        mt2 /= p.tiles[i];
+      }
+      const int col2 = nt2 * OUT_BN + static_cast<int>(gg % CPT) * 32;
+      if (col2 >= p.n_out) return;
+      const uint32_t b2 = gg & (NUM_OUT_BUFS - 1);
+      mbar_arrive_expect_tx(&res_bar[b2], OUT_CHUNK_BYTES);
+      tma_load_5d(smO + b2 * OUT_CHUNK_BYTES, &tmR, &res_bar[b2], col2, c2[0], c2[1], c2[2], c2[3]);
+    };
+    if (has_res && et == 0) {
+      issue_res_load(0);
+      issue_res_load(1);
+    }
+
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
       const uint32_t as = tl & 1;
       const uint32_t aph = (tl >> 1) & 1;
@@ -207,24 +242,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int n0 = nt * OUT_BN;
       const float* bias2row =
           (p.bias2 != nullptr && rvalid) ? p.bias2 + (grow / p.rows_per_bias2) * static_cast<long>(p.ld_bias2) : nullptr;
-      const uint8_t* resrow = (p.residual != nullptr && rvalid)
-                                  ? reinterpret_cast<const uint8_t*>(p.residual) + grow * p.ld_res * 2
-                                  : nullptr;
 
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
 
 #pragma unroll 1
-      for (int cc = 0; cc < OUT_BN; cc += 32) {
-        const int col = n0 + cc;                  // global output column of this 32-wide group
-        const int half = (cc >> 5) & 1;
-        uint8_t* stage_buf = smO + (chunk_ctr & 1) * OUT_CHUNK_BYTES;
-        if (!DIRECT && half == 0) {
-          // the TMA store that used this staging buffer two chunks ago must have finished reading it
-          if (et == 0) tma_store_wait_read<1>();
-          named_bar_sync(1, 128);
-        }
+      for (int cc = 0; cc < OUT_BN; cc += 32, ++gch) {
+        const int col = n0 + cc;                  // global output column of this 32-wide chunk
+        const uint32_t buf = gch & (NUM_OUT_BUFS - 1);
+        uint8_t* stage_buf = smO + buf * OUT_CHUNK_BYTES;
         if (col < p.n_out) {                      // warp-uniform
           float v[32];
           {
@@ -267,11 +294,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
               }
             }
-            if (resrow != nullptr) {
-              const uint4* rp = reinterpret_cast<const uint4*>(resrow + col * 2);
+            // this thread's 64-byte row of the staging tile; 16-byte piece c lives at ((c ^ ((row >> 1) & 3)) << 4)
+            uint8_t* rowp = stage_buf + row * 64;
+            const int sw = (row >> 1) & 3;
+            if (has_res) {
+              mbar_wait(&res_bar[buf], (res_phase >> buf) & 1);
+              res_phase ^= (1u << buf);
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
-                const uint4 u = __ldg(rp + j4);
+                const uint4 u = *reinterpret_cast<const uint4*>(rowp + ((j4 ^ sw) << 4));
                 const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -289,8 +320,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
             }
-            // 16-bit pack into the 128B-swizzled staging tile: row r, 16-byte chunk c -> r*128 + ((c ^ (r&7))*16)
-            uint8_t* rowp = stage_buf + row * 128;
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               uint4 u;
@@ -298,11 +327,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               u.y = pack2(v[j4 * 8 + 2], v[j4 * 8 + 3], bf16);
               u.z = pack2(v[j4 * 8 + 4], v[j4 * 8 + 5], bf16);
               u.w = pack2(v[j4 * 8 + 6], v[j4 * 8 + 7], bf16);
-              const int chunk = half * 4 + j4;
-              *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row & 7)) << 4)) = u;
+              *reinterpret_cast<uint4*>(rowp + ((j4 ^ sw) << 4)) = u;
             }
           } else {
             // ---------------- generic path: masked, any n_out, fp32 or 16-bit output, straight to global memory
+            const uint8_t* resrow = (p.residual != nullptr && rvalid)
+                                        ? reinterpret_cast<const uint8_t*>(p.residual) + grow * p.ld_res * 2
+                                        : nullptr;
             const int nv = (p.n_out - col < 32) ? (p.n_out - col) : 32;
 #pragma unroll 1
             for (int j = 0; j < 32; ++j) {
@@ -321,14 +352,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
         }
-        if (!DIRECT && (half == 1 || cc + 32 >= OUT_BN)) {
+        if (!DIRECT) {
           fence_proxy_async_smem();
           named_bar_sync(1, 128);
-          if (et == 0 && (col - half * 32) < p.n_out) {
-            tma_store_5d(&tmD, stage_buf, col - half * 32, cb[0], cb[1], cb[2], cb[3]);
-            tma_store_commit();
+          if (et == 0) {
+            if (col < p.n_out) tma_store_5d(&tmD, stage_buf, col, cb[0], cb[1], cb[2], cb[3]);
+            tma_store_commit();                   // (an empty group for skipped chunks keeps the ring count exact)
+            tma_store_wait_read<2>();             // store of chunk gch-2 has drained -> its buffer is free again
+            if (has_res) issue_res_load(gch + 2);
           }
-          ++chunk_ctr;
         }
       }
       // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
@@ -364,7 +396,7 @@ static PFN_encodeTiled get_encode_fn() {
 
 // rank-`rank` 16-bit tensor map, dims/strides innermost first (strides in elements, strides[0] must be 1)
 int make_tmap_16(CUtensorMap* out, const void* base, int rank, const long* dims, const long* strides, const int* box,
-                 int is_bf16) {
+                 int is_bf16, int swizzle_bytes) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return AAB_ERR_DRIVER;
   cuuint64_t gdim[5];
@@ -379,7 +411,9 @@ int make_tmap_16(CUtensorMap* out, const void* base, int rank, const long* dims,
   }
   CUresult r = enc(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                    static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? AAB_OK : AAB_ERR_DRIVER;
 }
@@ -397,7 +431,7 @@ int num_sms() {
 
 template <int BN, int EPI>
 static int launch_bn(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& d,
-                     const IgemmParams& p, int max_ctas, cudaStream_t stream) {
+                     const CUtensorMap& r, const IgemmParams& p, int max_ctas, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -408,7 +442,7 @@ static int launch_bn(const CUtensorMap& a, const CUtensorMap& a2, const CUtensor
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  igemm_kernel<BN, EPI><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(a, a2, b, d, p);
+  igemm_kernel<BN, EPI><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(a, a2, b, d, r, p);
   return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }
 
@@ -469,13 +503,13 @@ extern "C" int aab_igemm(const AabIgemmDesc* d, void* stream_) {
   p.act = d->act;
   p.flags = d->flags | (direct ? AAB_F_DIRECT : 0);
 
-  CUtensorMap tmA, tmA2, tmB, tmD;
+  CUtensorMap tmA, tmA2, tmB, tmD, tmR;
   {
     int box[5] = {BK, d->box[0], d->box[1], d->box[2], d->box[3]};
-    int r = make_tmap_16(&tmA, d->a, 5, d->a_dims, d->a_strides, box, is_bf16);
+    int r = make_tmap_16(&tmA, d->a, 5, d->a_dims, d->a_strides, box, is_bf16, 128);
     if (r) return r;
     if (d->a2) {
-      r = make_tmap_16(&tmA2, d->a2, 5, d->a2_dims, d->a2_strides, box, is_bf16);
+      r = make_tmap_16(&tmA2, d->a2, 5, d->a2_dims, d->a2_strides, box, is_bf16, 128);
       if (r) return r;
     } else {
       tmA2 = tmA;
@@ -485,38 +519,48 @@ extern "C" int aab_igemm(const AabIgemmDesc* d, void* stream_) {
     long dims[3] = {static_cast<long>(d->num_taps) * d->kc, d->n, d->b_batch > 0 ? d->b_batch : 1};
     long strides[3] = {1, d->ld_b, d->b_batch_stride > 0 ? d->b_batch_stride : static_cast<long>(d->n) * d->ld_b};
     int box[3] = {BK, geglu ? bn / 2 : bn, 1};
-    int r = make_tmap_16(&tmB, d->b, 3, dims, strides, box, is_bf16);
+    int r = make_tmap_16(&tmB, d->b, 3, dims, strides, box, is_bf16, 128);
     if (r) return r;
   }
   if (!direct) {
-    // D viewed with the same pixel decomposition as the tile grid: [n_out, dimD0..3], contiguous rows of ld_out
+    // D (and the residual) viewed with the same pixel decomposition as the tile grid: [n_out, dimD0..3]; rows are
+    // contiguous in pixel-linear order with a row stride of ld_out (ld_res) elements.  32-column boxes, 64B swizzle.
     long dims[5] = {n_out, d->dim_d[0], d->dim_d[1], d->dim_d[2], d->dim_d[3]};
     long strides[5];
     strides[0] = 1;
     strides[1] = d->ld_out;
     for (int i = 2; i < 5; ++i) strides[i] = strides[i - 1] * d->dim_d[i - 2];
-    int box[5] = {64, d->box[0], d->box[1], d->box[2], d->box[3]};
-    int r = make_tmap_16(&tmD, d->out, 5, dims, strides, box, is_bf16);
+    int box[5] = {32, d->box[0], d->box[1], d->box[2], d->box[3]};
+    int r = make_tmap_16(&tmD, d->out, 5, dims, strides, box, is_bf16, 64);
     if (r) return r;
+    if (d->residual) {
+      strides[1] = d->ld_res;
+      for (int i = 2; i < 5; ++i) strides[i] = strides[i - 1] * d->dim_d[i - 2];
+      r = make_tmap_16(&tmR, d->residual, 5, dims, strides, box, is_bf16, 64);
+      if (r) return r;
+    } else {
+      tmR = tmD;
+    }
   } else {
     tmD = tmB;
+    tmR = tmB;
   }
   if (direct) {
     switch (bn) {
-      case 32: return launch_bn<32, 2>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
-      case 64: return launch_bn<64, 2>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
-      case 128: return launch_bn<128, 2>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
-      default: return launch_bn<256, 2>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
+      case 32: return launch_bn<32, 2>(tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
+      case 64: return launch_bn<64, 2>(tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
+      case 128: return launch_bn<128, 2>(tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
+      default: return launch_bn<256, 2>(tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
     }
   }
   if (geglu) {
-    if (bn == 128) return launch_bn<128, 1>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
-    return launch_bn<256, 1>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
+    if (bn == 128) return launch_bn<128, 1>(tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
+    return launch_bn<256, 1>(tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
   }
   switch (bn) {
-    case 64: return launch_bn<64, 0>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
-    case 128: return launch_bn<128, 0>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
-    default: return launch_bn<256, 0>(tmA, tmA2, tmB, tmD, p, d->max_ctas, stream);
+    case 64: return launch_bn<64, 0>(tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
+    case 128: return launch_bn<128, 0>(tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
+    default: return launch_bn<256, 0>(tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
   }
 }
 

@@ -79,7 +79,7 @@ struct IgemmParams {
   int flags;
 };
 int make_tmap_16(CUtensorMap* out, const void* base, int rank, const long* dims, const long* strides, const int* box,
-                 int is_bf16);
+                 int is_bf16, int swizzle_bytes = 128);
 int num_sms();
 }  // namespace aab
 #endif
