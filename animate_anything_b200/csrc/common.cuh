@@ -210,6 +210,18 @@ __host__ __device__ inline uint32_t make_idesc_f16(int is_bf16, int M, int N, in
 // ---------------------------------------------------------------- numeric helpers
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. below fp32 epsilon of the 16-bit-rounded result):
+// 1 rcp + 1 ex2 + 6 fma instead of libdevice erff's ~25 instructions with a branch.
+__device__ __forceinline__ float gelu_fast_f(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = 1.0f - poly * t * __expf(-z * z);      // erf(|x|/sqrt2)
+  return 0.5f * x + 0.5f * fabsf(x) * e;                  // 0.5*x*(1 + sign(x)*e)
+}
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, bool bf16) {
   if (bf16) {

@@ -28,7 +28,7 @@ constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;       // 16 KiB
 constexpr int OUT_CHUNK_BYTES = BM * 32 * 2;     // one 32-column output chunk (64-byte rows, SWIZZLE_64B), 8 KiB
 constexpr int NUM_OUT_BUFS = 4;                  // staging ring: residual prefetch (TMA load) + output (TMA store)
-constexpr int NUM_THREADS = 192;                 // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int NUM_THREADS = 352;                 // warp0 TMA, warp1 MMA, warps2-9 epilogue (2 groups), warp10 store
 
 template <int BN>
 struct Cfg {
@@ -71,7 +71,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint64_t* res_bar = bars + 2 * STAGES + 4;     // [NUM_OUT_BUFS] residual chunk landed in staging buffer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + NUM_OUT_BUFS);
+  uint64_t* ready_bar = res_bar + NUM_OUT_BUFS;  // [NUM_OUT_BUFS] output chunk written by 128 epilogue threads
+  uint64_t* bfree_bar = ready_bar + NUM_OUT_BUFS;  // [NUM_OUT_BUFS] staging buffer drained by its TMA store
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfree_bar + NUM_OUT_BUFS);
 
   const int warp = threadIdx.x >> 5;
   const bool bf16 = (p.flags & AAB_F_BF16) != 0;
@@ -94,9 +96,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull_bar[i], 1);
-        mbar_init(&tempty_bar[i], 128);
+        mbar_init(&tempty_bar[i], 256);
       }
-      for (int i = 0; i < NUM_OUT_BUFS; ++i) mbar_init(&res_bar[i], 1);
+      for (int i = 0; i < NUM_OUT_BUFS; ++i) {
+        mbar_init(&res_bar[i], 1);
+        mbar_init(&ready_bar[i], 128);
+        mbar_init(&bfree_bar[i], 1);
+      }
       fence_barrier_init();
     }
     __syncwarp();
@@ -177,45 +183,71 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __syncwarp();
       }
     }
+  } else if (warp == 10) {
+    // ===================================================== store warp: drains the staging ring with TMA stores and
+    // prefetches residual chunks (TMA loads) into freed staging buffers; epilogue warps never wait on a store.
+    constexpr int CPT = OUT_BN / 32;
+    if (!DIRECT && elect_one()) {
+      const bool has_res = (p.residual != nullptr);
+      auto issue_res_load = [&](uint32_t gg) {
+        const uint32_t tseq = gg / CPT;
+        const long tile2 = static_cast<long>(blockIdx.x) + static_cast<long>(tseq) * gridDim.x;
+        if (tile2 >= num_tiles) return;
+        const int nt2 = static_cast<int>(tile2 % p.num_n_tiles);
+        int mt2 = static_cast<int>(tile2 / p.num_n_tiles);
+        int c2[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          c2[i] = (mt2 % p.tiles[i]) * p.box[i];
+          mt2 /= p.tiles[i];
+        }
+        const int col2 = nt2 * OUT_BN + static_cast<int>(gg % CPT) * 32;
+        if (col2 >= p.n_out) return;
+        const uint32_t b2 = gg & (NUM_OUT_BUFS - 1);
+        mbar_arrive_expect_tx(&res_bar[b2], OUT_CHUNK_BYTES);
+        tma_load_5d(smO + b2 * OUT_CHUNK_BYTES, &tmR, &res_bar[b2], col2, c2[0], c2[1], c2[2], c2[3]);
+      };
+      if (has_res)
+        for (uint32_t g0 = 0; g0 < NUM_OUT_BUFS; ++g0) issue_res_load(g0);
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = tile % p.num_n_tiles;
+        int mt = tile / p.num_n_tiles;
+        int cb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          cb[i] = (mt % p.tiles[i]) * p.box[i];
+          mt /= p.tiles[i];
+        }
+        for (int ci = 0; ci < CPT; ++ci, ++g) {
+          const uint32_t buf = g & (NUM_OUT_BUFS - 1);
+          const int col = nt * OUT_BN + ci * 32;
+          mbar_wait(&ready_bar[buf], (g >> 2) & 1);
+          if (col < p.n_out) tma_store_5d(&tmD, smO + buf * OUT_CHUNK_BYTES, col, cb[0], cb[1], cb[2], cb[3]);
+          tma_store_commit();                 // (an empty group for skipped chunks keeps the ring count exact)
+          tma_store_wait_read<1>();           // every store but the newest has drained its staging buffer
+          if (g >= 1) {
+            mbar_arrive(&bfree_bar[(g - 1) & (NUM_OUT_BUFS - 1)]);
+            if (has_res) issue_res_load(g + NUM_OUT_BUFS - 1);
+          }
+        }
+      }
+      tma_store_wait_all<0>();
+    }
   } else {
-    // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
-    // Output leaves in 32-column chunks through a ring of 4 staging buffers (64-byte rows, SWIZZLE_64B).  When a
-    // residual is added, its chunk is TMA-loaded into the SAME staging buffer two chunks ahead (also across tile
-    // boundaries), so each thread finds its residual piece exactly where it will write its output piece: no
-    // latency-exposed global loads in the epilogue, one named barrier per chunk.
+    // ===================================================== epilogue: warps 2..9 = two groups of four warps (TMEM lane
+    // quarter = warp % 4).  Group eg takes the 32-column chunks with (chunk index % 2 == eg) of every tile and writes
+    // them (16-bit, SWIZZLE_64B) into the staging ring; when a residual is added its chunk has been TMA-prefetched
+    // into the same staging buffer, so each thread finds its residual piece exactly where it will write its output.
     const int q = warp & 3;
+    const int eg = (warp - 2) >> 2;
     const int row = q * 32 + lane_id();           // row inside the 128-row tile == TMEM lane
-    const int et = threadIdx.x - 64;              // 0..127
     constexpr int CPT = OUT_BN / 32;              // chunks per tile
     const bool has_res = !DIRECT && (p.residual != nullptr);
     uint32_t tl = 0;
-    uint32_t gch = 0;                             // global chunk counter of this CTA
-    uint32_t res_phase = 0;                       // per staging buffer phase bits
-
-    auto issue_res_load = [&](uint32_t gg) {      // called by et == 0 only
-      const uint32_t tseq = gg / CPT;
-      const long tile2 = static_cast<long>(blockIdx.x) + static_cast<long>(tseq) * gridDim.x;
-      if (tile2 >= num_tiles) return;
-      const int nt2 = static_cast<int>(tile2 % p.num_n_tiles);
-      int mt2 = static_cast<int>(tile2 / p.num_n_tiles);
-      int c2[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        c2[i] = (mt2 % p.tiles[i]) * p.box[i];
-        mt2 /= p.tiles[i];
-      }
-      const int col2 = nt2 * OUT_BN + static_cast<int>(gg % CPT) * 32;
-      if (col2 >= p.n_out) return;
-      const uint32_t b2 = gg & (NUM_OUT_BUFS - 1);
-      mbar_arrive_expect_tx(&res_bar[b2], OUT_CHUNK_BYTES);
-      tma_load_5d(smO + b2 * OUT_CHUNK_BYTES, &tmR, &res_bar[b2], col2, c2[0], c2[1], c2[2], c2[3]);
-    };
-    if (has_res && et == 0) {
-      issue_res_load(0);
-      issue_res_load(1);
-    }
-
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+    uint32_t gbase = 0;                           // global chunk index of the first chunk of the current tile
+    uint32_t res_phase = 0;                       // per staging buffer phase bits of res_bar
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl, gbase += CPT) {
       const uint32_t as = tl & 1;
       const uint32_t aph = (tl >> 1) & 1;
       const int nt = tile % p.num_n_tiles;
@@ -248,10 +280,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t tmem_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
 
 #pragma unroll 1
-      for (int cc = 0; cc < OUT_BN; cc += 32, ++gch) {
+      for (int ci = eg; ci < CPT; ci += 2) {
+        const int cc = ci * 32;
         const int col = n0 + cc;                  // global output column of this 32-wide chunk
+        const uint32_t gch = gbase + ci;
         const uint32_t buf = gch & (NUM_OUT_BUFS - 1);
         uint8_t* stage_buf = smO + buf * OUT_CHUNK_BYTES;
+        if (!DIRECT) mbar_wait(&bfree_bar[buf], ((gch >> 2) & 1) ^ 1);
         if (col < p.n_out) {                      // warp-uniform
           float v[32];
           {
@@ -280,10 +315,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               for (int j4 = 0; j4 < 8; ++j4) {
                 float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p.bias != nullptr) b = __ldg(gp + j4);
-                v[j4 * 4 + 0] *= gelu_erf_f(__uint_as_float(r[j4 * 4 + 0]) + b.x);
-                v[j4 * 4 + 1] *= gelu_erf_f(__uint_as_float(r[j4 * 4 + 1]) + b.y);
-                v[j4 * 4 + 2] *= gelu_erf_f(__uint_as_float(r[j4 * 4 + 2]) + b.z);
-                v[j4 * 4 + 3] *= gelu_erf_f(__uint_as_float(r[j4 * 4 + 3]) + b.w);
+                v[j4 * 4 + 0] *= gelu_fast_f(__uint_as_float(r[j4 * 4 + 0]) + b.x);
+                v[j4 * 4 + 1] *= gelu_fast_f(__uint_as_float(r[j4 * 4 + 1]) + b.y);
+                v[j4 * 4 + 2] *= gelu_fast_f(__uint_as_float(r[j4 * 4 + 2]) + b.z);
+                v[j4 * 4 + 3] *= gelu_fast_f(__uint_as_float(r[j4 * 4 + 3]) + b.w);
               }
             }
             if (bias2row != nullptr) {
@@ -354,20 +389,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         if (!DIRECT) {
           fence_proxy_async_smem();
-          named_bar_sync(1, 128);
-          if (et == 0) {
-            if (col < p.n_out) tma_store_5d(&tmD, stage_buf, col, cb[0], cb[1], cb[2], cb[3]);
-            tma_store_commit();                   // (an empty group for skipped chunks keeps the ring count exact)
-            tma_store_wait_read<2>();             // store of chunk gch-2 has drained -> its buffer is free again
-            if (has_res) issue_res_load(gch + 2);
-          }
+          mbar_arrive(&ready_bar[buf]);           // non-blocking hand-off to the store warp
         }
       }
       // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
     }
-    if (!DIRECT && et == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
