@@ -154,12 +154,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    const uint32_t idesc = make_idesc_f16(bf16 ? 1 : 0, BM, BN, 0, 0);
     uint32_t it = 0;
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
       const uint32_t as = tl & 1;
       const uint32_t aph = (tl >> 1) & 1;
+      // ragged last N tile: issue the MMA only over the valid columns (multiple of 16); the TMA box of B is zero-filled
+      // beyond N, so no extra traffic either.  N = 320 -> tiles of 256 + 64 columns instead of 3 x 128.
+      int n_mma = BN;
+      if (!GEGLU) {
+        const int nvalid = p.N - (tile % p.num_n_tiles) * BN;
+        if (nvalid < BN) n_mma = (nvalid + 15) & ~15;
+      }
+      const uint32_t idesc = make_idesc_f16(bf16 ? 1 : 0, BM, n_mma, 0, 0);
       mbar_wait(&tempty_bar[as], aph ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * BN;

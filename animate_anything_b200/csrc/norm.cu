@@ -54,15 +54,24 @@ __global__ void gn_stats_kernel(GnArgs a, double* __restrict__ partial /* [S][ch
   int cc;
   if (c0 < a.C1) { base = reinterpret_cast<const uint8_t*>(a.x1); ld = a.ld1; cc = c0; }
   else { base = reinterpret_cast<const uint8_t*>(a.x2); ld = a.ld2; cc = c0 - a.C1; }
-  for (long r = r0 + rsub; r < r1; r += rpi) {
-    const long row = static_cast<long>(s) * a.rows + r;
-    const uint4 u = ldg16(base + (row * ld + cc) * 2);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  // 4 independent 16-byte loads in flight per thread (the kernel is latency-bound otherwise)
+  for (long r = r0 + rsub; r < r1; r += 4 * rpi) {
+    uint4 u[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = unpack2(w[e], bf);
-      sum[2 * e] += f.x; sq[2 * e] += f.x * f.x;
-      sum[2 * e + 1] += f.y; sq[2 * e + 1] += f.y * f.y;
+    for (int k = 0; k < 4; ++k) {
+      const long rk = r + static_cast<long>(k) * rpi;
+      u[k] = make_uint4(0, 0, 0, 0);
+      if (rk < r1) u[k] = ldg16(base + ((static_cast<long>(s) * a.rows + rk) * ld + cc) * 2);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack2(w[e], bf);
+        sum[2 * e] += f.x; sq[2 * e] += f.x * f.x;
+        sum[2 * e + 1] += f.y; sq[2 * e + 1] += f.y * f.y;
+      }
     }
   }
   float* shs = sh;
@@ -141,20 +150,31 @@ __global__ void gn_apply_kernel(GnArgs a, const float* __restrict__ mean_rstd, c
   int cc;
   if (c0 < a.C1) { base = reinterpret_cast<const uint8_t*>(a.x1); ld = a.ld1; cc = c0; }
   else { base = reinterpret_cast<const uint8_t*>(a.x2); ld = a.ld2; cc = c0 - a.C1; }
-  for (long r = r0 + rsub; r < r1; r += rpi) {
-    const long row = static_cast<long>(s) * a.rows + r;
-    const uint4 u = ldg16(base + (row * ld + cc) * 2);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-    uint32_t o[4];
+  for (long r = r0 + rsub; r < r1; r += 4 * rpi) {
+    uint4 u[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = unpack2(w[e], bf);
-      float v0 = fmaf(f.x, sc[2 * e], sf[2 * e]);
-      float v1 = fmaf(f.y, sc[2 * e + 1], sf[2 * e + 1]);
-      if (silu) { v0 = silu_f(v0); v1 = silu_f(v1); }
-      o[e] = pack2(v0, v1, bf);
+    for (int k = 0; k < 4; ++k) {
+      const long rk = r + static_cast<long>(k) * rpi;
+      u[k] = make_uint4(0, 0, 0, 0);
+      if (rk < r1) u[k] = ldg16(base + ((static_cast<long>(s) * a.rows + rk) * ld + cc) * 2);
     }
-    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y) + (row * ldy + c0) * 2) = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long rk = r + static_cast<long>(k) * rpi;
+      if (rk >= r1) break;
+      const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack2(w[e], bf);
+        float v0 = fmaf(f.x, sc[2 * e], sf[2 * e]);
+        float v1 = fmaf(f.y, sc[2 * e + 1], sf[2 * e + 1]);
+        if (silu) { v0 = silu_f(v0); v1 = silu_f(v1); }
+        o[e] = pack2(v0, v1, bf);
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y) + ((static_cast<long>(s) * a.rows + rk) * ldy + c0) * 2) =
+          make_uint4(o[0], o[1], o[2], o[3]);
+    }
   }
 }
 
@@ -272,8 +292,8 @@ static int gn_launch_cfg(int C, long samples, long rows, int* threads, int* rows
   if (rpi < 1) rpi = 1;
   *threads = V * rpi;
   // ~4 CTAs per SM in total, at least 4 row-iterations per CTA
-  long want = (4L * 148 + samples - 1) / samples;
-  long maxc = (rows + 4L * rpi - 1) / (4L * rpi);
+  long want = (8L * 148 + samples - 1) / samples;
+  long maxc = (rows + 8L * rpi - 1) / (8L * rpi);
   if (want > maxc) want = maxc;
   if (want < 1) want = 1;
   long rpc = (rows + want - 1) / want;
