@@ -103,21 +103,39 @@ __global__ void gn_stats_kernel(GnArgs a, double* __restrict__ partial /* [S][ch
     if (is_last) ticket[s] = 0;          // self-reset for the next launch
   }
   __syncthreads();
-  if (is_last && threadIdx.x < a.groups) {
+  if (is_last) {
+    // final, fixed-order reduction over the chunk partials, spread over the whole CTA:
+    // part p of group g adds chunks p, p+P, p+2P, ... ; then the P parts are added in index order.
     __threadfence();
-    const int g = threadIdx.x;
-    double ds = 0.0, dq = 0.0;
-    const volatile double* pp = partial + (static_cast<long>(s) * chunks * a.groups + g) * 2;
-    for (int ch = 0; ch < chunks; ++ch) {
-      ds += pp[static_cast<long>(ch) * a.groups * 2];
-      dq += pp[static_cast<long>(ch) * a.groups * 2 + 1];
+    const int P = blockDim.x / a.groups;                 // >= 1 (blockDim >= groups is guaranteed by the host)
+    double* red = reinterpret_cast<double*>(sh);         // [P][groups][2] doubles (fits: P*groups*16 B <= smem)
+    const int g = threadIdx.x % a.groups;
+    const int part = threadIdx.x / a.groups;
+    if (part < P) {
+      double ds = 0.0, dq = 0.0;
+      const double* pp = partial + (static_cast<long>(s) * chunks * a.groups + g) * 2;
+      for (int ch = part; ch < chunks; ch += P) {
+        const double2 v = __ldcg(reinterpret_cast<const double2*>(pp + static_cast<long>(ch) * a.groups * 2));
+        ds += v.x;
+        dq += v.y;
+      }
+      red[(part * a.groups + g) * 2] = ds;
+      red[(part * a.groups + g) * 2 + 1] = dq;
     }
-    const double n = static_cast<double>(a.rows) * cpg;
-    const double m = ds / n;
-    double var = dq / n - m * m;
-    if (var < 0) var = 0;
-    mean_rstd[(static_cast<long>(s) * a.groups + g) * 2] = static_cast<float>(m);
-    mean_rstd[(static_cast<long>(s) * a.groups + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    __syncthreads();
+    if (threadIdx.x < a.groups) {
+      double ds = 0.0, dq = 0.0;
+      for (int q = 0; q < P; ++q) {
+        ds += red[(q * a.groups + g) * 2];
+        dq += red[(q * a.groups + g) * 2 + 1];
+      }
+      const double n = static_cast<double>(a.rows) * cpg;
+      const double m = ds / n;
+      double var = dq / n - m * m;
+      if (var < 0) var = 0;
+      mean_rstd[(static_cast<long>(s) * a.groups + g) * 2] = static_cast<float>(m);
+      mean_rstd[(static_cast<long>(s) * a.groups + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
   }
 }
 
@@ -336,8 +354,10 @@ extern "C" int aab_groupnorm(const void* x1, long ld1, int c1, const void* x2, l
   off += ((samples * groups * 2 * 4 + 255) / 256) * 256;
   double* partial = reinterpret_cast<double*>(ws + off);
   const int rpi = threads / (C / 8);
-  const size_t smem = static_cast<size_t>(2) * rpi * C * sizeof(float);
-  if (smem > 48 * 1024) return AAB_ERR_ARG;
+  size_t smem = static_cast<size_t>(2) * rpi * C * sizeof(float);
+  const size_t smem_red = static_cast<size_t>(threads / groups) * groups * 2 * sizeof(double);
+  if (smem_red > smem) smem = smem_red;
+  if (smem > 48 * 1024 || threads < groups) return AAB_ERR_ARG;
   dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(samples));
   gn_stats_kernel<<<grid, threads, smem, stream>>>(a, partial, mean_rstd, ticket, eps);
   gn_apply_kernel<<<grid, threads, 0, stream>>>(a, mean_rstd, gamma, beta, silu, y, ldy);

@@ -57,10 +57,13 @@ def pick_box(dims: Sequence[int], fixed_one: Sequence[int] = ()) -> list:
     return box
 
 
-def pick_block_n(n_out: int, m_tiles: int, geglu: bool = False) -> int:
+def pick_block_n(n_out: int, m_tiles: int, geglu: bool = False, k_total: int = 1 << 30) -> int:
     """Largest tile width that still yields at least one tile per SM.  A ragged last N tile costs neither MMA cycles
     (per-tile UMMA N) nor traffic (TMA zero-fill), so wider is better: fewer re-reads of the activation rows."""
     cands = [256, 128] if geglu else [256, 128, 64]
+    if not geglu and k_total <= 384 and n_out <= 640:
+        # HBM-bound (tiny K): what matters is bytes of A in flight = stages x 16 KiB; BN=128 has 6 stages, BN=256 has 4
+        cands = [128, 64]
     for bn in cands:
         obn = bn // 2 if geglu else bn
         if obn >= 2 * n_out and bn != cands[-1]:
@@ -152,7 +155,7 @@ def igemm(a: torch.Tensor, a_dims, a_strides, w: torch.Tensor, n: int, kc: int, 
         if n_out < 64 and not geglu:
             block_n = 32 if n_out <= 32 else 64
         else:
-            block_n = pick_block_n(n_out, m_tiles, geglu)
+            block_n = pick_block_n(n_out, m_tiles, geglu, kc * len(taps))
     d.block_n = block_n
     d.max_ctas = max_ctas
     if IGEMM_PROFILE is not None:

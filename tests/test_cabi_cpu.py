@@ -74,7 +74,8 @@ def test_pick_box_and_block_n():
     assert ops.pick_block_n(1280, 1088) == 256
     assert ops.pick_block_n(1280, 10, geglu=True) in (128, 256)
     assert ops.pick_block_n(320, 1088) == 256
-    assert ops.pick_block_n(1280, 17) == 64
+    assert ops.pick_block_n(1280, 17) in (64, 128)
+    assert ops.pick_block_n(320, 1088, k_total=320) == 128
 
 
 def test_state_dict_keys_match_reference_naming():

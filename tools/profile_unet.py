@@ -37,6 +37,27 @@ if mode == "ncu":
     fwd()
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
+elif mode == "vae_time":
+    lat = inp["latents"]
+    for _ in range(2):
+        pipe.vae.decode_video(lat)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        pipe.vae.decode_video(lat)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"vae decode 16 frames 512x512: {e0.elapsed_time(e1) / 3:.2f} ms  ({40.2e12 / (e0.elapsed_time(e1) / 3) / 1e9:.0f} TFLOP/s)")
+    img = torch.randn(1, 3, 512, 512, device=dev).to(torch.bfloat16)
+    pipe.vae.encode(img)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        pipe.vae.encode(img)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"vae encode 1 frame 512x512: {e0.elapsed_time(e1) / 3:.2f} ms")
 elif mode == "vae":
     lat = inp["latents"]
     pipe.vae.decode_video(lat)
