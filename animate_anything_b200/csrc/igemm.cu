@@ -27,16 +27,39 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;       // 16 KiB
 constexpr int OUT_CHUNK_BYTES = BM * 32 * 2;     // one 32-column output chunk (64-byte rows, SWIZZLE_64B), 8 KiB
-constexpr int NUM_OUT_BUFS = 4;                  // staging ring: residual prefetch (TMA load) + output (TMA store)
 constexpr int NUM_THREADS = 352;                 // warp0 TMA, warp1 MMA, warps2-9 epilogue (2 groups), warp10 store
 
-template <int BN>
+// DEEP = epilogue-heavy launches (few K iterations per tile): one pipeline stage less, staging ring twice as deep
+// (residual prefetch distance / store slack 7 chunks instead of 3).
+template <int BN, bool DEEP>
 struct Cfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
+  static constexpr int STAGES_BASE = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
+  static constexpr int STAGES = DEEP ? ((BN == 64 || BN == 32) ? STAGES_BASE - 2 : STAGES_BASE - 1) : STAGES_BASE;
+  static constexpr int NBUF = DEEP ? 8 : 4;
+  static constexpr int NBUF_LOG2 = DEEP ? 3 : 2;
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator stages
-  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + NUM_OUT_BUFS * OUT_CHUNK_BYTES +
-                                    1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + NBUF * OUT_CHUNK_BYTES +
+                                    1024 /*align*/ + 512 /*barriers*/;
+};
+
+// profiling aid: cycles spent inside an mbarrier wait, accumulated per warp role when IgemmParams::dbg != NULL
+struct WaitTimer {
+  unsigned long long acc = 0;
+  bool on;
+  __device__ explicit WaitTimer(const void* dbg) : on(dbg != nullptr) {}
+  __device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity) {
+    if (on) {
+      const long long t0 = clock64();
+      mbar_wait(bar, parity);
+      acc += static_cast<unsigned long long>(clock64() - t0);
+    } else {
+      mbar_wait(bar, parity);
+    }
+  }
+  __device__ __forceinline__ void flush(unsigned long long* dbg, int slot) {
+    if (on) atomicAdd(dbg + slot, acc);
+  }
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -50,13 +73,15 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 //      2 = generic direct-to-global store (any n_out, fp32 or 16-bit output, masked).
 // The epilogue is written as compact loops (no full unrolling): its instruction footprint is executed once per tile by
 // four warps, and a bloated epilogue thrashes the instruction cache when K is small.
-template <int BN, int EPI>
+template <int BN, int EPI, bool DEEP>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
              const __grid_constant__ CUtensorMap tmR, const IgemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, DEEP>;
   constexpr int STAGES = C::STAGES;
+  constexpr int NUM_OUT_BUFS = C::NBUF;
+  constexpr int NB_LOG2 = C::NBUF_LOG2;
   constexpr bool GEGLU = (EPI == 1);
   constexpr bool DIRECT = (EPI == 2);
   constexpr int OUT_BN = GEGLU ? BN / 2 : BN;
@@ -117,6 +142,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 0) {
     // ===================================================== TMA producer
     if (elect_one()) {
+      WaitTimer w_empty(p.dbg);
+      const long long t_start = clock64();
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int nt = tile % p.num_n_tiles;
@@ -135,7 +162,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int kb = 0; kb < kb_per_tap; ++kb, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
-            mbar_wait(&empty_bar[s], ph ^ 1);
+            w_empty.wait(&empty_bar[s], ph ^ 1);
             mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + C::B_STAGE_BYTES);
             const int kc = kb * BK;
             if (kc < p.Kc1)
@@ -151,9 +178,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
       }
+      w_empty.flush(p.dbg, 0);                                  // slot 0: producer waiting for a free stage
+      if (p.dbg) atomicAdd(p.dbg + 15, static_cast<unsigned long long>(clock64() - t_start));   // slot 15: producer lifetime
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
+    WaitTimer w_full(p.dbg), w_tempty(p.dbg);
     uint32_t it = 0;
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
@@ -167,13 +197,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (nvalid < BN) n_mma = (nvalid + 15) & ~15;
       }
       const uint32_t idesc = make_idesc_f16(bf16 ? 1 : 0, BM, n_mma, 0, 0);
-      mbar_wait(&tempty_bar[as], aph ^ 1);
+      w_tempty.wait(&tempty_bar[as], aph ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * BN;
       for (int ki = 0; ki < k_iters; ++ki, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+        w_full.wait(&full_bar[s], ph);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smA + s * A_STAGE_BYTES);
@@ -189,6 +219,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         __syncwarp();
       }
+    }
+    if (lane_id() == 0) {
+      w_full.flush(p.dbg, 1);                                   // slot 1: MMA waiting for TMA data
+      w_tempty.flush(p.dbg, 2);                                 // slot 2: MMA waiting for a drained accumulator
     }
   } else if (warp == 10) {
     // ===================================================== store warp: drains the staging ring with TMA stores and
@@ -216,6 +250,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       };
       if (has_res)
         for (uint32_t g0 = 0; g0 < NUM_OUT_BUFS; ++g0) issue_res_load(g0);
+      WaitTimer w_ready(p.dbg);
+      unsigned long long drain = 0;
       uint32_t g = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int nt = tile % p.num_n_tiles;
@@ -229,10 +265,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int ci = 0; ci < CPT; ++ci, ++g) {
           const uint32_t buf = g & (NUM_OUT_BUFS - 1);
           const int col = nt * OUT_BN + ci * 32;
-          mbar_wait(&ready_bar[buf], (g >> 2) & 1);
+          w_ready.wait(&ready_bar[buf], (g >> NB_LOG2) & 1);
           if (col < p.n_out) tma_store_5d(&tmD, smO + buf * OUT_CHUNK_BYTES, col, cb[0], cb[1], cb[2], cb[3]);
           tma_store_commit();                 // (an empty group for skipped chunks keeps the ring count exact)
+          const long long td = p.dbg ? clock64() : 0;
           tma_store_wait_read<1>();           // every store but the newest has drained its staging buffer
+          if (p.dbg) drain += static_cast<unsigned long long>(clock64() - td);
           if (g >= 1) {
             mbar_arrive(&bfree_bar[(g - 1) & (NUM_OUT_BUFS - 1)]);
             if (has_res) issue_res_load(g + NUM_OUT_BUFS - 1);
@@ -240,6 +278,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
       tma_store_wait_all<0>();
+      w_ready.flush(p.dbg, 3);                                  // slot 3: store warp waiting for a written chunk
+      if (p.dbg) atomicAdd(p.dbg + 4, drain);                   // slot 4: store warp waiting for TMA stores to drain
     }
   } else {
     // ===================================================== epilogue: warps 2..9 = two groups of four warps (TMEM lane
@@ -254,6 +294,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint32_t tl = 0;
     uint32_t gbase = 0;                           // global chunk index of the first chunk of the current tile
     uint32_t res_phase = 0;                       // per staging buffer phase bits of res_bar
+    WaitTimer w_tfull(p.dbg), w_bfree(p.dbg), w_res(p.dbg);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl, gbase += CPT) {
       const uint32_t as = tl & 1;
       const uint32_t aph = (tl >> 1) & 1;
@@ -282,10 +323,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const float* bias2row =
           (p.bias2 != nullptr && rvalid) ? p.bias2 + (grow / p.rows_per_bias2) * static_cast<long>(p.ld_bias2) : nullptr;
 
-      mbar_wait(&tfull_bar[as], aph);
+      w_tfull.wait(&tfull_bar[as], aph);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
 
+      // software pipeline on TMEM: the accumulator columns of the NEXT chunk are requested (tcgen05.ld is asynchronous
+      // until tcgen05.wait::ld) before the current chunk is post-processed.
+      uint32_t racc[32];
+      uint32_t rgate[GEGLU ? 32 : 1];
+      if (eg < CPT && n0 + eg * 32 < p.n_out) {
+        tmem_ld_32x32(tmem_acc + eg * 32, racc);
+        if (GEGLU) tmem_ld_32x32(tmem_acc + BN / 2 + eg * 32, rgate);
+      }
 #pragma unroll 1
       for (int ci = eg; ci < CPT; ci += 2) {
         const int cc = ci * 32;
@@ -293,15 +342,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const uint32_t gch = gbase + ci;
         const uint32_t buf = gch & (NUM_OUT_BUFS - 1);
         uint8_t* stage_buf = smO + buf * OUT_CHUNK_BYTES;
-        if (!DIRECT) mbar_wait(&bfree_bar[buf], ((gch >> 2) & 1) ^ 1);
+        if (!DIRECT) w_bfree.wait(&bfree_bar[buf], ((gch >> NB_LOG2) & 1) ^ 1);
         if (col < p.n_out) {                      // warp-uniform
           float v[32];
-          {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_acc + cc, r);
-            tmem_ld_wait();
+          float gt[GEGLU ? 32 : 1];
+          tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(racc[j]);
+          if (GEGLU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) gt[j] = __uint_as_float(rgate[j]);
+          }
+          if (ci + 2 < CPT && col + 64 < p.n_out) {      // prefetch the next chunk of this group
+            tmem_ld_32x32(tmem_acc + cc + 64, racc);
+            if (GEGLU) tmem_ld_32x32(tmem_acc + BN / 2 + cc + 64, rgate);
           }
           if (!DIRECT) {
             // ---------------- fast path: n_out % 32 == 0, everything vectorised
@@ -314,18 +368,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               }
             }
             if (GEGLU) {
-              uint32_t r[32];
-              tmem_ld_32x32(tmem_acc + BN / 2 + cc, r);
-              tmem_ld_wait();
               const float4* gp = reinterpret_cast<const float4*>(p.bias + p.N / 2 + col);
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
                 float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p.bias != nullptr) b = __ldg(gp + j4);
-                v[j4 * 4 + 0] *= gelu_fast_f(__uint_as_float(r[j4 * 4 + 0]) + b.x);
-                v[j4 * 4 + 1] *= gelu_fast_f(__uint_as_float(r[j4 * 4 + 1]) + b.y);
-                v[j4 * 4 + 2] *= gelu_fast_f(__uint_as_float(r[j4 * 4 + 2]) + b.z);
-                v[j4 * 4 + 3] *= gelu_fast_f(__uint_as_float(r[j4 * 4 + 3]) + b.w);
+                v[j4 * 4 + 0] *= gelu_fast_f(gt[j4 * 4 + 0] + b.x);
+                v[j4 * 4 + 1] *= gelu_fast_f(gt[j4 * 4 + 1] + b.y);
+                v[j4 * 4 + 2] *= gelu_fast_f(gt[j4 * 4 + 2] + b.z);
+                v[j4 * 4 + 3] *= gelu_fast_f(gt[j4 * 4 + 3] + b.w);
               }
             }
             if (bias2row != nullptr) {
@@ -340,7 +391,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             uint8_t* rowp = stage_buf + row * 64;
             const int sw = (row >> 1) & 3;
             if (has_res) {
-              mbar_wait(&res_bar[buf], (res_phase >> buf) & 1);
+              w_res.wait(&res_bar[buf], (res_phase >> buf) & 1);
               res_phase ^= (1u << buf);
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
@@ -403,6 +454,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
     }
+    if (threadIdx.x == 64 || threadIdx.x == 64 + 128) {          // one thread per epilogue group
+      w_tfull.flush(p.dbg, 5 + 3 * eg);                          // slots 5/8: epilogue waiting for the accumulator
+      w_bfree.flush(p.dbg, 6 + 3 * eg);                          // slots 6/9: waiting for a free staging buffer
+      w_res.flush(p.dbg, 7 + 3 * eg);                            // slots 7/10: waiting for the residual chunk
+    }
   }
 
   tc_fence_before();
@@ -464,21 +520,29 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int EPI>
-static int launch_bn(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& d,
-                     const CUtensorMap& r, const IgemmParams& p, int max_ctas, cudaStream_t stream) {
+template <int BN, int EPI, bool DEEP>
+static int launch_cfg(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& d,
+                      const CUtensorMap& r, const IgemmParams& p, int max_ctas, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg<BN>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, EPI, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg<BN, DEEP>::SMEM_BYTES);
     if (e != cudaSuccess) return AAB_ERR_CUDA;
     attr_set = true;
   }
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  igemm_kernel<BN, EPI><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(a, a2, b, d, r, p);
+  igemm_kernel<BN, EPI, DEEP><<<grid, NUM_THREADS, Cfg<BN, DEEP>::SMEM_BYTES, stream>>>(a, a2, b, d, r, p);
   return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
+}
+
+template <int BN, int EPI>
+static int launch_bn(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& d,
+                     const CUtensorMap& r, const IgemmParams& p, int max_ctas, cudaStream_t stream) {
+  // epilogue-heavy launches (<= 12 K-iterations per tile, i.e. K <= 768) take the deep staging ring
+  if (EPI != 2 && p.num_taps * p.kb_per_tap <= 12) return launch_cfg<BN, EPI, true>(a, a2, b, d, r, p, max_ctas, stream);
+  return launch_cfg<BN, EPI, false>(a, a2, b, d, r, p, max_ctas, stream);
 }
 
 }  // namespace aab
@@ -537,6 +601,7 @@ extern "C" int aab_igemm(const AabIgemmDesc* d, void* stream_) {
   p.out_scale = d->out_scale;
   p.act = d->act;
   p.flags = d->flags | (direct ? AAB_F_DIRECT : 0);
+  p.dbg = d->debug_cycles;
 
   CUtensorMap tmA, tmA2, tmB, tmD, tmR;
   {

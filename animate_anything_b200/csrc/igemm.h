@@ -50,6 +50,7 @@ typedef struct AabIgemmDesc {
   int flags;
   int block_n;              // 32 / 64 / 128 / 256
   int max_ctas;             // 0 = one CTA per SM
+  unsigned long long* debug_cycles;   // optional [16] device counters: per-role wait cycles (profiling aid), or NULL
 } AabIgemmDesc;
 
 #ifdef __cplusplus
@@ -77,6 +78,7 @@ struct IgemmParams {
   float out_scale;
   int act;
   int flags;
+  unsigned long long* dbg;
 };
 int make_tmap_16(CUtensorMap* out, const void* base, int rank, const long* dims, const long* strides, const int* box,
                  int is_bf16, int swizzle_bytes = 128);

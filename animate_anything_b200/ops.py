@@ -14,6 +14,7 @@ from . import _lib
 from ._lib import ACT_GELU, ACT_NONE, ACT_SILU, F_BF16, F_DIRECT, F_GEGLU, F_OUT_F32, IgemmDesc
 
 NUM_SMS = 148
+IGEMM_DEBUG = None       # optional uint64[16] device tensor: per-role wait-cycle counters (tools/igemm_roles.py)
 IGEMM_PROFILE = None     # bench.py sets this to a list to time every implicit-GEMM launch with CUDA events
 
 
@@ -158,6 +159,7 @@ def igemm(a: torch.Tensor, a_dims, a_strides, w: torch.Tensor, n: int, kc: int, 
             block_n = pick_block_n(n_out, m_tiles, geglu, kc * len(taps))
     d.block_n = block_n
     d.max_ctas = max_ctas
+    d.debug_cycles = None if IGEMM_DEBUG is None else IGEMM_DEBUG.data_ptr()
     if IGEMM_PROFILE is not None:
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
