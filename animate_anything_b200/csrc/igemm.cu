@@ -295,6 +295,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint32_t gbase = 0;                           // global chunk index of the first chunk of the current tile
     uint32_t res_phase = 0;                       // per staging buffer phase bits of res_bar
     WaitTimer w_tfull(p.dbg), w_bfree(p.dbg), w_res(p.dbg);
+    unsigned long long t_tmem = 0, t_fence = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl, gbase += CPT) {
       const uint32_t as = tl & 1;
       const uint32_t aph = (tl >> 1) & 1;
@@ -346,7 +347,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (col < p.n_out) {                      // warp-uniform
           float v[32];
           float gt[GEGLU ? 32 : 1];
+          const long long tq0 = p.dbg ? clock64() : 0;
           tmem_ld_wait();
+          if (p.dbg) t_tmem += static_cast<unsigned long long>(clock64() - tq0);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(racc[j]);
           if (GEGLU) {
@@ -446,8 +449,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
         if (!DIRECT) {
+          const long long tf0 = p.dbg ? clock64() : 0;
           fence_proxy_async_smem();
           mbar_arrive(&ready_bar[buf]);           // non-blocking hand-off to the store warp
+          if (p.dbg) t_fence += static_cast<unsigned long long>(clock64() - tf0);
         }
       }
       // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
@@ -458,6 +463,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       w_tfull.flush(p.dbg, 5 + 3 * eg);                          // slots 5/8: epilogue waiting for the accumulator
       w_bfree.flush(p.dbg, 6 + 3 * eg);                          // slots 6/9: waiting for a free staging buffer
       w_res.flush(p.dbg, 7 + 3 * eg);                            // slots 7/10: waiting for the residual chunk
+      if (p.dbg && eg == 0) {
+        atomicAdd(p.dbg + 11, t_tmem);                           // slot 11: tcgen05.wait::ld
+        atomicAdd(p.dbg + 12, t_fence);                          // slot 12: fence.proxy.async + arrive
+      }
     }
   }
 
@@ -540,8 +549,10 @@ static int launch_cfg(const CUtensorMap& a, const CUtensorMap& a2, const CUtenso
 template <int BN, int EPI>
 static int launch_bn(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& d,
                      const CUtensorMap& r, const IgemmParams& p, int max_ctas, cudaStream_t stream) {
-  // epilogue-heavy launches (<= 12 K-iterations per tile, i.e. K <= 768) take the deep staging ring
-  if (EPI != 2 && p.num_taps * p.kb_per_tap <= 12) return launch_cfg<BN, EPI, true>(a, a2, b, d, r, p, max_ctas, stream);
+  // The DEEP variant (8-buffer staging ring, one pipeline stage less) was measured on B200 and is NOT faster: with
+  // K <= 768 the MMA warp then waits longer for TMA data (3 instead of 4 stages) than the epilogue gains from the deeper
+  // ring (profiles/r01_igemm_roles.md).  It stays selectable for experiments through AAB_F_DEEP_RING.
+  if (EPI != 2 && (p.flags & AAB_F_DEEP_RING)) return launch_cfg<BN, EPI, true>(a, a2, b, d, r, p, max_ctas, stream);
   return launch_cfg<BN, EPI, false>(a, a2, b, d, r, p, max_ctas, stream);
 }
 

@@ -11,6 +11,7 @@
 #define AAB_F_BF16 1      /* 16-bit type is bfloat16 (else float16) */
 #define AAB_F_DIRECT 2    /* epilogue stores straight to global memory instead of smem + TMA store */
 #define AAB_F_OUT_F32 4   /* output is float32 (direct store only) */
+#define AAB_F_DEEP_RING 16 /* experiment: 8-buffer output staging ring, one TMA pipeline stage less */
 #define AAB_F_GEGLU 8     /* B rows [0,N/2) are values, [N/2,N) gates: out = value * gelu(gate), N/2 columns */
 
 #ifdef __cplusplus

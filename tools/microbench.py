@@ -49,6 +49,10 @@ if "igemm_c320" in names or "igemm_c320_res" in names:
     if "igemm_c320_res" in names:
         timeit("igemm 139264x320x320 +res", lambda: ops.linear(x, w, b, residual=res), bytes_=3 * M * 320 * 2,
                flops=2 * M * 320 * 320)
+if "igemm_qkv" in names:
+    x = rnd(M, 320)
+    w = rnd(960, 320)
+    timeit("igemm qkv 139264x960x320", lambda: ops.linear(x, w, None), bytes_=M * (320 + 960) * 2, flops=2 * M * 320 * 960)
 if "igemm_geglu" in names:
     x = rnd(M, 320)
     w = rnd(2560, 320)
