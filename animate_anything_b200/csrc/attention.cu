@@ -312,108 +312,166 @@ flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
 // ------------------------------------------------------------------------------------------------ temporal
 // q/k/v rows of frame t of (b, position pos): base + ((b*T + t)*HW + pos)*ld + col0 + head*64
-// K and V of one (b, position, head) are unpacked to fp32 in shared memory once (T x 64 each); lane i < T owns query
-// row i: scores, softmax and P.V stay in registers, K/V reads are warp-wide broadcasts (LDS.128, no bank conflicts).
+// One warp per (b, pixel, head).  T <= 32 is far below the 128-row tcgen05 tile, so the two tiny GEMMs
+// (S = Q.K^T: 32x32x64, O = P.V: 32x64x32, T zero-padded to 32) run on warp-level mma.sync m16n8k16 with the online
+// softmax on the accumulator fragments (the S fragments are re-used as the A operand of P.V).  Q/K/V rows are gathered
+// with coalesced 8-byte loads into padded shared memory (row stride 144 B: conflict-free fragment loads).
+template <bool BF16>
+__device__ __forceinline__ void mma_16816(float* c, const uint32_t* a, const uint32_t* b) {
+  if (BF16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+constexpr int TA_ROW = 72;                    // halves per smem row (64 + 8 pad)
+constexpr int TA_WARP_HALVES = 3 * 32 * TA_ROW;
+
 template <bool BF16>
 __global__ void __launch_bounds__(128)
 temporal_attn_d64_kernel(const void* __restrict__ qkv, long ld, int q_col0, int k_col0, int v_col0, void* __restrict__ out,
                          long ld_out, int B, int T, int HW, int heads, float scale) {
-  extern __shared__ float4 sm4[];          // [4 warps][2 (K,V)][T][16 float4]
+  extern __shared__ uint16_t sm16[];
   const int w = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const long item = static_cast<long>(blockIdx.x) * 4 + w;
   const long total = static_cast<long>(B) * HW * heads;
   if (item >= total) return;
-  float4* sK = sm4 + static_cast<size_t>(w) * 2 * T * 16;
-  float4* sV = sK + static_cast<size_t>(T) * 16;
+  uint16_t* sQ = sm16 + static_cast<size_t>(w) * TA_WARP_HALVES;
+  uint16_t* sK = sQ + 32 * TA_ROW;
+  uint16_t* sV = sK + 32 * TA_ROW;
   const int head = item % heads;
   const long bp = item / heads;
   const int pos = bp % HW;
   const int b = bp / HW;
-  // 16 lanes cover one 128-byte row (8 bytes = 4 channels per lane); two rows (frames) per iteration
+  // gather: 16 lanes cover one 128-byte row (8 B per lane), two rows per iteration; rows >= T are zero
   const int sub = lane & 15;
-  for (int t = lane >> 4; t < T; t += 2) {
-    const long rowi = (static_cast<long>(b) * T + t) * HW + pos;
-    const uint2 ku = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(qkv) +
-                                                     (rowi * ld + k_col0 + head * 64 + sub * 4) * 2);
-    const uint2 vu = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(qkv) +
-                                                     (rowi * ld + v_col0 + head * 64 + sub * 4) * 2);
-    const float2 k0 = unpack2(ku.x, BF16), k1 = unpack2(ku.y, BF16);
-    const float2 v0 = unpack2(vu.x, BF16), v1 = unpack2(vu.y, BF16);
-    sK[t * 16 + sub] = make_float4(k0.x, k0.y, k1.x, k1.y);
-    sV[t * 16 + sub] = make_float4(v0.x, v0.y, v1.x, v1.y);
+  for (int t = lane >> 4; t < 32; t += 2) {
+    uint2 qu = make_uint2(0, 0), ku = make_uint2(0, 0), vu = make_uint2(0, 0);
+    if (t < T) {
+      const uint8_t* rowp = reinterpret_cast<const uint8_t*>(qkv) +
+                            (((static_cast<long>(b) * T + t) * HW + pos) * ld + head * 64 + sub * 4) * 2;
+      qu = *reinterpret_cast<const uint2*>(rowp + q_col0 * 2);
+      ku = *reinterpret_cast<const uint2*>(rowp + k_col0 * 2);
+      vu = *reinterpret_cast<const uint2*>(rowp + v_col0 * 2);
+    }
+    *reinterpret_cast<uint2*>(sQ + t * TA_ROW + sub * 4) = qu;
+    *reinterpret_cast<uint2*>(sK + t * TA_ROW + sub * 4) = ku;
+    *reinterpret_cast<uint2*>(sV + t * TA_ROW + sub * 4) = vu;
   }
   __syncwarp();
-  if (lane < T) {
-    const long rowi = (static_cast<long>(b) * T + lane) * HW + pos;
-    float q[64];
-    const uint4* qp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(qkv) +
-                                                     (rowi * ld + q_col0 + head * 64) * 2);
+  const int g = lane >> 2;      // fragment row group
+  const int t4 = lane & 3;      // fragment column pair
+  // ---------------- S = Q K^T  (2 m-tiles x 4 n-tiles)
+  float S[2][4][4];
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const uint4 u = qp[g];
-      const uint32_t ws[4] = {u.x, u.y, u.z, u.w};
+  for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = unpack2(ws[e], BF16);
-        q[g * 8 + e * 2] = f.x * scale;
-        q[g * 8 + e * 2 + 1] = f.y * scale;
-      }
+    for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) S[mi][nj][e] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t afr[2][4];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      const uint16_t* base = sQ + (16 * mi + g) * TA_ROW + 16 * kk + 2 * t4;
+      afr[mi][0] = *reinterpret_cast<const uint32_t*>(base);
+      afr[mi][1] = *reinterpret_cast<const uint32_t*>(base + 8 * TA_ROW);
+      afr[mi][2] = *reinterpret_cast<const uint32_t*>(base + 8);
+      afr[mi][3] = *reinterpret_cast<const uint32_t*>(base + 8 * TA_ROW + 8);
     }
-    float s[32];
-    float mx = -INFINITY;
 #pragma unroll
-    for (int t = 0; t < 32; ++t) {
-      s[t] = -INFINITY;
-      if (t < T) {
-        float acc = 0.f;
-#pragma unroll
-        for (int d4 = 0; d4 < 16; ++d4) {
-          const float4 kf = sK[t * 16 + d4];
-          acc = fmaf(q[d4 * 4], kf.x, acc);
-          acc = fmaf(q[d4 * 4 + 1], kf.y, acc);
-          acc = fmaf(q[d4 * 4 + 2], kf.z, acc);
-          acc = fmaf(q[d4 * 4 + 3], kf.w, acc);
-        }
-        s[t] = acc;
-        mx = fmaxf(mx, acc);
-      }
-    }
-    float l = 0.f;
-#pragma unroll
-    for (int t = 0; t < 32; ++t) {
-      s[t] = (t < T) ? __expf(s[t] - mx) : 0.f;
-      l += s[t];
-    }
-    const float inv = 1.f / l;
-    float* o = q;                          // reuse the query registers for the output row
-#pragma unroll
-    for (int d = 0; d < 64; ++d) o[d] = 0.f;
-#pragma unroll
-    for (int t = 0; t < 32; ++t) {
-      if (t < T) {
-        const float pt = s[t] * inv;
-#pragma unroll
-        for (int d4 = 0; d4 < 16; ++d4) {
-          const float4 vf = sV[t * 16 + d4];
-          o[d4 * 4] = fmaf(pt, vf.x, o[d4 * 4]);
-          o[d4 * 4 + 1] = fmaf(pt, vf.y, o[d4 * 4 + 1]);
-          o[d4 * 4 + 2] = fmaf(pt, vf.z, o[d4 * 4 + 2]);
-          o[d4 * 4 + 3] = fmaf(pt, vf.w, o[d4 * 4 + 3]);
-        }
-      }
-    }
-    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out) + (rowi * ld_out + head * 64) * 2);
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      uint4 u;
-      u.x = pack2(o[g * 8 + 0], o[g * 8 + 1], BF16);
-      u.y = pack2(o[g * 8 + 2], o[g * 8 + 3], BF16);
-      u.z = pack2(o[g * 8 + 4], o[g * 8 + 5], BF16);
-      u.w = pack2(o[g * 8 + 6], o[g * 8 + 7], BF16);
-      op[g] = u;
+    for (int nj = 0; nj < 4; ++nj) {
+      uint32_t bfr[2];
+      const uint16_t* kb = sK + (8 * nj + g) * TA_ROW + 16 * kk + 2 * t4;
+      bfr[0] = *reinterpret_cast<const uint32_t*>(kb);
+      bfr[1] = *reinterpret_cast<const uint32_t*>(kb + 8);
+      mma_16816<BF16>(S[0][nj], afr[0], bfr);
+      mma_16816<BF16>(S[1][nj], afr[1], bfr);
     }
   }
+  // ---------------- softmax over the key axis (columns), rows (16 mi + g) and (16 mi + g + 8)
+  const float sl2 = scale * 1.4426950408889634f;
+  float inv_l[2][2];
+  uint32_t pfr[2][2][4];       // P as A fragments: [m-tile][k-step of 16 keys][4]
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {          // h = 0: row g, h = 1: row g + 8
+      float mx = -INFINITY;
+#pragma unroll
+      for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = 8 * nj + 2 * t4 + e;
+          float v = S[mi][nj][2 * h + e] * sl2;
+          v = (col < T) ? v : -INFINITY;
+          S[mi][nj][2 * h + e] = v;
+          mx = fmaxf(mx, v);
+        }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float l = 0.f;
+#pragma unroll
+      for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float pv = fast_exp2(S[mi][nj][2 * h + e] - mx);
+          S[mi][nj][2 * h + e] = pv;
+          l += pv;
+        }
+      l += __shfl_xor_sync(0xffffffffu, l, 1);
+      l += __shfl_xor_sync(0xffffffffu, l, 2);
+      inv_l[mi][h] = 1.0f / l;
+    }
+#pragma unroll
+    for (int k2 = 0; k2 < 2; ++k2) {
+      pfr[mi][k2][0] = pack2(S[mi][2 * k2][0], S[mi][2 * k2][1], BF16);
+      pfr[mi][k2][1] = pack2(S[mi][2 * k2][2], S[mi][2 * k2][3], BF16);
+      pfr[mi][k2][2] = pack2(S[mi][2 * k2 + 1][0], S[mi][2 * k2 + 1][1], BF16);
+      pfr[mi][k2][3] = pack2(S[mi][2 * k2 + 1][2], S[mi][2 * k2 + 1][3], BF16);
+    }
+  }
+  // ---------------- O = P V  (2 m-tiles x 8 n-tiles of d, 2 k-steps of 16 keys)
+  float O[2][8][4];
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int dj = 0; dj < 8; ++dj)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) O[mi][dj][e] = 0.f;
+#pragma unroll
+  for (int k2 = 0; k2 < 2; ++k2) {
+#pragma unroll
+    for (int dj = 0; dj < 8; ++dj) {
+      const uint16_t* vb = sV + (16 * k2 + 2 * t4) * TA_ROW + 8 * dj + g;
+      uint32_t bfr[2];
+      bfr[0] = static_cast<uint32_t>(vb[0]) | (static_cast<uint32_t>(vb[TA_ROW]) << 16);
+      bfr[1] = static_cast<uint32_t>(vb[8 * TA_ROW]) | (static_cast<uint32_t>(vb[9 * TA_ROW]) << 16);
+      mma_16816<BF16>(O[0][dj], pfr[0][k2], bfr);
+      mma_16816<BF16>(O[1][dj], pfr[1][k2], bfr);
+    }
+  }
+  // ---------------- normalise and store rows < T
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int row = 16 * mi + g + 8 * h;
+      if (row < T) {
+        const float il = inv_l[mi][h];
+        uint8_t* op = reinterpret_cast<uint8_t*>(out) +
+                      (((static_cast<long>(b) * T + row) * HW + pos) * ld_out + head * 64 + 2 * t4) * 2;
+#pragma unroll
+        for (int dj = 0; dj < 8; ++dj)
+          *reinterpret_cast<uint32_t*>(op + dj * 16) = pack2(O[mi][dj][2 * h] * il, O[mi][dj][2 * h + 1] * il, BF16);
+      }
+    }
 }
 
 }  // namespace aab
@@ -475,7 +533,7 @@ extern "C" int aab_temporal_attn_d64(const void* qkv, long ld, int q_col0, int k
   if (!qkv || !out || t < 1 || t > 32 || (ld % 8) || (ld_out % 8)) return AAB_ERR_ARG;
   const long total = static_cast<long>(b) * hw * heads;
   const int grid = static_cast<int>((total + 3) / 4);
-  const size_t smem = static_cast<size_t>(4) * 2 * t * 64 * sizeof(float);     // 34 KiB at T = 17, 64 KiB at T = 32
+  const size_t smem = static_cast<size_t>(4) * TA_WARP_HALVES * sizeof(uint16_t);   // 54 KiB: Q, K, V padded to 32 rows
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(temporal_attn_d64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);

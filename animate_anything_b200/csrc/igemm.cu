@@ -248,8 +248,28 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_arrive_expect_tx(&res_bar[b2], OUT_CHUNK_BYTES);
         tma_load_5d(smO + b2 * OUT_CHUNK_BYTES, &tmR, &res_bar[b2], col2, c2[0], c2[1], c2[2], c2[3]);
       };
-      if (has_res)
+      // residual rows are pulled into L2 two tiles ahead (HBM latency is longer than the ring can cover),
+      // the ring loads below then hit L2
+      auto prefetch_res_tile = [&](long tile2) {
+        if (tile2 >= num_tiles) return;
+        const int nt2 = static_cast<int>(tile2 % p.num_n_tiles);
+        int mt2 = static_cast<int>(tile2 / p.num_n_tiles);
+        int c2[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          c2[i] = (mt2 % p.tiles[i]) * p.box[i];
+          mt2 /= p.tiles[i];
+        }
+        for (int ci = 0; ci < CPT; ++ci) {
+          const int col2 = nt2 * OUT_BN + ci * 32;
+          if (col2 < p.n_out) tma_prefetch_l2_5d(&tmR, col2, c2[0], c2[1], c2[2], c2[3]);
+        }
+      };
+      if (has_res) {
+        prefetch_res_tile(blockIdx.x);
+        prefetch_res_tile(static_cast<long>(blockIdx.x) + gridDim.x);
         for (uint32_t g0 = 0; g0 < NUM_OUT_BUFS; ++g0) issue_res_load(g0);
+      }
       WaitTimer w_ready(p.dbg);
       unsigned long long drain = 0;
       uint32_t g = 0;
@@ -262,6 +282,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           cb[i] = (mt % p.tiles[i]) * p.box[i];
           mt /= p.tiles[i];
         }
+        if (has_res) prefetch_res_tile(static_cast<long>(tile) + 2L * gridDim.x);
         for (int ci = 0; ci < CPT; ++ci, ++g) {
           const uint32_t buf = g & (NUM_OUT_BUFS - 1);
           const int col = nt * OUT_BN + ci * 32;
