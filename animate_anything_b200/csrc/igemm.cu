@@ -349,14 +349,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
 
-      // software pipeline on TMEM: the accumulator columns of the NEXT chunk are requested (tcgen05.ld is asynchronous
-      // until tcgen05.wait::ld) before the current chunk is post-processed.
-      uint32_t racc[32];
-      uint32_t rgate[GEGLU ? 32 : 1];
-      if (eg < CPT && n0 + eg * 32 < p.n_out) {
-        tmem_ld_32x32(tmem_acc + eg * 32, racc);
-        if (GEGLU) tmem_ld_32x32(tmem_acc + BN / 2 + eg * 32, rgate);
-      }
 #pragma unroll 1
       for (int ci = eg; ci < CPT; ci += 2) {
         const int cc = ci * 32;
@@ -366,20 +358,24 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint8_t* stage_buf = smO + buf * OUT_CHUNK_BYTES;
         if (!DIRECT) w_bfree.wait(&bfree_bar[buf], ((gch >> NB_LOG2) & 1) ^ 1);
         if (col < p.n_out) {                      // warp-uniform
+          // (prefetching the next chunk's accumulator columns before post-processing this one was measured: it costs
+          //  32-64 registers and made the GEGLU epilogue 25 % slower; tcgen05.wait::ld is ~0 % of the epilogue time)
           float v[32];
           float gt[GEGLU ? 32 : 1];
-          const long long tq0 = p.dbg ? clock64() : 0;
-          tmem_ld_wait();
-          if (p.dbg) t_tmem += static_cast<unsigned long long>(clock64() - tq0);
+          {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_acc + cc, r);
+            if (GEGLU) {
+              uint32_t r2[32];
+              tmem_ld_32x32(tmem_acc + BN / 2 + cc, r2);
+              tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(racc[j]);
-          if (GEGLU) {
+              for (int j = 0; j < 32; ++j) gt[j] = __uint_as_float(r2[j]);
+            } else {
+              tmem_ld_wait();
+            }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) gt[j] = __uint_as_float(rgate[j]);
-          }
-          if (ci + 2 < CPT && col + 64 < p.n_out) {      // prefetch the next chunk of this group
-            tmem_ld_32x32(tmem_acc + cc + 64, racc);
-            if (GEGLU) tmem_ld_32x32(tmem_acc + BN / 2 + cc + 64, rgate);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           }
           if (!DIRECT) {
             // ---------------- fast path: n_out % 32 == 0, everything vectorised
