@@ -143,32 +143,38 @@ flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
       __syncwarp();
     };
+    // Issue order = strict ping-pong of the two query tiles: the S MMA of a tile is only issued when the OTHER tile's
+    // softmax has finished, so at any time one softmax warpgroup owns the exp2 (MUFU) pipe while the tensor core works
+    // for the other tile (P.V of the finished block and S of its next block):
+    //   S_A(0) | pA(j): S_B(j), PV_A(j) | pB(j): S_A(j+1), PV_B(j) | pA(j+1): ...
     mbar_wait(q_full, 0);
     mbar_wait(&kv_full[0], 0);
     tc_fence_after();
     issue_s(0, 0);
-    issue_s(1, 0);
     for (int j = 0; j < nkv; ++j) {
       const int s = j % FA_KV_STAGES;
       const uint32_t jph = j & 1;
       const int sn = (j + 1) % FA_KV_STAGES;
       const uint32_t phn = ((j + 1) / FA_KV_STAGES) & 1;
-#pragma unroll
-      for (int tile = 0; tile < 2; ++tile) {
-        mbar_wait(&p_ready[tile], jph);
-        if (j > 0) mbar_wait(&o_free[tile], jph ^ 1);
+      // ---- tile A finished its softmax of block j
+      mbar_wait(&p_ready[0], jph);
+      tc_fence_after();
+      issue_s(1, s);
+      if (j > 0) mbar_wait(&o_free[0], jph ^ 1);
+      tc_fence_after();
+      issue_pv(0, s);
+      // ---- tile B finished its softmax of block j
+      mbar_wait(&p_ready[1], jph);
+      if (j + 1 < nkv) {
+        mbar_wait(&kv_full[sn], phn);
         tc_fence_after();
-        issue_pv(tile, s);
-        if (tile == 1 && elect_one()) umma_commit(&kv_empty[s]);
-        __syncwarp();
-        if (j + 1 < nkv) {
-          if (tile == 0) {
-            mbar_wait(&kv_full[sn], phn);
-            tc_fence_after();
-          }
-          issue_s(tile, sn);
-        }
+        issue_s(0, sn);
       }
+      if (j > 0) mbar_wait(&o_free[1], jph ^ 1);
+      tc_fence_after();
+      issue_pv(1, s);
+      if (elect_one()) umma_commit(&kv_empty[s]);
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------ softmax warpgroups
