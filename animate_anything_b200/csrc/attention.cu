@@ -16,6 +16,7 @@
 //    FLOPs: CUDA cores, one warp per (position, head).
 #include "common.cuh"
 #include "igemm.h"
+#include <stdlib.h>
 
 namespace aab {
 
@@ -143,38 +144,32 @@ flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
       __syncwarp();
     };
-    // Issue order = strict ping-pong of the two query tiles: the S MMA of a tile is only issued when the OTHER tile's
-    // softmax has finished, so at any time one softmax warpgroup owns the exp2 (MUFU) pipe while the tensor core works
-    // for the other tile (P.V of the finished block and S of its next block):
-    //   S_A(0) | pA(j): S_B(j), PV_A(j) | pB(j): S_A(j+1), PV_B(j) | pA(j+1): ...
     mbar_wait(q_full, 0);
     mbar_wait(&kv_full[0], 0);
     tc_fence_after();
     issue_s(0, 0);
+    issue_s(1, 0);
     for (int j = 0; j < nkv; ++j) {
       const int s = j % FA_KV_STAGES;
       const uint32_t jph = j & 1;
       const int sn = (j + 1) % FA_KV_STAGES;
       const uint32_t phn = ((j + 1) / FA_KV_STAGES) & 1;
-      // ---- tile A finished its softmax of block j
-      mbar_wait(&p_ready[0], jph);
-      tc_fence_after();
-      issue_s(1, s);
-      if (j > 0) mbar_wait(&o_free[0], jph ^ 1);
-      tc_fence_after();
-      issue_pv(0, s);
-      // ---- tile B finished its softmax of block j
-      mbar_wait(&p_ready[1], jph);
-      if (j + 1 < nkv) {
-        mbar_wait(&kv_full[sn], phn);
+#pragma unroll
+      for (int tile = 0; tile < 2; ++tile) {
+        mbar_wait(&p_ready[tile], jph);
+        if (j > 0) mbar_wait(&o_free[tile], jph ^ 1);
         tc_fence_after();
-        issue_s(0, sn);
+        issue_pv(tile, s);
+        if (tile == 1 && elect_one()) umma_commit(&kv_empty[s]);
+        __syncwarp();
+        if (j + 1 < nkv) {
+          if (tile == 0) {
+            mbar_wait(&kv_full[sn], phn);
+            tc_fence_after();
+          }
+          issue_s(tile, sn);
+        }
       }
-      if (j > 0) mbar_wait(&o_free[1], jph ^ 1);
-      tc_fence_after();
-      issue_pv(1, s);
-      if (elect_one()) umma_commit(&kv_empty[s]);
-      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------ softmax warpgroups
@@ -292,6 +287,238 @@ flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       mbar_arrive(&o_free[tile]);
     }
     const int q = q0 + tile * 128 + row;
+    if (q < p.Lq) {
+      const float inv = 1.0f / l_run;
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) +
+                                           (static_cast<long>(b) * p.out_batch_stride + static_cast<long>(q) * p.ld_out +
+                                            p.out_col0 + head * 64) * 2);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        uint4 u;
+        u.x = pack2(o_acc[g * 8 + 0] * inv, o_acc[g * 8 + 1] * inv, bf16);
+        u.y = pack2(o_acc[g * 8 + 2] * inv, o_acc[g * 8 + 3] * inv, bf16);
+        u.z = pack2(o_acc[g * 8 + 4] * inv, o_acc[g * 8 + 5] * inv, bf16);
+        u.w = pack2(o_acc[g * 8 + 6] * inv, o_acc[g * 8 + 7] * inv, bf16);
+        op[g] = u;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ flash v2
+// One 128-query tile per CTA, S DOUBLE-BUFFERED in TMEM: the tensor core computes S(j+1) while the single softmax
+// warpgroup (4 warps, one per SM sub-partition) works on S(j), so the exp2 (MUFU) pipe — the real bound of d=64
+// attention on Blackwell — never waits for an MMA.  The O_j = P_j.V_j read-back is deferred by one block.
+//   TMEM columns: S0 [0,128)  S1 [128,256)  O_j [256,320)
+constexpr int FA2_THREADS = 192;      // warp0 TMA, warp1 MMA, warps 2-5 softmax
+constexpr int FA2_SMEM_BYTES = FA_TILE_BYTES + FA_KV_STAGES * 2 * FA_TILE_BYTES + 2 * FA_TILE_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(FA2_THREADS, 1)
+flash_attn_d64_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                         const __grid_constant__ CUtensorMap tmV, const FaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smQ = smem;
+  uint8_t* smK = smQ + FA_TILE_BYTES;
+  uint8_t* smV = smK + FA_KV_STAGES * FA_TILE_BYTES;
+  uint8_t* smP = smV + FA_KV_STAGES * FA_TILE_BYTES;      // two 64-key halves
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smP + 2 * FA_TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + FA_KV_STAGES;
+  uint64_t* s_full = kv_empty + FA_KV_STAGES;   // 2
+  uint64_t* s_free = s_full + 2;                // 2 (128 arrivals)
+  uint64_t* p_ready = s_free + 2;               // 1 (128 arrivals)
+  uint64_t* p_free = p_ready + 1;               // 1
+  uint64_t* o_full = p_free + 1;                // 1
+  uint64_t* o_free = o_full + 1;                // 1 (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int q0 = blockIdx.x * 128;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int bkv = b / p.kv_batch_div;
+  const int nkv = (p.Lk + 127) / 128;
+  const bool bf16 = p.is_bf16 != 0;
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      mbar_init(q_full, 1);
+      for (int i = 0; i < FA_KV_STAGES; ++i) {
+        mbar_init(&kv_full[i], 1);
+        mbar_init(&kv_empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&s_full[i], 1);
+        mbar_init(&s_free[i], 128);
+      }
+      mbar_init(p_ready, 128);
+      mbar_init(p_free, 1);
+      mbar_init(o_full, 1);
+      mbar_init(o_free, 128);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, FA_TILE_BYTES);
+      tma_load_3d(smQ, &tmQ, q_full, p.q_col0 + head * 64, q0, b);
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j % FA_KV_STAGES;
+        const uint32_t ph = (j / FA_KV_STAGES) & 1;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], 2 * FA_TILE_BYTES);
+        tma_load_3d(smK + s * FA_TILE_BYTES, &tmK, &kv_full[s], p.k_col0 + head * 64, j * 128, bkv);
+        tma_load_3d(smV + s * FA_TILE_BYTES, &tmV, &kv_full[s], p.v_col0 + head * 64, j * 128, bkv);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc_s = make_idesc_f16(bf16 ? 1 : 0, 128, 128, 0, 0);
+    const uint32_t idesc_o = make_idesc_f16(bf16 ? 1 : 0, 128, 64, 0, 1);   // B (=V) is MN-major
+    auto issue_s = [&](int jj) {
+      if (elect_one()) {
+        const uint32_t qa = smem_u32(smQ);
+        const uint32_t ka = smem_u32(smK + (jj % FA_KV_STAGES) * FA_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(tmem_base + (jj & 1) * 128, make_desc_kmajor_sw128(qa + k * 32),
+                      make_desc_kmajor_sw128(ka + k * 32), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[jj & 1]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    issue_s(0);
+    for (int j = 0; j < nkv; ++j) {
+      if (j + 1 < nkv) {                      // S(j+1) into the other buffer while the softmax works on S(j)
+        mbar_wait(&kv_full[(j + 1) % FA_KV_STAGES], ((j + 1) / FA_KV_STAGES) & 1);
+        if (j >= 1) mbar_wait(&s_free[(j + 1) & 1], ((j - 1) >> 1) & 1);   // softmax(j-1) has read that buffer
+        tc_fence_after();
+        issue_s(j + 1);
+      }
+      mbar_wait(p_ready, j & 1);
+      if (j > 0) mbar_wait(o_free, (j - 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t pa = smem_u32(smP);
+        const uint32_t va = smem_u32(smV + (j % FA_KV_STAGES) * FA_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_f16_ss(tmem_base + 256, make_desc_kmajor_sw128(pa + (k >> 2) * FA_TILE_BYTES + (k & 3) * 32),
+                      make_desc_mnmajor_sw128(va + k * 2048, 8192), idesc_o, k > 0 ? 1u : 0u);
+        umma_commit(o_full);
+        umma_commit(p_free);
+        umma_commit(&kv_empty[j % FA_KV_STAGES]);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane_id();
+    const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t t_o = tmem_base + 256 + lane_off;
+    uint8_t* prow = smP + row * 128;
+    float o_acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+    auto accumulate = [&](int jj, float alpha) {        // o_acc = alpha * o_acc + O_jj
+      mbar_wait(o_full, jj & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_o + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha, __uint_as_float(r[i]));
+      }
+      tc_fence_before();
+      mbar_arrive(o_free);
+    };
+    for (int j = 0; j < nkv; ++j) {
+      const uint32_t t_s = tmem_base + (j & 1) * 128 + lane_off;
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const int valid = p.Lk - j * 128;
+      const bool tail = valid < 128;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_s + c * 32, r);
+        tmem_ld_wait();
+        if (!tail) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
+      }
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const float alpha = fast_exp2(m_run - m_new);
+      m_run = m_new;
+      if (j > 0) mbar_wait(p_free, (j - 1) & 1);        // P.V of the previous block has consumed the P tile
+      float lsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_s + c * 32, r);
+        tmem_ld_wait();
+        uint8_t* hp = prow + (c >> 1) * FA_TILE_BYTES;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float x = fast_exp2(fmaf(__uint_as_float(r[g * 8 + i]), p.scale_log2, -m_new));
+            if (tail && (c * 32 + g * 8 + i >= valid)) x = 0.f;
+            e[i] = x;
+            lsum += x;
+          }
+          uint4 u;
+          u.x = pack2(e[0], e[1], bf16);
+          u.y = pack2(e[2], e[3], bf16);
+          u.z = pack2(e[4], e[5], bf16);
+          u.w = pack2(e[6], e[7], bf16);
+          const int chunk = (c & 1) * 4 + g;
+          *reinterpret_cast<uint4*>(hp + ((chunk ^ (row & 7)) << 4)) = u;
+        }
+      }
+      l_run = l_run * alpha + lsum;
+      tc_fence_before();
+      mbar_arrive(&s_free[j & 1]);
+      fence_proxy_async_smem();
+      mbar_arrive(p_ready);
+      if (j > 0) accumulate(j - 1, alpha_prev);          // deferred read-back of the previous block's P.V
+      alpha_prev = alpha;
+    }
+    accumulate(nkv - 1, alpha_prev);
+    const int q = q0 + row;
     if (q < p.Lq) {
       const float inv = 1.0f / l_run;
       uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) +
@@ -527,8 +754,25 @@ extern "C" int aab_flash_attn_d64(const void* q, long ldq, long q_batch_stride, 
   p.out_col0 = out_col0;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.is_bf16 = is_bf16;
-  dim3 grid((lq + 255) / 256, heads, nb);
-  flash_attn_d64_kernel<<<grid, FA_THREADS, FA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  static int use_v1 = -1;
+  if (use_v1 < 0) {
+    const char* e = getenv("AAB_FLASH_V1");
+    use_v1 = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (use_v1) {       // first version: two query tiles per CTA, S single-buffered (kept for A/B measurements)
+    dim3 grid((lq + 255) / 256, heads, nb);
+    flash_attn_d64_kernel<<<grid, FA_THREADS, FA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  } else {
+    static bool attr2 = false;
+    if (!attr2) {
+      if (cudaFuncSetAttribute(flash_attn_d64_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA2_SMEM_BYTES) !=
+          cudaSuccess)
+        return AAB_ERR_CUDA;
+      attr2 = true;
+    }
+    dim3 grid((lq + 127) / 128, heads, nb);
+    flash_attn_d64_v2_kernel<<<grid, FA2_THREADS, FA2_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  }
   return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }
 
