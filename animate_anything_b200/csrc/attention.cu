@@ -754,12 +754,15 @@ extern "C" int aab_flash_attn_d64(const void* q, long ldq, long q_batch_stride, 
   p.out_col0 = out_col0;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.is_bf16 = is_bf16;
+  // Measured on B200 (nb=34, L=4096, 5 heads, bf16): v1 = 1.33 ms, v2 = 2.03 ms.  One softmax warpgroup per SM
+  // (v2) cannot hide its own tcgen05.ld / MUFU latencies; two warpgroups (v1) do, even though they wait for the MMAs in
+  // phase.  v1 is the default; AAB_FLASH_V2=1 selects v2 for experiments.
   static int use_v1 = -1;
   if (use_v1 < 0) {
-    const char* e = getenv("AAB_FLASH_V1");
-    use_v1 = (e && e[0] == '1') ? 1 : 0;
+    const char* e = getenv("AAB_FLASH_V2");
+    use_v1 = (e && e[0] == '1') ? 0 : 1;
   }
-  if (use_v1) {       // first version: two query tiles per CTA, S single-buffered (kept for A/B measurements)
+  if (use_v1) {       // two query tiles per CTA (two softmax warpgroups), S single-buffered
     dim3 grid((lq + 255) / 256, heads, nb);
     flash_attn_d64_kernel<<<grid, FA_THREADS, FA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   } else {
