@@ -27,7 +27,9 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;       // 16 KiB
 constexpr int OUT_CHUNK_BYTES = BM * 32 * 2;     // one 32-column output chunk (64-byte rows, SWIZZLE_64B), 8 KiB
-constexpr int NUM_THREADS = 352;                 // warp0 TMA, warp1 MMA, warps2-9 epilogue (2 groups), warp10 store
+constexpr int NUM_EPI_GROUPS = 4;                // epilogue warpgroups (4 warps each): latency-bound chains, so more in parallel
+constexpr int STORE_WARP = 2 + 4 * NUM_EPI_GROUPS;
+constexpr int NUM_THREADS = 32 * (STORE_WARP + 1);  // warp0 TMA, warp1 MMA, warps 2..17 epilogue, warp 18 store
 
 // DEEP = epilogue-heavy launches (few K iterations per tile): one pipeline stage less, staging ring twice as deep
 // (residual prefetch distance / store slack 7 chunks instead of 3).
@@ -121,7 +123,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull_bar[i], 1);
-        mbar_init(&tempty_bar[i], 256);
+        mbar_init(&tempty_bar[i], 128 * NUM_EPI_GROUPS);
       }
       for (int i = 0; i < NUM_OUT_BUFS; ++i) {
         mbar_init(&res_bar[i], 1);
@@ -224,7 +226,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       w_full.flush(p.dbg, 1);                                   // slot 1: MMA waiting for TMA data
       w_tempty.flush(p.dbg, 2);                                 // slot 2: MMA waiting for a drained accumulator
     }
-  } else if (warp == 10) {
+  } else if (warp == STORE_WARP) {
     // ===================================================== store warp: drains the staging ring with TMA stores and
     // prefetches residual chunks (TMA loads) into freed staging buffers; epilogue warps never wait on a store.
     constexpr int CPT = OUT_BN / 32;
@@ -303,8 +305,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (p.dbg) atomicAdd(p.dbg + 4, drain);                   // slot 4: store warp waiting for TMA stores to drain
     }
   } else {
-    // ===================================================== epilogue: warps 2..9 = two groups of four warps (TMEM lane
-    // quarter = warp % 4).  Group eg takes the 32-column chunks with (chunk index % 2 == eg) of every tile and writes
+    // ===================================================== epilogue: warps 2..17 = four groups of four warps (TMEM lane
+    // quarter = warp % 4).  Group eg takes the 32-column chunks with (chunk index % 4 == eg) of every tile and writes
     // them (16-bit, SWIZZLE_64B) into the staging ring; when a residual is added its chunk has been TMA-prefetched
     // into the same staging buffer, so each thread finds its residual piece exactly where it will write its output.
     const int q = warp & 3;
@@ -350,7 +352,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t tmem_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
 
 #pragma unroll 1
-      for (int ci = eg; ci < CPT; ci += 2) {
+      for (int ci = eg; ci < CPT; ci += NUM_EPI_GROUPS) {
         const int cc = ci * 32;
         const int col = n0 + cc;                  // global output column of this 32-wide chunk
         const uint32_t gch = gbase + ci;
@@ -476,7 +478,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
     }
-    if (threadIdx.x == 64 || threadIdx.x == 64 + 128) {          // one thread per epilogue group
+    if ((threadIdx.x == 64 || threadIdx.x == 64 + 128) && eg < 2) {   // one thread of epilogue groups 0 and 1
       w_tfull.flush(p.dbg, 5 + 3 * eg);                          // slots 5/8: epilogue waiting for the accumulator
       w_bfree.flush(p.dbg, 6 + 3 * eg);                          // slots 6/9: waiting for a free staging buffer
       w_res.flush(p.dbg, 7 + 3 * eg);                            // slots 7/10: waiting for the residual chunk
