@@ -28,8 +28,7 @@ constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;       // 16 KiB
 constexpr int OUT_CHUNK_BYTES = BM * 32 * 2;     // one 32-column output chunk (64-byte rows, SWIZZLE_64B), 8 KiB
 constexpr int NUM_EPI_GROUPS = 4;                // epilogue warpgroups (4 warps each): latency-bound chains, so more in parallel
-constexpr int STORE_WARP = 2 + 4 * NUM_EPI_GROUPS;
-constexpr int NUM_THREADS = 32 * (STORE_WARP + 1);  // warp0 TMA, warp1 MMA, warps 2..17 epilogue, warp 18 store
+constexpr int NUM_THREADS = 32 * (2 + 4 * NUM_EPI_GROUPS);  // warp0 TMA, warp1 MMA, warps 2..17 epilogue
 
 // DEEP = epilogue-heavy launches (few K iterations per tile): one pipeline stage less, staging ring twice as deep
 // (residual prefetch distance / store slack 7 chunks instead of 3).
@@ -41,7 +40,7 @@ struct Cfg {
   static constexpr int NBUF_LOG2 = DEEP ? 3 : 2;
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator stages
-  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + NBUF * OUT_CHUNK_BYTES +
+  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 4 /*epilogue groups*/ * OUT_CHUNK_BYTES +
                                     1024 /*align*/ + 512 /*barriers*/;
 };
 
@@ -70,21 +69,24 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
-// EPI: 0 = 16-bit output through swizzled smem staging + TMA store (n_out % 32 == 0);
-//      1 = same with the GEGLU gate (B tile = [values | gates], out = value * gelu(gate));
-//      2 = generic direct-to-global store (any n_out, fp32 or 16-bit output, masked).
+// EPI (compile-time epilogue variant; the hot loop of each variant is straight-line code):
+//      0 = + bias                                  -> 16-bit, swizzled smem staging + TMA store (n_out % 32 == 0)
+//      1 = GEGLU gate (B tile = [values | gates], out = value * gelu(gate))
+//      2 = generic direct-to-global store (any n_out, fp32 / 16-bit output, masked, any flag combination)
+//      3 = + bias + residual       4 = + bias + per-sample bias (time embedding)       5 = + bias, SiLU
 // The epilogue is written as compact loops (no full unrolling): its instruction footprint is executed once per tile by
 // four warps, and a bloated epilogue thrashes the instruction cache when K is small.
-template <int BN, int EPI, bool DEEP>
+template <int BN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
              const __grid_constant__ CUtensorMap tmR, const IgemmParams p) {
-  using C = Cfg<BN, DEEP>;
+  using C = Cfg<BN, false>;
   constexpr int STAGES = C::STAGES;
-  constexpr int NUM_OUT_BUFS = C::NBUF;
-  constexpr int NB_LOG2 = C::NBUF_LOG2;
   constexpr bool GEGLU = (EPI == 1);
+  constexpr bool HAS_RES = (EPI == 3);
+  constexpr bool HAS_BIAS2 = (EPI == 4);
+  constexpr bool HAS_SILU = (EPI == 5);
   constexpr bool DIRECT = (EPI == 2);
   constexpr int OUT_BN = GEGLU ? BN / 2 : BN;
   extern __shared__ uint8_t smem_raw[];
@@ -92,15 +94,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* smA = smem;
   uint8_t* smB = smA + STAGES * A_STAGE_BYTES;
   uint8_t* smO = smB + STAGES * C::B_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smO + NUM_OUT_BUFS * OUT_CHUNK_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smO + NUM_EPI_GROUPS * OUT_CHUNK_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
-  uint64_t* res_bar = bars + 2 * STAGES + 4;     // [NUM_OUT_BUFS] residual chunk landed in staging buffer
-  uint64_t* ready_bar = res_bar + NUM_OUT_BUFS;  // [NUM_OUT_BUFS] output chunk written by 128 epilogue threads
-  uint64_t* bfree_bar = ready_bar + NUM_OUT_BUFS;  // [NUM_OUT_BUFS] staging buffer drained by its TMA store
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfree_bar + NUM_OUT_BUFS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
   const bool bf16 = (p.flags & AAB_F_BF16) != 0;
@@ -124,11 +123,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull_bar[i], 1);
         mbar_init(&tempty_bar[i], 128 * NUM_EPI_GROUPS);
-      }
-      for (int i = 0; i < NUM_OUT_BUFS; ++i) {
-        mbar_init(&res_bar[i], 1);
-        mbar_init(&ready_bar[i], 128);
-        mbar_init(&bfree_bar[i], 1);
       }
       fence_barrier_init();
     }
@@ -226,100 +220,44 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       w_full.flush(p.dbg, 1);                                   // slot 1: MMA waiting for TMA data
       w_tempty.flush(p.dbg, 2);                                 // slot 2: MMA waiting for a drained accumulator
     }
-  } else if (warp == STORE_WARP) {
-    // ===================================================== store warp: drains the staging ring with TMA stores and
-    // prefetches residual chunks (TMA loads) into freed staging buffers; epilogue warps never wait on a store.
-    constexpr int CPT = OUT_BN / 32;
-    if (!DIRECT && elect_one()) {
-      const bool has_res = (p.residual != nullptr);
-      auto issue_res_load = [&](uint32_t gg) {
-        const uint32_t tseq = gg / CPT;
-        const long tile2 = static_cast<long>(blockIdx.x) + static_cast<long>(tseq) * gridDim.x;
-        if (tile2 >= num_tiles) return;
-        const int nt2 = static_cast<int>(tile2 % p.num_n_tiles);
-        int mt2 = static_cast<int>(tile2 / p.num_n_tiles);
-        int c2[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          c2[i] = (mt2 % p.tiles[i]) * p.box[i];
-          mt2 /= p.tiles[i];
-        }
-        const int col2 = nt2 * OUT_BN + static_cast<int>(gg % CPT) * 32;
-        if (col2 >= p.n_out) return;
-        const uint32_t b2 = gg & (NUM_OUT_BUFS - 1);
-        mbar_arrive_expect_tx(&res_bar[b2], OUT_CHUNK_BYTES);
-        tma_load_5d(smO + b2 * OUT_CHUNK_BYTES, &tmR, &res_bar[b2], col2, c2[0], c2[1], c2[2], c2[3]);
-      };
-      // residual rows are pulled into L2 two tiles ahead (HBM latency is longer than the ring can cover),
-      // the ring loads below then hit L2
-      auto prefetch_res_tile = [&](long tile2) {
-        if (tile2 >= num_tiles) return;
-        const int nt2 = static_cast<int>(tile2 % p.num_n_tiles);
-        int mt2 = static_cast<int>(tile2 / p.num_n_tiles);
-        int c2[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          c2[i] = (mt2 % p.tiles[i]) * p.box[i];
-          mt2 /= p.tiles[i];
-        }
-        for (int ci = 0; ci < CPT; ++ci) {
-          const int col2 = nt2 * OUT_BN + ci * 32;
-          if (col2 < p.n_out) tma_prefetch_l2_5d(&tmR, col2, c2[0], c2[1], c2[2], c2[3]);
-        }
-      };
-      if (has_res) {
-        prefetch_res_tile(blockIdx.x);
-        prefetch_res_tile(static_cast<long>(blockIdx.x) + gridDim.x);
-        for (uint32_t g0 = 0; g0 < NUM_OUT_BUFS; ++g0) issue_res_load(g0);
-      }
-      WaitTimer w_ready(p.dbg);
-      unsigned long long drain = 0;
-      uint32_t g = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int nt = tile % p.num_n_tiles;
-        int mt = tile / p.num_n_tiles;
-        int cb[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          cb[i] = (mt % p.tiles[i]) * p.box[i];
-          mt /= p.tiles[i];
-        }
-        if (has_res) prefetch_res_tile(static_cast<long>(tile) + 2L * gridDim.x);
-        for (int ci = 0; ci < CPT; ++ci, ++g) {
-          const uint32_t buf = g & (NUM_OUT_BUFS - 1);
-          const int col = nt * OUT_BN + ci * 32;
-          w_ready.wait(&ready_bar[buf], (g >> NB_LOG2) & 1);
-          if (col < p.n_out) tma_store_5d(&tmD, smO + buf * OUT_CHUNK_BYTES, col, cb[0], cb[1], cb[2], cb[3]);
-          tma_store_commit();                 // (an empty group for skipped chunks keeps the ring count exact)
-          const long long td = p.dbg ? clock64() : 0;
-          tma_store_wait_read<1>();           // every store but the newest has drained its staging buffer
-          if (p.dbg) drain += static_cast<unsigned long long>(clock64() - td);
-          if (g >= 1) {
-            mbar_arrive(&bfree_bar[(g - 1) & (NUM_OUT_BUFS - 1)]);
-            if (has_res) issue_res_load(g + NUM_OUT_BUFS - 1);
-          }
-        }
-      }
-      tma_store_wait_all<0>();
-      w_ready.flush(p.dbg, 3);                                  // slot 3: store warp waiting for a written chunk
-      if (p.dbg) atomicAdd(p.dbg + 4, drain);                   // slot 4: store warp waiting for TMA stores to drain
-    }
   } else {
-    // ===================================================== epilogue: warps 2..17 = four groups of four warps (TMEM lane
-    // quarter = warp % 4).  Group eg takes the 32-column chunks with (chunk index % 4 == eg) of every tile and writes
-    // them (16-bit, SWIZZLE_64B) into the staging ring; when a residual is added its chunk has been TMA-prefetched
-    // into the same staging buffer, so each thread finds its residual piece exactly where it will write its output.
+    // ===================================================== epilogue: warps 2..17 = four independent groups of four warps
+    // (TMEM lane quarter = warp % 4).  Group eg owns the 32-column chunks with (chunk index % 4 == eg) of every tile, ONE
+    // private 8 KiB staging buffer (64-byte rows, SWIZZLE_64B) and its own TMA-store bulk groups, so no group ever waits
+    // for another one: the drain of its previous store (~350 clk, measured) overlaps the TMEM load + math of its next
+    // chunk.  The accumulator stage is handed back to the MMA warp right after the group's last TMEM read of the tile.
     const int q = warp & 3;
     const int eg = (warp - 2) >> 2;
     const int row = q * 32 + lane_id();           // row inside the 128-row tile == TMEM lane
+    const bool leader = (q == 2) && (lane_id() == 0);   // first thread of the group's first warp (warp 2 + 4 eg)
     constexpr int CPT = OUT_BN / 32;              // chunks per tile
-    const bool has_res = !DIRECT && (p.residual != nullptr);
+    uint8_t* stage_buf = smO + eg * OUT_CHUNK_BYTES;
+    uint8_t* rowp = stage_buf + row * 64;         // this thread's 64-byte row; 16-byte piece c at ((c ^ sw) << 4)
+    const int sw = (row >> 1) & 3;
+    const uint32_t bar_id = 1 + eg;
     uint32_t tl = 0;
-    uint32_t gbase = 0;                           // global chunk index of the first chunk of the current tile
-    uint32_t res_phase = 0;                       // per staging buffer phase bits of res_bar
-    WaitTimer w_tfull(p.dbg), w_bfree(p.dbg), w_res(p.dbg);
-    unsigned long long t_tmem = 0, t_fence = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl, gbase += CPT) {
+    WaitTimer w_tfull(p.dbg);
+    unsigned long long t_bar = 0, t_math = 0;
+
+    auto prefetch_res_tile = [&](long tile2) {    // residual rows -> L2, one tile ahead (leader of group 0 only)
+      if (tile2 >= num_tiles) return;
+      const int nt2 = static_cast<int>(tile2 % p.num_n_tiles);
+      int mt2 = static_cast<int>(tile2 / p.num_n_tiles);
+      int c2[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        c2[i] = (mt2 % p.tiles[i]) * p.box[i];
+        mt2 /= p.tiles[i];
+      }
+      for (int ci = 0; ci < CPT; ++ci) {
+        const int col2 = nt2 * OUT_BN + ci * 32;
+        if (col2 < p.n_out) tma_prefetch_l2_5d(&tmR, col2, c2[0], c2[1], c2[2], c2[3]);
+      }
+    };
+    const bool do_prefetch = HAS_RES && p.residual != nullptr && leader && eg == 0;
+    if (do_prefetch) prefetch_res_tile(blockIdx.x);
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
       const uint32_t as = tl & 1;
       const uint32_t aph = (tl >> 1) & 1;
       const int nt = tile % p.num_n_tiles;
@@ -344,147 +282,155 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         grow = ((static_cast<long>(g[3]) * p.dimD[2] + g[2]) * p.dimD[1] + g[1]) * p.dimD[0] + g[0];
       }
       const int n0 = nt * OUT_BN;
-      const float* bias2row =
-          (p.bias2 != nullptr && rvalid) ? p.bias2 + (grow / p.rows_per_bias2) * static_cast<long>(p.ld_bias2) : nullptr;
+      const float* bias2row = ((HAS_BIAS2 || DIRECT) && p.bias2 != nullptr && rvalid)
+                                  ? p.bias2 + (grow / p.rows_per_bias2) * static_cast<long>(p.ld_bias2)
+                                  : nullptr;
+      const uint8_t* resrow = ((HAS_RES || DIRECT) && p.residual != nullptr && rvalid)
+                                  ? reinterpret_cast<const uint8_t*>(p.residual) + grow * p.ld_res * 2
+                                  : nullptr;
+      if (do_prefetch) prefetch_res_tile(static_cast<long>(tile) + gridDim.x);
 
       w_tfull.wait(&tfull_bar[as], aph);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
+      bool released = false;
 
 #pragma unroll 1
       for (int ci = eg; ci < CPT; ci += NUM_EPI_GROUPS) {
         const int cc = ci * 32;
         const int col = n0 + cc;                  // global output column of this 32-wide chunk
-        const uint32_t gch = gbase + ci;
-        const uint32_t buf = gch & (NUM_OUT_BUFS - 1);
-        uint8_t* stage_buf = smO + buf * OUT_CHUNK_BYTES;
-        if (!DIRECT) w_bfree.wait(&bfree_bar[buf], ((gch >> NB_LOG2) & 1) ^ 1);
-        if (col < p.n_out) {                      // warp-uniform
-          // (prefetching the next chunk's accumulator columns before post-processing this one was measured: it costs
-          //  32-64 registers and made the GEGLU epilogue 25 % slower; tcgen05.wait::ld is ~0 % of the epilogue time)
-          float v[32];
-          float gt[GEGLU ? 32 : 1];
-          {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_acc + cc, r);
-            if (GEGLU) {
-              uint32_t r2[32];
-              tmem_ld_32x32(tmem_acc + BN / 2 + cc, r2);
-              tmem_ld_wait();
+        if (col >= p.n_out) break;                // warp-uniform; later chunks of this group are out of range too
+        const long long tm0 = p.dbg ? clock64() : 0;
+        // residual piece of this thread: issued first so that its (L2) latency hides behind the TMEM load
+        uint4 rres[HAS_RES ? 4 : 1];
+        if (HAS_RES && resrow != nullptr) {
+          const uint4* rp = reinterpret_cast<const uint4*>(resrow + col * 2);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) gt[j] = __uint_as_float(r2[j]);
-            } else {
-              tmem_ld_wait();
-            }
+          for (int j4 = 0; j4 < 4; ++j4) rres[j4] = __ldg(rp + j4);
+        }
+        float v[32];
+        float gt[GEGLU ? 32 : 1];
+        {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_acc + cc, r);
+          if (GEGLU) {
+            uint32_t r2[32];
+            tmem_ld_32x32(tmem_acc + BN / 2 + cc, r2);
+            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          }
-          if (!DIRECT) {
-            // ---------------- fast path: n_out % 32 == 0, everything vectorised
-            if (p.bias != nullptr) {
-              const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 b = __ldg(bp + j4);
-                v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
-              }
-            }
-            if (GEGLU) {
-              const float4* gp = reinterpret_cast<const float4*>(p.bias + p.N / 2 + col);
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias != nullptr) b = __ldg(gp + j4);
-                v[j4 * 4 + 0] *= gelu_fast_f(gt[j4 * 4 + 0] + b.x);
-                v[j4 * 4 + 1] *= gelu_fast_f(gt[j4 * 4 + 1] + b.y);
-                v[j4 * 4 + 2] *= gelu_fast_f(gt[j4 * 4 + 2] + b.z);
-                v[j4 * 4 + 3] *= gelu_fast_f(gt[j4 * 4 + 3] + b.w);
-              }
-            }
-            if (bias2row != nullptr) {
-              const float4* bp = reinterpret_cast<const float4*>(bias2row + col);
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 b = __ldg(bp + j4);
-                v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
-              }
-            }
-            // this thread's 64-byte row of the staging tile; 16-byte piece c lives at ((c ^ ((row >> 1) & 3)) << 4)
-            uint8_t* rowp = stage_buf + row * 64;
-            const int sw = (row >> 1) & 3;
-            if (has_res) {
-              w_res.wait(&res_bar[buf], (res_phase >> buf) & 1);
-              res_phase ^= (1u << buf);
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const uint4 u = *reinterpret_cast<const uint4*>(rowp + ((j4 ^ sw) << 4));
-                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = unpack2(w[e], bf16);
-                  v[j4 * 8 + e * 2] += f.x;
-                  v[j4 * 8 + e * 2 + 1] += f.y;
-                }
-              }
-            }
-            if (p.act == AAB_ACT_SILU) {          // (GELU as a plain activation takes the generic path)
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-            }
-            if (p.out_scale != 1.0f) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
-            }
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              uint4 u;
-              u.x = pack2(v[j4 * 8 + 0], v[j4 * 8 + 1], bf16);
-              u.y = pack2(v[j4 * 8 + 2], v[j4 * 8 + 3], bf16);
-              u.z = pack2(v[j4 * 8 + 4], v[j4 * 8 + 5], bf16);
-              u.w = pack2(v[j4 * 8 + 6], v[j4 * 8 + 7], bf16);
-              *reinterpret_cast<uint4*>(rowp + ((j4 ^ sw) << 4)) = u;
-            }
+            for (int j = 0; j < 32; ++j) gt[j] = __uint_as_float(r2[j]);
           } else {
-            // ---------------- generic path: masked, any n_out, fp32 or 16-bit output, straight to global memory
-            const uint8_t* resrow = (p.residual != nullptr && rvalid)
-                                        ? reinterpret_cast<const uint8_t*>(p.residual) + grow * p.ld_res * 2
-                                        : nullptr;
-            const int nv = (p.n_out - col < 32) ? (p.n_out - col) : 32;
-#pragma unroll 1
-            for (int j = 0; j < 32; ++j) {
-              // v[] is indexed dynamically here on purpose (compact code); it lives in local memory on this path
-              if (j < nv) {
-                float x = v[j];
-                if (p.bias != nullptr) x += __ldg(p.bias + col + j);
-                if (bias2row != nullptr) x += __ldg(bias2row + col + j);
-                if (resrow != nullptr) x += load_elem(resrow, col + j, bf16);
-                x = apply_act(x, p.act) * p.out_scale;
-                if (rvalid) {
-                  if (p.flags & AAB_F_OUT_F32) reinterpret_cast<float*>(p.out)[grow * p.ld_out + col + j] = x;
-                  else store_elem(p.out, grow * p.ld_out + col + j, x, bf16);
-                }
-              }
-            }
+            tmem_ld_wait();
           }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        }
+        if (ci + NUM_EPI_GROUPS >= CPT || col + 32 * NUM_EPI_GROUPS >= p.n_out) {
+          // last TMEM read of this group for this tile: give the accumulator stage back before the (slower) store path
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[as]);
+          released = true;
         }
         if (!DIRECT) {
-          const long long tf0 = p.dbg ? clock64() : 0;
+          // ---------------- fast path: n_out % 32 == 0, everything vectorised
+          if (p.bias != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b = __ldg(bp + j4);
+              v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
+            }
+          }
+          if (GEGLU) {
+            const float4* gp = reinterpret_cast<const float4*>(p.bias + p.N / 2 + col);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias != nullptr) b = __ldg(gp + j4);
+              v[j4 * 4 + 0] *= gelu_fast_f(gt[j4 * 4 + 0] + b.x);
+              v[j4 * 4 + 1] *= gelu_fast_f(gt[j4 * 4 + 1] + b.y);
+              v[j4 * 4 + 2] *= gelu_fast_f(gt[j4 * 4 + 2] + b.z);
+              v[j4 * 4 + 3] *= gelu_fast_f(gt[j4 * 4 + 3] + b.w);
+            }
+          }
+          if (HAS_BIAS2 && bias2row != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(bias2row + col);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b = __ldg(bp + j4);
+              v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
+            }
+          }
+          if (HAS_RES && resrow != nullptr) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const uint32_t w[4] = {rres[j4].x, rres[j4].y, rres[j4].z, rres[j4].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack2(w[e], bf16);
+                v[j4 * 8 + e * 2] += f.x;
+                v[j4 * 8 + e * 2 + 1] += f.y;
+              }
+            }
+          }
+          if (HAS_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] * __fdividef(1.0f, 1.0f + __expf(-v[j]));
+          }
+          uint4 o[4];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            o[j4].x = pack2(v[j4 * 8 + 0], v[j4 * 8 + 1], bf16);
+            o[j4].y = pack2(v[j4 * 8 + 2], v[j4 * 8 + 3], bf16);
+            o[j4].z = pack2(v[j4 * 8 + 4], v[j4 * 8 + 5], bf16);
+            o[j4].w = pack2(v[j4 * 8 + 6], v[j4 * 8 + 7], bf16);
+          }
+          const long long tm1 = p.dbg ? clock64() : 0;
+          if (leader) tma_store_wait_read<0>();    // the group's previous store has drained the staging buffer
+          named_bar_sync(bar_id, 128);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) *reinterpret_cast<uint4*>(rowp + ((j4 ^ sw) << 4)) = o[j4];
           fence_proxy_async_smem();
-          mbar_arrive(&ready_bar[buf]);           // non-blocking hand-off to the store warp
-          if (p.dbg) t_fence += static_cast<unsigned long long>(clock64() - tf0);
+          named_bar_sync(bar_id, 128);
+          if (leader) {
+            tma_store_5d(&tmD, stage_buf, col, cb[0], cb[1], cb[2], cb[3]);
+            tma_store_commit();
+          }
+          if (p.dbg) {
+            t_math += static_cast<unsigned long long>(tm1 - tm0);
+            t_bar += static_cast<unsigned long long>(clock64() - tm1);
+          }
+        } else {
+          // ---------------- generic path: masked, any n_out, fp32 or 16-bit output, straight to global memory
+          const int nv = (p.n_out - col < 32) ? (p.n_out - col) : 32;
+#pragma unroll 1
+          for (int j = 0; j < 32; ++j) {
+            // v[] is indexed dynamically here on purpose (compact code); it lives in local memory on this path
+            if (j < nv) {
+              float x = v[j];
+              if (p.bias != nullptr) x += __ldg(p.bias + col + j);
+              if (bias2row != nullptr) x += __ldg(bias2row + col + j);
+              if (resrow != nullptr) x += load_elem(resrow, col + j, bf16);
+              x = apply_act(x, p.act) * p.out_scale;
+              if (rvalid) {
+                if (p.flags & AAB_F_OUT_F32) reinterpret_cast<float*>(p.out)[grow * p.ld_out + col + j] = x;
+                else store_elem(p.out, grow * p.ld_out + col + j, x, bf16);
+              }
+            }
+          }
         }
       }
-      // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
-      tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);
+      if (!released) {                            // this group had no chunk in range for this tile
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[as]);
+      }
     }
-    if ((threadIdx.x == 64 || threadIdx.x == 64 + 128) && eg < 2) {   // one thread of epilogue groups 0 and 1
-      w_tfull.flush(p.dbg, 5 + 3 * eg);                          // slots 5/8: epilogue waiting for the accumulator
-      w_bfree.flush(p.dbg, 6 + 3 * eg);                          // slots 6/9: waiting for a free staging buffer
-      w_res.flush(p.dbg, 7 + 3 * eg);                            // slots 7/10: waiting for the residual chunk
-      if (p.dbg && eg == 0) {
-        atomicAdd(p.dbg + 11, t_tmem);                           // slot 11: tcgen05.wait::ld
-        atomicAdd(p.dbg + 12, t_fence);                          // slot 12: fence.proxy.async + arrive
+    if (!DIRECT && leader) tma_store_wait_all<0>();
+    if (leader && eg == 0) {
+      w_tfull.flush(p.dbg, 5);                                   // slot 5: epilogue group 0 waiting for the accumulator
+      if (p.dbg) {
+        atomicAdd(p.dbg + 6, t_math);                            // slot 6: residual/TMEM load + math + pack (group 0)
+        atomicAdd(p.dbg + 7, t_bar);                             // slot 7: drain wait + barriers + st.shared + store issue
       }
     }
   }
@@ -548,31 +494,32 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int EPI, bool DEEP>
-static int launch_cfg(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& d,
-                      const CUtensorMap& r, const IgemmParams& p, int max_ctas, cudaStream_t stream) {
+template <int BN, int EPI>
+static int launch_bn(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& d,
+                     const CUtensorMap& r, const IgemmParams& p, int max_ctas, cudaStream_t stream) {
+  using CF = Cfg<BN, false>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, EPI, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg<BN, DEEP>::SMEM_BYTES);
+    cudaError_t e =
+        cudaFuncSetAttribute(igemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES);
     if (e != cudaSuccess) return AAB_ERR_CUDA;
     attr_set = true;
   }
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  igemm_kernel<BN, EPI, DEEP><<<grid, NUM_THREADS, Cfg<BN, DEEP>::SMEM_BYTES, stream>>>(a, a2, b, d, r, p);
+  igemm_kernel<BN, EPI><<<grid, NUM_THREADS, CF::SMEM_BYTES, stream>>>(a, a2, b, d, r, p);
   return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }
 
-template <int BN, int EPI>
-static int launch_bn(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& d,
-                     const CUtensorMap& r, const IgemmParams& p, int max_ctas, cudaStream_t stream) {
-  // The DEEP variant (8-buffer staging ring, one pipeline stage less) was measured on B200 and is NOT faster: with
-  // K <= 768 the MMA warp then waits longer for TMA data (3 instead of 4 stages) than the epilogue gains from the deeper
-  // ring (profiles/r01_igemm_roles.md).  It stays selectable for experiments through AAB_F_DEEP_RING.
-  if (EPI != 2 && (p.flags & AAB_F_DEEP_RING)) return launch_cfg<BN, EPI, true>(a, a2, b, d, r, p, max_ctas, stream);
-  return launch_cfg<BN, EPI, false>(a, a2, b, d, r, p, max_ctas, stream);
+template <int EPI>
+static int launch_epi(int bn, const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& d,
+                      const CUtensorMap& r, const IgemmParams& p, int max_ctas, cudaStream_t stream) {
+  switch (bn) {
+    case 64: return launch_bn<64, EPI>(a, a2, b, d, r, p, max_ctas, stream);
+    case 128: return launch_bn<128, EPI>(a, a2, b, d, r, p, max_ctas, stream);
+    default: return launch_bn<256, EPI>(a, a2, b, d, r, p, max_ctas, stream);
+  }
 }
 
 }  // namespace aab
@@ -592,6 +539,11 @@ extern "C" int aab_igemm(const AabIgemmDesc* d, void* stream_) {
   if (geglu && (bn < 128 || direct)) return AAB_ERR_ARG;   // output tile must cover whole 64-column store boxes
   if (d->residual && (d->ld_res % 8) != 0 && !direct) direct = true;
   if (d->act == AAB_ACT_GELU && !geglu) direct = true;
+  {   // the staged variants cover one extra term each (residual | per-sample bias | SiLU) and no output scaling
+    const int extras = (d->residual ? 1 : 0) + (d->bias2 ? 1 : 0) + (d->act == AAB_ACT_SILU ? 1 : 0);
+    if (!geglu && (extras > 1 || d->out_scale != 1.0f)) direct = true;
+    if (geglu && (extras > 0 || d->out_scale != 1.0f)) return AAB_ERR_ARG;
+  }
   if (d->num_taps < 1 || d->num_taps > AAB_MAX_TAPS) return AAB_ERR_ARG;
   if (d->kc % 8 != 0) return AAB_ERR_ARG;
   if (d->a2 && (d->kc1 % 64 != 0)) return AAB_ERR_ARG;
@@ -687,11 +639,10 @@ extern "C" int aab_igemm(const AabIgemmDesc* d, void* stream_) {
     if (bn == 128) return launch_bn<128, 1>(tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
     return launch_bn<256, 1>(tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
   }
-  switch (bn) {
-    case 64: return launch_bn<64, 0>(tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
-    case 128: return launch_bn<128, 0>(tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
-    default: return launch_bn<256, 0>(tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
-  }
+  if (d->residual) return launch_epi<3>(bn, tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
+  if (d->bias2) return launch_epi<4>(bn, tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
+  if (d->act == AAB_ACT_SILU) return launch_epi<5>(bn, tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
+  return launch_epi<0>(bn, tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
 }
 
 extern "C" int aab_num_sms(void) { return aab::num_sms(); }

@@ -11,8 +11,8 @@ from animate_anything_b200 import ops  # noqa: E402
 dt = torch.bfloat16
 g = torch.Generator(device="cuda").manual_seed(0)
 rnd = lambda *s: torch.randn(*s, device="cuda", generator=g).to(dt)
-NAMES = ["prod_wait_empty", "mma_wait_full", "mma_wait_tempty", "store_wait_ready", "store_wait_drain", "epi0_wait_tfull",
-         "epi0_wait_bfree", "epi0_wait_res", "epi1_wait_tfull", "epi1_wait_bfree", "epi1_wait_res", "epi0_tmem_wait", "epi0_fence"]
+NAMES = ["prod_wait_empty", "mma_wait_full", "mma_wait_tempty", "-", "-", "epi0_wait_tfull", "epi0_load_math",
+         "epi0_drain_bar_store"]
 cases = [("139264x320x320+res", 139264, 320, 320, True, False), ("139264x320x320", 139264, 320, 320, False, False),
          ("139264x960x320", 139264, 960, 320, False, False), ("geglu 139264x2560x320", 139264, 2560, 320, False, True)]
 for name, m, n, k, res, geglu in cases:
