@@ -62,7 +62,8 @@ flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* p_ready = s_full + 2;               // 2
   uint64_t* o_full = p_ready + 2;               // 2
   uint64_t* o_free = o_full + 2;                // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+  uint64_t* p_free = o_free + 2;                // 2: P.V of the previous block has consumed the P tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 2);
 
   const int warp = threadIdx.x >> 5;
   const int q0 = blockIdx.x * 256;
@@ -89,6 +90,7 @@ flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         mbar_init(&p_ready[i], 128);
         mbar_init(&o_full[i], 1);
         mbar_init(&o_free[i], 128);
+        mbar_init(&p_free[i], 1);
       }
       fence_barrier_init();
     }
@@ -141,6 +143,7 @@ flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                       make_desc_kmajor_sw128(pa + (k >> 2) * FA_TILE_BYTES + (k & 3) * 32),
                       make_desc_mnmajor_sw128(va + k * 2048, 8192), idesc_o, k > 0 ? 1u : 0u);
         umma_commit(&o_full[tile]);
+        umma_commit(&p_free[tile]);
       }
       __syncwarp();
     };
@@ -156,19 +159,19 @@ flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const uint32_t phn = ((j + 1) / FA_KV_STAGES) & 1;
 #pragma unroll
       for (int tile = 0; tile < 2; ++tile) {
+        // softmax(j) of this tile is done: first give it S(j+1) (so that it never waits for a score tile), then run
+        // P.V(j) once the (deferred) read-back of O(j-1) has released the O columns
         mbar_wait(&p_ready[tile], jph);
+        if (j + 1 < nkv) {
+          if (tile == 0) mbar_wait(&kv_full[sn], phn);
+          tc_fence_after();
+          issue_s(tile, sn);
+        }
         if (j > 0) mbar_wait(&o_free[tile], jph ^ 1);
         tc_fence_after();
         issue_pv(tile, s);
         if (tile == 1 && elect_one()) umma_commit(&kv_empty[s]);
         __syncwarp();
-        if (j + 1 < nkv) {
-          if (tile == 0) {
-            mbar_wait(&kv_full[sn], phn);
-            tc_fence_after();
-          }
-          issue_s(tile, sn);
-        }
       }
     }
   } else {
@@ -184,6 +187,7 @@ flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
     float m_run = -INFINITY;
     float l_run = 0.f;
+    float alpha_prev = 0.f;
     for (int j = 0; j < nkv; ++j) {
       const uint32_t jph = j & 1;
       mbar_wait(&s_full[tile], jph);
@@ -205,6 +209,7 @@ flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const float m_new = fmaxf(m_run, mx * p.scale_log2);
         alpha = fast_exp2(m_run - m_new);
         m_run = m_new;
+        if (j > 0) mbar_wait(&p_free[tile], jph ^ 1);   // P.V(j-1) has read the P tile
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t r[32];
@@ -243,6 +248,7 @@ flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const float m_new = fmaxf(m_run, mx * p.scale_log2);
         alpha = fast_exp2(m_run - m_new);
         m_run = m_new;
+        if (j > 0) mbar_wait(&p_free[tile], jph ^ 1);
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t r[32];
@@ -272,8 +278,25 @@ flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(&p_ready[tile]);
-      // O_j = P_j . V_j  ->  o_acc = alpha * o_acc + O_j
-      mbar_wait(&o_full[tile], jph);
+      // deferred read-back of the previous block: o_acc = alpha_{j-1} * o_acc + O_{j-1}
+      if (j > 0) {
+        mbar_wait(&o_full[tile], jph ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_o + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(r[i]));
+        }
+        tc_fence_before();
+        mbar_arrive(&o_free[tile]);
+      }
+      alpha_prev = alpha;
+    }
+    {
+      mbar_wait(&o_full[tile], (nkv - 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -281,10 +304,8 @@ flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tmem_ld_32x32(t_o + c * 32, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha, __uint_as_float(r[i]));
+        for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(r[i]));
       }
-      tc_fence_before();
-      mbar_arrive(&o_free[tile]);
     }
     const int q = q0 + tile * 128 + row;
     if (q < p.Lq) {

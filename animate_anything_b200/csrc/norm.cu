@@ -54,17 +54,17 @@ __global__ void gn_stats_kernel(GnArgs a, double* __restrict__ partial /* [S][ch
   int cc;
   if (c0 < a.C1) { base = reinterpret_cast<const uint8_t*>(a.x1); ld = a.ld1; cc = c0; }
   else { base = reinterpret_cast<const uint8_t*>(a.x2); ld = a.ld2; cc = c0 - a.C1; }
-  // 4 independent 16-byte loads in flight per thread (the kernel is latency-bound otherwise)
-  for (long r = r0 + rsub; r < r1; r += 4 * rpi) {
-    uint4 u[4];
+  // 8 independent 16-byte loads in flight per thread (the kernel is latency-bound otherwise)
+  for (long r = r0 + rsub; r < r1; r += 8 * rpi) {
+    uint4 u[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 8; ++k) {
       const long rk = r + static_cast<long>(k) * rpi;
       u[k] = make_uint4(0, 0, 0, 0);
       if (rk < r1) u[k] = ldg16(base + ((static_cast<long>(s) * a.rows + rk) * ld + cc) * 2);
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 8; ++k) {
       const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -84,16 +84,26 @@ __global__ void gn_stats_kernel(GnArgs a, double* __restrict__ partial /* [S][ch
   __syncthreads();
   const int cpg = C / a.groups;
   if (threadIdx.x < a.groups) {
+    // fixed-order fp32 combine of the <= rows_per_cta x cpg values of this CTA (two independent chains per quantity),
+    // fp64 only across CTAs
     const int g = threadIdx.x;
-    double ds = 0.0, dq = 0.0;
-    for (int r = 0; r < rpi; ++r)
-      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-        ds += static_cast<double>(shs[r * C + c]);
-        dq += static_cast<double>(shq[r * C + c]);
+    float fs0 = 0.f, fs1 = 0.f, fq0 = 0.f, fq1 = 0.f;
+    for (int r = 0; r < rpi; ++r) {
+      int c = g * cpg;
+      for (; c + 1 < (g + 1) * cpg; c += 2) {
+        fs0 += shs[r * C + c];
+        fs1 += shs[r * C + c + 1];
+        fq0 += shq[r * C + c];
+        fq1 += shq[r * C + c + 1];
       }
+      if (c < (g + 1) * cpg) {
+        fs0 += shs[r * C + c];
+        fq0 += shq[r * C + c];
+      }
+    }
     double* pp = partial + ((static_cast<long>(s) * chunks + blockIdx.x) * a.groups + g) * 2;
-    pp[0] = ds;
-    pp[1] = dq;
+    pp[0] = static_cast<double>(fs0) + static_cast<double>(fs1);
+    pp[1] = static_cast<double>(fq0) + static_cast<double>(fq1);
   }
   __threadfence();
   __syncthreads();

@@ -42,8 +42,7 @@ class LatentToVideoPipeline:
         self.vae, self.text_encoder, self.tokenizer, self.unet, self.scheduler = vae, text_encoder, tokenizer, unet, scheduler
         self.vae_scale_factor = 2 ** (len(self.vae.config.block_out_channels) - 1) if vae is not None else 8
         self.use_cuda_graph = False
-        self._graph = None
-        self._graph_key = None
+        self.cfg_group = None          # torch.distributed group of size 2: CFG halves split over two GPUs (parallel.py)
         self.last_gpu_launches = 0
 
     @classmethod
@@ -128,14 +127,26 @@ class LatentToVideoPipeline:
     def _one_step(self, latents_in, latents_out, t_dev, ehs, cond2, mask, motion_dev, cfg, guidance, coef_row, step_idx,
                   x0_hist, kv_cache):
         n = latents_in.shape[0]
-        if not cfg:
-            sample = latents_in
-        elif n == 1:
-            sample = latents_in.expand(2, *latents_in.shape[1:])          # stride-0 duplicate, no copy
+        if cfg and self.cfg_group is not None:
+            # CFG halves on two GPUs: rank 0 of the pair runs the unconditional half, rank 1 the text half;
+            # the fp32 noise predictions (4 B x 4 x T x h x w per half) are all-gathered, then both ranks apply the
+            # same fused CFG + scheduler step, so the latents stay bit-identical on the two GPUs.
+            import torch.distributed as dist
+            r = dist.get_rank(self.cfg_group)
+            eps_half, g = self.unet(latents_in, t_dev, ehs[r * n:(r + 1) * n], condition_latent=cond2[r * n:(r + 1) * n],
+                                    mask=mask, motion=motion_dev, _raw_eps=True, _kv_cache=kv_cache)
+            eps = torch.empty((2,) + tuple(eps_half.shape), dtype=eps_half.dtype, device=eps_half.device)
+            dist.all_gather_into_tensor(eps, eps_half.unsqueeze(0), group=self.cfg_group)
+            eps = eps.view(2 * eps_half.shape[0], eps_half.shape[1])
         else:
-            sample = torch.cat([latents_in, latents_in])                  # multi-prompt: [uncond..., text...]
-        eps, g = self.unet(sample, t_dev, ehs, condition_latent=cond2, mask=mask, motion=motion_dev, _raw_eps=True,
-                           _kv_cache=kv_cache)
+            if not cfg:
+                sample = latents_in
+            elif n == 1:
+                sample = latents_in.expand(2, *latents_in.shape[1:])          # stride-0 duplicate, no copy
+            else:
+                sample = torch.cat([latents_in, latents_in])                  # multi-prompt: [uncond..., text...]
+            eps, g = self.unet(sample, t_dev, ehs, condition_latent=cond2, mask=mask, motion=motion_dev, _raw_eps=True,
+                               _kv_cache=kv_cache)
         ops.cfg_scheduler_step(eps, eps.stride(0), cfg, guidance, latents_in, latents_out, x0_hist, coef_row, step_idx)
 
     @torch.no_grad()
