@@ -63,6 +63,7 @@ _SIGS = {
     "aab_geglu": [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_long, C.c_int, C.c_int, C.c_void_p],
     "aab_upsample2x": [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p],
     "aab_copy2d": [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_long, C.c_int, C.c_void_p],
+    "aab_dup_rows": [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p],
     "aab_transpose": [C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p],
     "aab_cfg_scheduler_step": [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],

@@ -132,6 +132,16 @@ __global__ void copy2d_kernel(const uint16_t* __restrict__ src, long lds, uint16
   dst[r * ldd + c] = src[r * lds + c];
 }
 
+// out[0:n16] = out[n16:2*n16] = src (16-byte units): duplicates the rows of the unconditional half for the text half when
+// the CFG pair shares its prefix (see UNet3DConditionModel.forward, `_cfg_shared_prefix`)
+__global__ void dup_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long n16) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n16) return;
+  const uint4 v = __ldg(src + i);
+  dst[i] = v;
+  dst[i + n16] = v;
+}
+
 // batched transpose: src [nb][rows][lds] (cols used) -> dst [nb][cols][rows]
 __global__ void transpose_kernel(const uint16_t* __restrict__ src, long lds, long src_batch, uint16_t* __restrict__ dst,
                                  int rows, int cols) {
@@ -369,6 +379,15 @@ extern "C" int aab_copy2d(const void* src, long lds, void* dst, long ldd, long r
   const long total = rows * cols;
   copy2d_kernel<<<AAB_GRID(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(src), lds,
                                                           reinterpret_cast<uint16_t*>(dst), ldd, rows, cols);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_dup_rows(const void* src, void* dst, long bytes, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!src || !dst || (bytes % 16)) return AAB_ERR_ARG;
+  const long n16 = bytes / 16;
+  dup_rows_kernel<<<AAB_GRID(n16, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(src),
+                                                         reinterpret_cast<uint4*>(dst), n16);
   AAB_LAUNCH_RET();
 }
 

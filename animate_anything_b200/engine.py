@@ -168,6 +168,9 @@ class Ctx:
         self.lk: int = 0
         self.kv_cache: Dict[int, torch.Tensor] = {}      # id(block) -> [B*Lk, 2*inner]
         self.fuse_geglu = True
+        # CFG pair with identical latents / condition / timestep: everything before the first text cross-attention is
+        # computed for ONE half (batch b/2) and duplicated right there (bit-identical to computing both halves)
+        self.dup_pending = False
 
 
 def resnet_forward(ctx: Ctx, m: L.ResnetBlock2D, x: torch.Tensor, g: Geo, skip: Optional[torch.Tensor] = None):
@@ -212,7 +215,8 @@ def _ff(ctx: Ctx, p: dict, hs: torch.Tensor, normed: torch.Tensor):
 
 def spatial_transformer_forward(ctx: Ctx, m: L.Transformer2DModel, x: torch.Tensor, g: Geo):
     """diffusers Transformer2DModel.forward (use_linear_projection=True) with BasicTransformerBlock:
-    spatial self-attention over H*W tokens per frame, cross-attention to the text states, GEGLU feed-forward."""
+    spatial self-attention over H*W tokens per frame, cross-attention to the text states, GEGLU feed-forward.
+    Returns (out, g): g differs from the input geometry only when the shared CFG prefix ends here."""
     assert m.head_dim == 64, "flash kernel is specialised for head_dim 64 (the reference's attention_head_dim)"
     p = ctx.prep.get(m)
     inner = m.heads * 64
@@ -225,6 +229,12 @@ def spatial_transformer_forward(ctx: Ctx, m: L.Transformer2DModel, x: torch.Tens
         a = ops.flash_attn_d64(qkv, 0, qkv, inner, 2 * inner, g.n, g.hw, g.hw, m.heads)
         hs = ops.linear(a, bp["o1"][0], bp["o1"][1], residual=hs)
         if blk.attn2 is not None:
+            if ctx.dup_pending:
+                # first use of the text states: from here on the two CFG halves differ
+                hs = ops.dup_rows(hs)
+                x = ops.dup_rows(x)
+                g = Geo(g.b * 2, g.t, g.h, g.w)
+                ctx.dup_pending = False
             n2 = ops.layernorm(hs, bp["n2"][0], bp["n2"][1])
             q = ops.linear(n2, bp["q2"])
             kv = ctx.kv_cache.get(id(blk))
@@ -235,7 +245,7 @@ def spatial_transformer_forward(ctx: Ctx, m: L.Transformer2DModel, x: torch.Tens
             hs = ops.linear(a, bp["o2"][0], bp["o2"][1], residual=hs)
         n3 = ops.layernorm(hs, bp["n3"][0], bp["n3"][1])
         hs = _ff(ctx, bp, hs, n3)
-    return ops.linear(hs, p["po"][0], p["po"][1], residual=x)
+    return ops.linear(hs, p["po"][0], p["po"][1], residual=x), g
 
 
 def temporal_transformer_forward(ctx: Ctx, m: L.TransformerTemporalModel, x: torch.Tensor, g: Geo):

@@ -357,6 +357,14 @@ def upsample2x(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def dup_rows(x: torch.Tensor) -> torch.Tensor:
+    """[R, C] -> [2R, C] with both halves equal to x (CFG pair sharing its prefix)."""
+    assert x.is_contiguous()
+    out = torch.empty((2 * x.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
+    _lib.call("aab_dup_rows", _ptr(x), _ptr(out), x.numel() * x.element_size(), _stream())
+    return out
+
+
 def transpose_batched(src: torch.Tensor, col0: int, nb: int, rows: int, cols: int) -> torch.Tensor:
     """src [nb*rows, ld] -> dst [nb, cols, rows] taking columns col0..col0+cols."""
     dst = torch.empty((nb, cols, rows), device=src.device, dtype=src.dtype)

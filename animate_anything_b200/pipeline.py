@@ -42,6 +42,7 @@ class LatentToVideoPipeline:
         self.vae, self.text_encoder, self.tokenizer, self.unet, self.scheduler = vae, text_encoder, tokenizer, unet, scheduler
         self.vae_scale_factor = 2 ** (len(self.vae.config.block_out_channels) - 1) if vae is not None else 8
         self.use_cuda_graph = False
+        self.share_cfg_prefix = True   # evaluate the text-independent prefix of the UNet once per CFG pair
         self.cfg_group = None          # torch.distributed group of size 2: CFG halves split over two GPUs (parallel.py)
         self.last_gpu_launches = 0
 
@@ -138,6 +139,11 @@ class LatentToVideoPipeline:
             eps = torch.empty((2,) + tuple(eps_half.shape), dtype=eps_half.dtype, device=eps_half.device)
             dist.all_gather_into_tensor(eps, eps_half.unsqueeze(0), group=self.cfg_group)
             eps = eps.view(2 * eps_half.shape[0], eps_half.shape[1])
+        elif cfg and self.share_cfg_prefix:
+            # both guidance halves share latents / condition / timestep: the UNet evaluates the layers before the first
+            # text cross-attention once (cond2[:n] is the single copy of the condition latent)
+            eps, g = self.unet(latents_in, t_dev, ehs, condition_latent=cond2[:n], mask=mask, motion=motion_dev,
+                               _raw_eps=True, _kv_cache=kv_cache, _cfg_shared_prefix=True)
         else:
             if not cfg:
                 sample = latents_in

@@ -68,7 +68,7 @@ class UNetMidBlock3DCrossAttn(_Block):
         x = E.temporal_conv_forward(ctx, self.temp_convs[0], x, g)   # reference :354 (no num_frames guard)
         for attn, tattn, resnet, tconv in zip(self.attentions, self.temp_attentions, self.resnets[1:],
                                               self.temp_convs[1:]):
-            x = E.spatial_transformer_forward(ctx, attn, x, g)
+            x, g = E.spatial_transformer_forward(ctx, attn, x, g)
             if g.t > 1:
                 x = E.temporal_transformer_forward(ctx, tattn, x, g)
             x = E.resnet_forward(ctx, resnet, x, g)
@@ -108,7 +108,7 @@ class CrossAttnDownBlock3D(_Block):
             x = E.resnet_forward(ctx, resnet, x, g)
             if g.t > 1:
                 x = E.temporal_conv_forward(ctx, tconv, x, g)
-            x = E.spatial_transformer_forward(ctx, attn, x, g)
+            x, g = E.spatial_transformer_forward(ctx, attn, x, g)
             if g.t > 1:
                 x = E.temporal_transformer_forward(ctx, tattn, x, g)
             outs.append((x, g))
@@ -179,10 +179,12 @@ class CrossAttnUpBlock3D(_Block):
         for resnet, tconv, attn, tattn in zip(self.resnets, self.temp_convs, self.attentions, self.temp_attentions):
             skip, sg = skips.pop()
             assert (sg.h, sg.w) == (g.h, g.w)
+            if sg.b * 2 == g.b:                       # skip produced inside the shared CFG prefix (batch b/2)
+                skip = E.ops.dup_rows(skip)
             x = E.resnet_forward(ctx, resnet, x, g, skip=skip)
             if g.t > 1:
                 x = E.temporal_conv_forward(ctx, tconv, x, g)
-            x = E.spatial_transformer_forward(ctx, attn, x, g)
+            x, g = E.spatial_transformer_forward(ctx, attn, x, g)
             if g.t > 1:
                 x = E.temporal_transformer_forward(ctx, tattn, x, g)
         if self.upsamplers is not None:
@@ -212,6 +214,8 @@ class UpBlock3D(_Block):
         for resnet, tconv in zip(self.resnets, self.temp_convs):
             skip, sg = skips.pop()
             assert (sg.h, sg.w) == (g.h, g.w)
+            if sg.b * 2 == g.b:                       # skip produced inside the shared CFG prefix (batch b/2)
+                skip = E.ops.dup_rows(skip)
             x = E.resnet_forward(ctx, resnet, x, g, skip=skip)
             if g.t > 1:
                 x = E.temporal_conv_forward(ctx, tconv, x, g)

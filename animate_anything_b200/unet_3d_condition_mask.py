@@ -224,7 +224,13 @@ class UNet3DConditionModel(ModelBase):
         return_dict: bool = True,
         _raw_eps: bool = False,
         _kv_cache: Optional[dict] = None,
+        _cfg_shared_prefix: bool = False,
     ):
+        """`_cfg_shared_prefix=True` (used by LatentToVideoPipeline under classifier-free guidance): `sample`,
+        `condition_latent` hold ONE copy per prompt ([n, ...]) while `encoder_hidden_states` holds [2n, ...]
+        (unconditional first).  Both guidance halves see identical latents / condition / timestep, so every layer before
+        the first text cross-attention is evaluated once and duplicated there; the result equals the reference's
+        `torch.cat([latents] * 2)` evaluation (models/pipeline.py:165) up to the summation order inside GroupNorm."""
         if (class_labels is not None or timestep_cond is not None or attention_mask is not None or
                 down_block_additional_residuals is not None or mid_block_additional_residual is not None):
             raise NotImplementedError("class_labels / timestep_cond / attention_mask / ControlNet residuals are not "
@@ -238,6 +244,9 @@ class UNet3DConditionModel(ModelBase):
         if condition_latent.dtype != dt:
             condition_latent = condition_latent.to(dt)
         b, c, f, h, w = sample.shape
+        b_full = 2 * b if _cfg_shared_prefix else b
+        if _cfg_shared_prefix and encoder_hidden_states.shape[0] != b_full:
+            raise ValueError("_cfg_shared_prefix needs encoder_hidden_states of batch 2 x sample batch")
         if any(s % (2 ** self.num_upsamplers) != 0 for s in (h, w)):
             raise NotImplementedError("latent height/width must be multiples of 8 (the reference's "
                                       "`forward_upsample_size` interpolation path is not implemented)")
@@ -245,7 +254,8 @@ class UNet3DConditionModel(ModelBase):
         ctx = E.Ctx(prep, g)
         ctx.fuse_geglu = self.fuse_geglu
         ctx.temb_off = own["temb_off"]
-        ctx.temb_all = self._time_embedding(prep, timestep, motion, b, dev)
+        ctx.dup_pending = bool(_cfg_shared_prefix)
+        ctx.temb_all = self._time_embedding(prep, timestep, motion, b_full, dev)
         ehs = encoder_hidden_states
         if ehs.dtype != dt:
             ehs = ehs.to(dt)
@@ -283,12 +293,16 @@ class UNet3DConditionModel(ModelBase):
             if trace is not None:
                 trace.append((f"up_blocks.{i}", x, g))
 
+        if ctx.dup_pending:                       # no cross-attention anywhere: duplicate at the very end
+            x = ops.dup_rows(x)
+            g = E.Geo(g.b * 2, g.t, g.h, g.w)
+            ctx.dup_pending = False
         c0 = self.conv_in.out_channels
         x = ops.groupnorm(x, g.n, g.hw, own["norm_out"][0], own["norm_out"][1], self.conv_norm_out.eps, True, 32)
         eps = ops.conv3x3(x.view(g.n, g.h, g.w, c0), own["conv_out"][0], own["conv_out"][1], out_f32=True)
         if _raw_eps:
             return eps, g            # fp32 [B*T*h*w, 4] channels-last, consumed by the fused CFG+scheduler kernel
-        out = ops.unet_out_finalize(eps, b, g.t, h, w, dt)
+        out = ops.unet_out_finalize(eps, b_full, g.t, h, w, dt)
         if not return_dict:
             return (out,)
         return UNet3DConditionOutput(sample=out)

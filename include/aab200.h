@@ -72,6 +72,8 @@ int aab_timestep_embed(const float* t, int t_count, void* out, int b, int dim, i
 int aab_geglu(const void* x, long ldx, void* out, long ldo, long rows, int nh, int is_bf16, void* stream);
 int aab_upsample2x(const void* x, void* y, long n, int h, int w, int c, void* stream);
 int aab_copy2d(const void* src, long lds, void* dst, long ldd, long rows, int cols, void* stream);
+/* dst[0:bytes] = dst[bytes:2*bytes] = src: batch duplication for the shared CFG prefix (torch.cat([latents] * 2), models/pipeline.py:165) */
+int aab_dup_rows(const void* src, void* dst, long bytes, void* stream);
 int aab_transpose(const void* src, long lds, long src_batch, void* dst, int nb, int rows, int cols, void* stream);
 
 /* Classifier-free guidance + scheduler step + layout shuffles in one kernel (models/pipeline.py:180-192):

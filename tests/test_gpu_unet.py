@@ -107,3 +107,25 @@ def test_unet_config1_fullsize():
     """BASELINE config 1 shapes on the full-size architecture: sample [1,4,8,32,32], text [1,77,1024], t=500, motion 4."""
     cfg = dict(sample_size=32, motion_mask=True, motion_strength=True)
     _run_case(cfg, torch.float16, b=1, f=8, hw=32, lk=77, trace=True)
+
+
+def test_cfg_shared_prefix_matches_duplicated_batch():
+    """The shared-prefix evaluation (one copy of the latents per CFG pair, duplicated at the first text cross-attention)
+    equals the reference's `torch.cat([latents] * 2)` evaluation up to the GroupNorm summation order."""
+    from util import check
+    dtype = torch.float16
+    oracle, ours = _models(SMALL, dtype)
+    inp = _inputs(1, 4, 16, 77, SMALL["cross_attention_dim"], dtype)
+    g = torch.Generator().manual_seed(9)
+    ehs = torch.randn(2, 77, SMALL["cross_attention_dim"], generator=g).to(dtype).cuda()
+    mot = torch.tensor([4.0], device="cuda")
+    dup = ours(inp["sample"].expand(2, -1, -1, -1, -1), 321, ehs, condition_latent=inp["cond"].expand(2, -1, -1, -1, -1),
+               mask=inp["mask"], motion=mot).sample
+    shared = ours(inp["sample"], 321, ehs, condition_latent=inp["cond"], mask=inp["mask"], motion=mot,
+                  _cfg_shared_prefix=True).sample
+    assert shared.shape == dup.shape == (2, 4, 4, 16, 16)
+    check("cfg shared prefix vs duplicated batch", shared, dup, 1e-2, 5e-3)
+    with torch.no_grad():
+        ref = oracle(inp["sample"].float().expand(2, -1, -1, -1, -1), 321, ehs.float(),
+                     inp["cond"].float().expand(2, -1, -1, -1, -1), inp["mask"].float(), motion=mot)
+    check("cfg shared prefix vs fp32 oracle", shared, ref, 2e-2, 1e-2)
