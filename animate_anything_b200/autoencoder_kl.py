@@ -226,8 +226,9 @@ class AutoencoderKL(ModelBase):
         mom = ops.conv3x3(h.view(g.n, g.h, g.w, c_last), own["enc_out"][0], own["enc_out"][1])   # [rows, 8]
         return ops.vae_enc_finalize(mom, own["quant"][0], own["quant"][1], 1.0, n, 1, g.h, g.w)[:, :, 0]
 
-    def _decode_chunk(self, prep, lat5: torch.Tensor, inv_scale: float) -> torch.Tensor:
-        """lat5 [b, 4, f, h, w] (already divided by scaling unless inv_scale != 1) -> fp32 [b, 3, f, 8h, 8w]."""
+    def _decode_chunk(self, prep, lat5: torch.Tensor, inv_scale: float, as_uint8: bool = False) -> torch.Tensor:
+        """lat5 [b, 4, f, h, w] (already divided by scaling unless inv_scale != 1) -> fp32 [b, 3, f, 8h, 8w]
+        (or uint8 frames [f, 8h, b*8w, 3] when `as_uint8`)."""
         own = prep.get(self)
         b, _, f, hh, ww = lat5.shape
         g = E.Geo(b * f, 1, hh, ww)
@@ -244,6 +245,8 @@ class AutoencoderKL(ModelBase):
         c0 = self.decoder.conv_out.in_channels
         h = ops.groupnorm(h, g.n, g.hw, own["dec_norm"][0], own["dec_norm"][1], 1e-6, True, 32)
         y = ops.conv3x3(h.view(g.n, g.h, g.w, c0), own["dec_out"][0], own["dec_out"][1], out_f32=True)   # [rows, 3]
+        if as_uint8:
+            return ops.vae_dec_finalize_u8(y, b, f, g.h, g.w, prep.dtype == torch.bfloat16)
         return ops.vae_dec_finalize(y, b, f, g.h, g.w, prep.dtype == torch.bfloat16)
 
     # ------------------------------------------------------------------ public API (diffusers surface)
@@ -279,3 +282,15 @@ class AutoencoderKL(ModelBase):
         for i in range(0, f, self.frame_chunk):
             outs.append(self._decode_chunk(prep, latents[:, :, i: i + self.frame_chunk].contiguous(), inv_scale))
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=2)
+
+    @torch.no_grad()
+    def decode_frames_uint8(self, latents: torch.Tensor, inv_scale: Optional[float] = None) -> torch.Tensor:
+        """decode_latents + tensor2vid fused: latents [b, 4, f, h, w] -> uint8 frames [f, 8h, b*8w, 3] on the device."""
+        prep = self._prepared()
+        if inv_scale is None:
+            inv_scale = 1.0 / self.config.scaling_factor
+        latents = latents.to(prep.dtype).contiguous()
+        f = latents.shape[2]
+        outs = [self._decode_chunk(prep, latents[:, :, i: i + self.frame_chunk].contiguous(), inv_scale, as_uint8=True)
+                for i in range(0, f, self.frame_chunk)]
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)

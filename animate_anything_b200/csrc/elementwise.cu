@@ -305,6 +305,32 @@ __global__ void vae_dec_finalize_kernel(const float* __restrict__ y, int ldc, fl
   out[i] = BF16 ? __bfloat162float(__float2bfloat16_rn(v)) : __half2float(__float2half_rn(v));
 }
 
+// decoder tail fused with diffusers tensor2vid (models/pipeline.py:205): conv_out result [B*F, H, W, ldc] (fp32) ->
+// uint8 frames [F, H, B*W, 3]:  x -> round to model dtype -> x*0.5 -> +0.5 -> clamp(0,1) -> *255 -> truncate
+// (separate fp32 multiply and add, like `video.mul_(std).add_(mean)`; numpy `astype("uint8")` truncates).
+template <bool BF16>
+__global__ void vae_dec_finalize_u8_kernel(const float* __restrict__ y, int ldc, uint8_t* __restrict__ out, int B, int F,
+                                           int H, int W) {
+  const long total = static_cast<long>(F) * H * B * W;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = i % W;
+  long r = i / W;
+  const int b = r % B;
+  r /= B;
+  const int yy = r % H;
+  const int f = r / H;
+  const float* src = y + (((static_cast<long>(b) * F + f) * H + yy) * W + x) * ldc;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = src[c];
+    v = BF16 ? __bfloat162float(__float2bfloat16_rn(v)) : __half2float(__float2half_rn(v));
+    v = __fadd_rn(__fmul_rn(v, 0.5f), 0.5f);
+    v = fminf(fmaxf(v, 0.0f), 1.0f);
+    out[i * 3 + c] = static_cast<uint8_t>(__fmul_rn(v, 255.0f));
+  }
+}
+
 // fp32 -> 16-bit convert (weights / small tensors)
 template <bool BF16>
 __global__ void cast_f32_kernel(const float* __restrict__ x, void* __restrict__ y, long n) {
@@ -449,6 +475,17 @@ extern "C" int aab_vae_dec_finalize(const float* y, int ldc, float* out, int b, 
   const long total = static_cast<long>(b) * 3 * f * h * w;
   if (is_bf16) vae_dec_finalize_kernel<true><<<AAB_GRID(total, 256), 256, 0, stream>>>(y, ldc, out, b, f, h, w);
   else vae_dec_finalize_kernel<false><<<AAB_GRID(total, 256), 256, 0, stream>>>(y, ldc, out, b, f, h, w);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_vae_dec_finalize_u8(const float* y, int ldc, void* out, int b, int f, int h, int w, int is_bf16,
+                                       void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const long total = static_cast<long>(b) * f * h * w;
+  if (is_bf16)
+    vae_dec_finalize_u8_kernel<true><<<AAB_GRID(total, 256), 256, 0, stream>>>(y, ldc, reinterpret_cast<uint8_t*>(out), b, f, h, w);
+  else
+    vae_dec_finalize_u8_kernel<false><<<AAB_GRID(total, 256), 256, 0, stream>>>(y, ldc, reinterpret_cast<uint8_t*>(out), b, f, h, w);
   AAB_LAUNCH_RET();
 }
 

@@ -409,3 +409,10 @@ def vae_dec_finalize(y: torch.Tensor, b, f, h, w, bf16: bool) -> torch.Tensor:
     out = torch.empty((b, 3, f, h, w), device=y.device, dtype=torch.float32)
     _lib.call("aab_vae_dec_finalize", _ptr(y), y.stride(0), _ptr(out), b, f, h, w, int(bf16), _stream())
     return out
+
+
+def vae_dec_finalize_u8(y: torch.Tensor, b, f, h, w, bf16: bool) -> torch.Tensor:
+    """conv_out result -> uint8 frames [f, h, b*w, 3] (diffusers tensor2vid layout and rounding)."""
+    out = torch.empty((f, h, b * w, 3), device=y.device, dtype=torch.uint8)
+    _lib.call("aab_vae_dec_finalize_u8", _ptr(y), y.stride(0), _ptr(out), b, f, h, w, int(bf16), _stream())
+    return out

@@ -206,8 +206,12 @@ class LatentToVideoPipeline:
                     callback(i, t, dst)
             latents = src
 
-        video_tensor = self.decode_latents(latents)
-        video = video_tensor if output_type == "pt" else tensor2vid(video_tensor)
+        if output_type == "pt":
+            video = self.decode_latents(latents)
+        else:
+            # decode_latents + tensor2vid fused on the device (uint8 frames, 4x less D2H traffic than the fp32 video)
+            frames = self.vae.decode_frames_uint8(latents).cpu().numpy()
+            video = [frames[i] for i in range(frames.shape[0])]
         self.last_gpu_launches = _lib.launch_count() - launches0
         if not return_dict:
             return (video, latents)

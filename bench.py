@@ -223,17 +223,20 @@ def run_product(args):
         launches = launches + (per_step or 0) * STEPS_DDIM * args.steps
     finite = bool(torch.isfinite(lat.float()).all().item())
 
-    # ---- e2e: host inputs (pinned) copied in every step, decoded video read back to the host every step
+    # ---- e2e: the call a user makes — pinned HOST inputs copied in every step, default output (uint8 numpy frames, i.e.
+    # decode + tensor2vid fused on the device, then one D2H read of the frames) returned on the host every step
     h2d = sum(v.numel() * v.element_size() for v in host.values())
-    host_out = torch.empty((1, 3, FRAMES, HW, HW), dtype=torch.float32).pin_memory()
-    d2h = host_out.numel() * host_out.element_size()
+    d2h = FRAMES * HW * HW * 3
+    kw_np = dict(kw)
+    kw_np["output_type"] = "np"
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for _ in range(args.steps):
         inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        video, _ = one_clip(inp)
-        host_out.copy_(video, non_blocking=True)
+        frames, _ = pipe(prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
+                         latents=inp["latents"], condition_latent=inp["condition_latent"], mask=inp["mask"], **kw_np)
+        assert len(frames) == FRAMES and frames[0].dtype.name == "uint8"
     e3.record()
     barrier()
     sampler.stop_flag = True

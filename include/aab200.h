@@ -89,6 +89,8 @@ int aab_vae_enc_finalize(const void* mom, int ldm, const float* wq, const float*
 int aab_vae_dec_in(const void* lat, float inv_scale, const float* wp, const float* bp, void* out, int b, int f, int h, int w,
                    int is_bf16, void* stream);
 int aab_vae_dec_finalize(const float* y, int ldc, float* out, int b, int f, int h, int w, int is_bf16, void* stream);
+/* decoder tail fused with diffusers tensor2vid (models/pipeline.py:205): uint8 frames [f, h, b*w, 3] */
+int aab_vae_dec_finalize_u8(const float* y, int ldc, void* out, int b, int f, int h, int w, int is_bf16, void* stream);
 
 int aab_cast_f32(const float* x, void* y, long n, int is_bf16, void* stream);
 int aab_num_sms(void);

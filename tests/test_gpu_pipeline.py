@@ -118,3 +118,9 @@ def test_full_loop(sched_name, steps):
     frames, _ = pipe(prompt_embeds=pe, negative_prompt_embeds=ne, latents=lat, condition_latent=cond, mask=mask,
                      motion=[4], guidance_scale=9.0, num_inference_steps=steps, return_dict=False)
     assert len(frames) == 4 and frames[0].shape == (128, 128, 3) and frames[0].dtype.name == "uint8"
+    # the fused uint8 path is bit-identical to diffusers' tensor2vid applied to the float video
+    from animate_anything_b200.pipeline import tensor2vid
+    ref_frames = tensor2vid(vid.clone())
+    import numpy as np
+    for a, b2 in zip(frames, ref_frames):
+        assert np.array_equal(a, b2)
