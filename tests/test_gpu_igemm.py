@@ -8,7 +8,8 @@ from util import check
 
 pytestmark = pytest.mark.gpu
 
-TOL = {torch.float16: (1e-3, 2e-3), torch.bfloat16: (8e-3, 1.6e-2)}   # (rtol, atol) with |out| ~ O(1)
+# fp16: the north-star tolerance (rtol=1e-3, atol=1e-4).  bf16 has 3 fewer mantissa bits: 8x looser.
+TOL = {torch.float16: (1e-3, 1e-4), torch.bfloat16: (8e-3, 8e-4)}
 
 
 def _ops():

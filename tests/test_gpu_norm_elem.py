@@ -8,7 +8,8 @@ import torch.nn.functional as F
 from util import check
 
 pytestmark = pytest.mark.gpu
-TOL = {torch.float16: (1e-3, 1e-3), torch.bfloat16: (8e-3, 8e-3)}
+# fp16: the north-star tolerance (rtol=1e-3, atol=1e-4); bf16 8x looser
+TOL = {torch.float16: (1e-3, 1e-4), torch.bfloat16: (8e-3, 8e-4)}
 
 
 def _rand(shape, dtype, scale=1.0, seed=0, shift=0.0):
