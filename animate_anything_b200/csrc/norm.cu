@@ -9,6 +9,7 @@
 //   * LayerNorm over C (one warp per token row, exact two-pass variance in registers).
 // Algorithmic bytes: stats = 1 read of the activation; apply = 1 read + 1 write; layernorm = 1 read + 1 write.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace aab {
 
@@ -332,12 +333,19 @@ static int gn_launch_cfg(int C, long samples, long rows, int* threads, int* rows
   int rpi = 256 / V;
   if (rpi < 1) rpi = 1;
   *threads = V * rpi;
-  // ~4 CTAs per SM in total, at least 4 row-iterations per CTA
-  long want = (8L * 148 + samples - 1) / samples;
-  long maxc = (rows + 8L * rpi - 1) / (8L * rpi);
-  if (want > maxc) want = maxc;
-  if (want < 1) want = 1;
-  long rpc = (rows + want - 1) / want;
+  // The row partition depends on (rows, C) only -- never on the number of samples -- so a sample's statistics are
+  // summed in the same order whatever batch it arrives in (CFG halves split over two GPUs stay bit-identical to the
+  // batched evaluation).  Elements per CTA from the measured sweep (profiles/r01_gn_chunk_sweep.md): 72K for the
+  // wide-row levels (C <= 640, or very large samples), 18K where C >= 1280 (few rows per sample: CTA count matters),
+  // 12K for tiny samples; at least 8 row-iterations per CTA; at most 1024 chunks per sample.
+  (void)samples;
+  const long elems = rows * C;
+  long tgt = 73728;
+  if (elems < (1L << 18)) tgt = 12288;
+  else if (C >= 1280 && elems < (1L << 23)) tgt = 18432;
+  long rpc = (tgt + C - 1) / C;
+  if (rpc < 8L * rpi) rpc = 8L * rpi;
+  if ((rows + rpc - 1) / rpc > 1024) rpc = (rows + 1023) / 1024;
   rpc = ((rpc + rpi - 1) / rpi) * rpi;
   *rows_per_cta = static_cast<int>(rpc);
   *chunks = static_cast<int>((rows + rpc - 1) / rpc);

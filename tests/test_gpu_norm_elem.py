@@ -34,6 +34,17 @@ def test_groupnorm(dtype, samples, rows, c, silu):
     check(f"groupnorm s{samples} r{rows} c{c} {dtype}", y, ref, *TOL[dtype])
 
 
+def test_groupnorm_batch_invariant():
+    """A sample's output does not depend on the batch it is normalised in (fixed (rows, C) row partition)."""
+    from animate_anything_b200 import ops
+    x = _rand((4 * 1088, 320), torch.float16, 1.5, 5, shift=0.3)
+    gamma = _rand((320,), torch.float32, 0.2, 2, shift=1.0)
+    beta = _rand((320,), torch.float32, 0.2, 3)
+    full = ops.groupnorm(x, 4, 1088, gamma, beta, 1e-5, True)
+    one = ops.groupnorm(x[2 * 1088:3 * 1088].contiguous(), 1, 1088, gamma, beta, 1e-5, True)
+    assert torch.equal(full[2 * 1088:3 * 1088], one)
+
+
 def test_groupnorm_concat():
     from animate_anything_b200 import ops
     dtype = torch.float16
