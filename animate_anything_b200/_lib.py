@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaab200.so")
+LIB_PATH = os.environ.get("AAB_LIB_PATH") or os.path.join(_HERE, "libaab200.so")   # override: A/B builds while tuning
 
 MAX_TAPS = 9
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2

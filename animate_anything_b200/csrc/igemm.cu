@@ -30,14 +30,10 @@ constexpr int OUT_CHUNK_BYTES = BM * 32 * 2;     // one 32-column output chunk (
 constexpr int NUM_EPI_GROUPS = 4;                // epilogue warpgroups (4 warps each): latency-bound chains, so more in parallel
 constexpr int NUM_THREADS = 32 * (2 + 4 * NUM_EPI_GROUPS);  // warp0 TMA, warp1 MMA, warps 2..17 epilogue
 
-// DEEP = epilogue-heavy launches (few K iterations per tile): one pipeline stage less, staging ring twice as deep
-// (residual prefetch distance / store slack 7 chunks instead of 3).
-template <int BN, bool DEEP>
+// smem ring depth per tile width: 192 KiB of operands in flight whatever BN
+template <int BN>
 struct Cfg {
-  static constexpr int STAGES_BASE = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
-  static constexpr int STAGES = DEEP ? ((BN == 64 || BN == 32) ? STAGES_BASE - 2 : STAGES_BASE - 1) : STAGES_BASE;
-  static constexpr int NBUF = DEEP ? 8 : 4;
-  static constexpr int NBUF_LOG2 = DEEP ? 3 : 2;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator stages
   static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 4 /*epilogue groups*/ * OUT_CHUNK_BYTES +
@@ -81,14 +77,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
              const __grid_constant__ CUtensorMap tmR, const IgemmParams p) {
-  using C = Cfg<BN, false>;
+  using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   constexpr bool GEGLU = (EPI == 1);
+  constexpr int OUT_BN = GEGLU ? BN / 2 : BN;
   constexpr bool HAS_RES = (EPI == 3);
   constexpr bool HAS_BIAS2 = (EPI == 4);
   constexpr bool HAS_SILU = (EPI == 5);
   constexpr bool DIRECT = (EPI == 2);
-  constexpr int OUT_BN = GEGLU ? BN / 2 : BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;
@@ -158,7 +154,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int kb = 0; kb < kb_per_tap; ++kb, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
-            w_empty.wait(&empty_bar[s], ph ^ 1);
+            if (!(p.flags & AAB_F_DBG_NO_SYNC)) w_empty.wait(&empty_bar[s], ph ^ 1);
+#ifdef AAB_IGEMM_TRACE
+            if (p.dbg && blockIdx.x == 0 && it < 96) p.dbg[16 + it] = static_cast<unsigned long long>(clock64());
+#endif
+            if (p.flags & AAB_F_DBG_NO_LOAD) {
+              if (!(p.flags & AAB_F_DBG_NO_SYNC)) mbar_arrive(&full_bar[s]);
+              continue;
+            }
             mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + C::B_STAGE_BYTES);
             const int kc = kb * BK;
             if (kc < p.Kc1)
@@ -178,30 +181,51 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (p.dbg) atomicAdd(p.dbg + 15, static_cast<unsigned long long>(clock64() - t_start));   // slot 15: producer lifetime
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    WaitTimer w_full(p.dbg), w_tempty(p.dbg);
-    uint32_t it = 0;
-    uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
-      const uint32_t as = tl & 1;
-      const uint32_t aph = (tl >> 1) & 1;
-      // ragged last N tile: issue the MMA only over the valid columns (multiple of 16); the TMA box of B is zero-filled
-      // beyond N, so no extra traffic either.  N = 320 -> tiles of 256 + 64 columns instead of 3 x 128.
-      int n_mma = BN;
-      if (!GEGLU) {
-        const int nvalid = p.N - (tile % p.num_n_tiles) * BN;
-        if (nvalid < BN) n_mma = (nvalid + 15) & ~15;
-      }
-      const uint32_t idesc = make_idesc_f16(bf16 ? 1 : 0, BM, n_mma, 0, 0);
-      w_tempty.wait(&tempty_bar[as], aph ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + as * BN;
-      for (int ki = 0; ki < k_iters; ++ki, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        w_full.wait(&full_bar[s], ph);
-        tc_fence_after();
-        if (elect_one()) {
+    // ===================================================== MMA issuer: ONE elected thread runs the whole loop.
+    // Measured (profiles/r01_igemm_issue_trace.md): with "wait full -> 4 x tcgen05.mma -> commit" per k-block the
+    // issuing thread needed ~750 clk per k-block where the tensor pipe needs ~590 (raw issue rate): the blocking
+    // mbarrier wait sat between two k-blocks' MMAs and let the pipe's short queue run dry.  So the NEXT stage's full
+    // barrier is peeked (non-blocking test_wait) in the middle of the current k-block's MMAs; when it is already
+    // complete -- the common case -- the next k-block's MMAs follow back to back.
+    if (elect_one()) {
+      WaitTimer w_full(p.dbg), w_tempty(p.dbg);
+      const bool nosync = (p.flags & AAB_F_DBG_NO_SYNC) != 0;
+      const bool nomma = (p.flags & AAB_F_DBG_NO_MMA) != 0;
+#ifdef AAB_IGEMM_TRACE
+      const bool trace = p.dbg != nullptr && blockIdx.x == 0;
+#endif
+      uint32_t it = 0;
+      uint32_t tl = 0;
+      bool ready = false;   // full barrier of k-block `it` already observed complete
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+        const uint32_t as = tl & 1;
+        const uint32_t aph = (tl >> 1) & 1;
+        // ragged last N tile: issue the MMA only over the valid columns (multiple of 16); the TMA box of B is
+        // zero-filled beyond N, so no extra traffic either.
+        int n_mma = BN;
+        if (!GEGLU) {
+          const int nvalid = p.N - (tile % p.num_n_tiles) * BN;
+          if (nvalid < BN) n_mma = (nvalid + 15) & ~15;
+        }
+        const uint32_t idesc = make_idesc_f16(bf16 ? 1 : 0, BM, n_mma, 0, 0);
+        w_tempty.wait(&tempty_bar[as], aph ^ 1);
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int ki = 0; ki < k_iters; ++ki, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          if (!nosync && !ready) w_full.wait(&full_bar[s], ph);
+          tc_fence_after();
+#ifdef AAB_IGEMM_TRACE
+          if (trace && it < 96) p.dbg[16 + 96 + it] = static_cast<unsigned long long>(clock64());
+#endif
+          const int s1 = (it + 1) % STAGES;
+          const uint32_t ph1 = ((it + 1) / STAGES) & 1;
+          if (nomma) {
+            mbar_arrive(&empty_bar[s]);
+            if (ki == k_iters - 1) mbar_arrive(&tfull_bar[as]);
+            ready = false;
+            continue;
+          }
           const uint32_t a_addr = smem_u32(smA + s * A_STAGE_BYTES);
           const uint32_t b_addr = smem_u32(smB + s * C::B_STAGE_BYTES);
 #pragma unroll
@@ -209,17 +233,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const uint64_t da = make_desc_kmajor_sw128(a_addr + k * 32);
             const uint64_t db = make_desc_kmajor_sw128(b_addr + k * 32);
             umma_f16_ss(tmem_d, da, db, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+            if (k == BK / 32 - 1) ready = !nosync && !(p.flags & AAB_F_DBG_NO_PEEK) && mbar_test_wait(&full_bar[s1], ph1);
           }
-          umma_commit(&empty_bar[s]);
+          if (!nosync) umma_commit(&empty_bar[s]);
           if (ki == k_iters - 1) umma_commit(&tfull_bar[as]);
+#ifdef AAB_IGEMM_TRACE
+          if (trace && it < 96) p.dbg[16 + 192 + it] = static_cast<unsigned long long>(clock64());
+#endif
         }
-        __syncwarp();
       }
-    }
-    if (lane_id() == 0) {
       w_full.flush(p.dbg, 1);                                   // slot 1: MMA waiting for TMA data
       w_tempty.flush(p.dbg, 2);                                 // slot 2: MMA waiting for a drained accumulator
     }
+    __syncwarp();
   } else {
     // ===================================================== epilogue: warps 2..17 = four independent groups of four warps
     // (TMEM lane quarter = warp % 4).  Group eg owns the 32-column chunks with (chunk index % 4 == eg) of every tile, ONE
@@ -497,7 +523,7 @@ int num_sms() {
 template <int BN, int EPI>
 static int launch_bn(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& d,
                      const CUtensorMap& r, const IgemmParams& p, int max_ctas, cudaStream_t stream) {
-  using CF = Cfg<BN, false>;
+  using CF = Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =

@@ -11,7 +11,10 @@
 #define AAB_F_BF16 1      /* 16-bit type is bfloat16 (else float16) */
 #define AAB_F_DIRECT 2    /* epilogue stores straight to global memory instead of smem + TMA store */
 #define AAB_F_OUT_F32 4   /* output is float32 (direct store only) */
-#define AAB_F_DEEP_RING 16 /* experiment: 8-buffer output staging ring, one TMA pipeline stage less */
+#define AAB_F_DBG_NO_MMA 64   /* diagnostics only (wrong results): stages are released without issuing tcgen05.mma -> pure TMA feed rate */
+#define AAB_F_DBG_NO_PEEK 4096 /* diagnostics only: blocking full-barrier wait before every k-block (the pre-peek issue loop) */
+#define AAB_F_DBG_NO_SYNC 256 /* diagnostics only: with NO_LOAD, the MMA warp neither waits for stages nor commits them -> raw tcgen05.mma issue rate */
+#define AAB_F_DBG_NO_LOAD 128 /* diagnostics only (wrong results): no TMA loads, stages are always full -> pure MMA + epilogue rate */
 #define AAB_F_GEGLU 8     /* B rows [0,N/2) are values, [N/2,N) gates: out = value * gelu(gate), N/2 columns */
 
 #ifdef __cplusplus

@@ -4,6 +4,7 @@ to torch compute.
 """
 from __future__ import annotations
 
+import os
 import ctypes as C
 import math
 from typing import Optional, Sequence
@@ -15,6 +16,7 @@ from ._lib import ACT_GELU, ACT_NONE, ACT_SILU, F_BF16, F_DIRECT, F_GEGLU, F_OUT
 
 NUM_SMS = 148
 IGEMM_DEBUG = None       # optional uint64[16] device tensor: per-role wait-cycle counters (tools/igemm_roles.py)
+IGEMM_DBG_FLAGS = 4096 if os.environ.get("AAB_IGEMM_NOPEEK") else 0     # tools/igemm_roles.py only: AAB_F_DBG_NO_MMA (64) / AAB_F_DBG_NO_LOAD (128); results are wrong by design
 IGEMM_PROFILE = None     # bench.py sets this to a list to time every implicit-GEMM launch with CUDA events
 
 
@@ -59,19 +61,20 @@ def pick_box(dims: Sequence[int], fixed_one: Sequence[int] = ()) -> list:
 
 
 def pick_block_n(n_out: int, m_tiles: int, geglu: bool = False, k_total: int = 1 << 30) -> int:
-    """Largest tile width that still yields at least one tile per SM.  A ragged last N tile costs neither MMA cycles
-    (per-tile UMMA N) nor traffic (TMA zero-fill), so wider is better: fewer re-reads of the activation rows."""
-    cands = [256, 128] if geglu else [256, 128, 64]
-    if not geglu and k_total <= 384 and n_out <= 640:
-        # HBM-bound (tiny K): what matters is bytes of A in flight = stages x 16 KiB; BN=128 has 6 stages, BN=256 has 4
-        cands = [128, 64]
-    for bn in cands:
-        obn = bn // 2 if geglu else bn
-        if obn >= 2 * n_out and bn != cands[-1]:
-            continue
-        if m_tiles * -(-n_out // obn) >= NUM_SMS:
-            return bn
-    return cands[-1]
+    """Tile width (GEMM columns, multiple of 32, <= 256).  Measured (profiles/r01_igemm_roles_small.log): a k-block
+    costs ~520-660 clk whatever the tile width (operand feed, not MMA rate), so the widest tile wins wherever the main
+    loop dominates -- even when it leaves SMs without a tile (8x8 level: 85 tiles of 256 beat 170 tiles of 128 by 1.7x).
+    A ragged last N tile costs neither MMA cycles (per-tile UMMA N) nor traffic (TMA zero-fill)."""
+    if geglu:
+        return 256 if n_out > 64 else 128
+    if m_tiles <= 2:
+        return 64           # weight-streaming (GEMV-like: text K/V, time embedding): spread the weight rows over many CTAs
+    if os.environ.get("AAB_SMALLK_BN"):
+        return int(os.environ["AAB_SMALLK_BN"]) if (k_total <= 384 and n_out <= 640) else 256
+    if k_total <= 384 and n_out <= 640:
+        # epilogue/HBM-bound (tiny K): more CTAs in flight hide the store drain; BN=128 has 6 stages, BN=64 has 8
+        return 128 if m_tiles * -(-n_out // 128) >= NUM_SMS else 64
+    return 256
 
 
 def _fix_strides(dims, strides):
@@ -151,7 +154,7 @@ def igemm(a: torch.Tensor, a_dims, a_strides, w: torch.Tensor, n: int, kc: int, 
     d.out_scale = out_scale
     d.act = act
     flags = (F_BF16 if bf else 0) | (F_GEGLU if geglu else 0) | (F_OUT_F32 if out_f32 else 0) | (F_DIRECT if direct else 0)
-    d.flags = flags
+    d.flags = flags | IGEMM_DBG_FLAGS
     if block_n is None:
         if n_out < 64 and not geglu:
             block_n = 32 if n_out <= 32 else 64
