@@ -75,6 +75,8 @@ _SIGS = {
                        C.c_int, C.c_void_p],
     "aab_vae_dec_finalize": [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
     "aab_vae_dec_finalize_u8": [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
+    "aab_add_noise": [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_long,
+                      C.c_int, C.c_void_p],
     "aab_cast_f32": [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p],
 }
 

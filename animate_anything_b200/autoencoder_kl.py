@@ -206,7 +206,8 @@ class AutoencoderKL(ModelBase):
         x = self._mid_attention(ctx, mid.attentions[0], x, g)
         return E.resnet_forward(ctx, mid.resnets[1], x, g)
 
-    def _encode_chunk(self, prep, x: torch.Tensor) -> torch.Tensor:
+    def _encode_chunk(self, prep, x: torch.Tensor, bf=None, scale: float = 1.0) -> torch.Tensor:
+        """x [n, 3, H, W] -> moments [n, 8, h, w]; with bf=(b, f) (n = b*f) -> scaled moments [b, 8, f, h, w]."""
         own = prep.get(self)
         n, _, hh, ww = x.shape
         if hh % 8 or ww % 8:
@@ -224,6 +225,8 @@ class AutoencoderKL(ModelBase):
         c_last = self.encoder.conv_out.in_channels
         h = ops.groupnorm(h, g.n, g.hw, own["enc_norm"][0], own["enc_norm"][1], 1e-6, True, 32)
         mom = ops.conv3x3(h.view(g.n, g.h, g.w, c_last), own["enc_out"][0], own["enc_out"][1])   # [rows, 8]
+        if bf is not None:
+            return ops.vae_enc_finalize(mom, own["quant"][0], own["quant"][1], scale, bf[0], bf[1], g.h, g.w)
         return ops.vae_enc_finalize(mom, own["quant"][0], own["quant"][1], 1.0, n, 1, g.h, g.w)[:, :, 0]
 
     def _decode_chunk(self, prep, lat5: torch.Tensor, inv_scale: float, as_uint8: bool = False) -> torch.Tensor:
@@ -260,6 +263,21 @@ class AutoencoderKL(ModelBase):
         if not return_dict:
             return (posterior,)
         return AutoencoderKLOutput(latent_dist=posterior)
+
+    @torch.no_grad()
+    def encode_video_latents(self, frames: torch.Tensor, scale: float = 0.18215) -> torch.Tensor:
+        """Fused `tensor_to_vae_latent` (utils/common.py:12-20): frames [b, f, 3, H, W] -> `latent_dist.mode() * scale`
+        laid out [b, 4, f, h, w]; the two rearranges and the scaling happen inside the quant_conv kernel (with the
+        reference's two 16-bit roundings)."""
+        prep = self._prepared()
+        b, f = frames.shape[:2]
+        x = frames.to(prep.dtype).reshape(b * f, *frames.shape[2:])
+        if f <= self.frame_chunk:
+            return self._encode_chunk(prep, x, bf=(b, f), scale=scale)[:, :4].contiguous()
+        outs = [self._encode_chunk(prep, frames[:, i: i + self.frame_chunk].to(prep.dtype).reshape(-1, *frames.shape[2:]),
+                                   bf=(b, min(self.frame_chunk, f - i)), scale=scale)[:, :4]
+                for i in range(0, f, self.frame_chunk)]
+        return torch.cat(outs, dim=2).contiguous()
 
     @torch.no_grad()
     def decode(self, z: torch.Tensor, return_dict: bool = True, generator=None):

@@ -261,6 +261,10 @@ __device__ __forceinline__ float2 unpack2(uint32_t u, bool bf16) {
     return __half22float2(h);
   }
 }
+// value after a round trip through the 16-bit type (what a torch op on a 16-bit tensor leaves behind)
+__device__ __forceinline__ float round16(float v, bool bf16) {
+  return bf16 ? __bfloat162float(__float2bfloat16_rn(v)) : __half2float(__float2half_rn(v));
+}
 __device__ __forceinline__ float load_elem(const void* p, size_t i, bool bf16) {
   return bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i])
               : __half2float(reinterpret_cast<const __half*>(p)[i]);

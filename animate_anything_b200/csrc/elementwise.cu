@@ -247,7 +247,9 @@ __global__ void vae_enc_finalize_kernel(const void* __restrict__ mom, int ldm, c
     float acc = bq[c];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc = fmaf(wq[c * 8 + j], m[j], acc);
-    store_elem(out, (((static_cast<long>(b) * 8 + c) * F + f) * H + y) * W + x, acc * scale, BF16);
+    // scale != 1: the reference multiplies the 16-bit moments by 0.18215 afterwards (utils/common.py:18) -> two roundings
+    const float v = (scale == 1.0f) ? acc : round16(acc, BF16) * scale;
+    store_elem(out, (((static_cast<long>(b) * 8 + c) * F + f) * H + y) * W + x, v, BF16);
   }
 }
 
@@ -329,6 +331,26 @@ __global__ void vae_dec_finalize_u8_kernel(const float* __restrict__ y, int ldc,
     v = fminf(fmaxf(v, 0.0f), 1.0f);
     out[i * 3 + c] = static_cast<uint8_t>(__fmul_rn(v, 255.0f));
   }
+}
+
+// x_t = sa * repeat(x0 over frames) + sb * noise, each product and the sum rounded to 16 bits like the three torch ops of
+// DDPMScheduler.add_noise (utils/common.py:40-47: repeat 'b c 1 h w -> b c f h w' + scheduler.add_noise).
+// x0 [B*C, FX, HW] with FX in {1, F}; noise / out [B*C, F, HW].
+template <bool BF16>
+__global__ void add_noise_kernel(const void* __restrict__ x0, const void* __restrict__ noise, float sa, float sb,
+                                 void* __restrict__ out, long bc, int F, int FX, long HW) {
+  const long total = bc * F * HW;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long p = i % HW;
+  const long r = i / HW;
+  const int f = static_cast<int>(r % F);
+  const long q = r / F;
+  const float x = load_elem(x0, (q * FX + (FX == 1 ? 0 : f)) * HW + p, BF16);
+  const float n = load_elem(noise, i, BF16);
+  const float t1 = round16(__fmul_rn(sa, x), BF16);
+  const float t2 = round16(__fmul_rn(sb, n), BF16);
+  store_elem(out, i, __fadd_rn(t1, t2), BF16);
 }
 
 // fp32 -> 16-bit convert (weights / small tensors)
@@ -486,6 +508,16 @@ extern "C" int aab_vae_dec_finalize_u8(const float* y, int ldc, void* out, int b
     vae_dec_finalize_u8_kernel<true><<<AAB_GRID(total, 256), 256, 0, stream>>>(y, ldc, reinterpret_cast<uint8_t*>(out), b, f, h, w);
   else
     vae_dec_finalize_u8_kernel<false><<<AAB_GRID(total, 256), 256, 0, stream>>>(y, ldc, reinterpret_cast<uint8_t*>(out), b, f, h, w);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_add_noise(const void* x0, const void* noise, float sa, float sb, void* out, long bc, int f, int fx,
+                             long hw, int is_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x0 || !noise || !out || bc < 1 || f < 1 || hw < 1 || (fx != 1 && fx != f)) return AAB_ERR_ARG;
+  const long total = bc * f * hw;
+  if (is_bf16) add_noise_kernel<true><<<AAB_GRID(total, 256), 256, 0, stream>>>(x0, noise, sa, sb, out, bc, f, fx, hw);
+  else add_noise_kernel<false><<<AAB_GRID(total, 256), 256, 0, stream>>>(x0, noise, sa, sb, out, bc, f, fx, hw);
   AAB_LAUNCH_RET();
 }
 

@@ -69,8 +69,6 @@ def pick_block_n(n_out: int, m_tiles: int, geglu: bool = False, k_total: int = 1
         return 256 if n_out > 64 else 128
     if m_tiles <= 2:
         return 64           # weight-streaming (GEMV-like: text K/V, time embedding): spread the weight rows over many CTAs
-    if os.environ.get("AAB_SMALLK_BN"):
-        return int(os.environ["AAB_SMALLK_BN"]) if (k_total <= 384 and n_out <= 640) else 256
     if k_total <= 384 and n_out <= 640:
         # epilogue/HBM-bound (tiny K): more CTAs in flight hide the store drain; BN=128 has 6 stages, BN=64 has 8
         return 128 if m_tiles * -(-n_out // 128) >= NUM_SMS else 64
@@ -397,6 +395,17 @@ def vae_enc_finalize(mom: torch.Tensor, wq, bq, scale, b, f, h, w) -> torch.Tens
     out = torch.empty((b, 8, f, h, w), device=mom.device, dtype=mom.dtype)
     _lib.call("aab_vae_enc_finalize", _ptr(mom), mom.stride(0), _ptr(wq), _ptr(bq), float(scale), _ptr(out), b, f, h, w,
               _is_bf16(mom), _stream())
+    return out
+
+
+def add_noise(x0: torch.Tensor, noise: torch.Tensor, sa: float, sb: float) -> torch.Tensor:
+    """x0 [b, c, 1|f, h, w], noise [b, c, f, h, w] (same 16-bit dtype, contiguous) -> sa * repeat(x0) + sb * noise."""
+    b, c, f, h, w = noise.shape
+    assert x0.dtype == noise.dtype and x0.shape[2] in (1, f) and x0.shape[:2] == noise.shape[:2]
+    x0, noise = x0.contiguous(), noise.contiguous()
+    out = torch.empty_like(noise)
+    _lib.call("aab_add_noise", _ptr(x0), _ptr(noise), float(sa), float(sb), _ptr(out), b * c, f, x0.shape[2], h * w,
+              _is_bf16(noise), _stream())
     return out
 
 

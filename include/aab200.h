@@ -92,6 +92,12 @@ int aab_vae_dec_finalize(const float* y, int ldc, float* out, int b, int f, int 
 /* decoder tail fused with diffusers tensor2vid (models/pipeline.py:205): uint8 frames [f, h, b*w, 3] */
 int aab_vae_dec_finalize_u8(const float* y, int ldc, void* out, int b, int f, int h, int w, int is_bf16, void* stream);
 
+/* Forward-diffuse the image latent to the first kept timestep: out = sa * repeat(x0 over f) + sb * noise with torch's
+ * per-op 16-bit roundings (utils/common.py:32-48 DDPM_forward_timesteps -> DDPMScheduler.add_noise; :22-30 DDPM_forward).
+ * x0 [bc, fx, hw] with fx in {1, f}; noise, out [bc, f, hw]. */
+int aab_add_noise(const void* x0, const void* noise, float sa, float sb, void* out, long bc, int f, int fx, long hw,
+                  int is_bf16, void* stream);
+
 int aab_cast_f32(const float* x, void* y, long n, int is_bf16, void* stream);
 int aab_num_sms(void);
 

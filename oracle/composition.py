@@ -189,6 +189,18 @@ def oracle_encode_image(vae, frames):
     return lat.reshape(b, f, *lat.shape[1:]).permute(0, 2, 1, 3, 4) * 0.18215
 
 
+def oracle_ddpm_forward_timesteps(x0, step, num_frames, scheduler, noise=None):
+    """utils/common.py:32-48 DDPM_forward_timesteps restated (noise drawn with torch.randn when not given, as the
+    reference does): keep the last `step` timesteps, repeat the single-frame latent, add noise at the first kept one."""
+    timesteps = scheduler.timesteps[len(scheduler.timesteps) - step:]
+    t = timesteps[0]
+    xt = x0.repeat(1, 1, num_frames, 1, 1) if x0.shape[2] == 1 else x0
+    if noise is None:
+        noise = torch.randn(xt.shape, dtype=xt.dtype, device=x0.device)
+    tt = torch.tensor([int(t)] * xt.shape[0], device=x0.device)
+    return scheduler.add_noise(xt, noise, tt), timesteps
+
+
 @torch.no_grad()
 def oracle_sampling_loop(unet, scheduler, latents, prompt_embeds, negative_prompt_embeds, condition_latent, mask,
                          motion, guidance_scale=9.0, num_inference_steps=50, timesteps=None, vae=None,

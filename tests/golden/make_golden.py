@@ -79,6 +79,35 @@ def main():
                 "vae_keys": sorted(vae.state_dict().keys())}, os.path.join(HERE, "pipeline_tiny_ref.pt"))
     print("pipeline golden:", video.shape, latents.shape, float(latents.abs().mean()), float(latents_dpm.abs().mean()))
 
+    common_golden(diffusers)
+
+
+def common_golden(diffusers):
+    """utils/common.py (verbatim) DDPM_forward_timesteps / tensor_to_vae_latent on the shim scheduler / VAE.
+    `imageio` is not installed here and is only used by the reference's video writers: stubbed for the import."""
+    import types
+    sys.modules.setdefault("imageio", types.ModuleType("imageio"))
+    from utils.common import DDPM_forward_timesteps, tensor_to_vae_latent      # verbatim reference
+    sched = diffusers.DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                                    clip_sample=False, set_alpha_to_one=False, steps_offset=1)
+    sched.set_timesteps(10)
+    g = torch.Generator().manual_seed(11)
+    x0 = torch.randn(2, 4, 1, 8, 8, generator=g)
+    out = {}
+    for name, dt in (("f32", torch.float32), ("bf16", torch.bfloat16), ("f16", torch.float16)):
+        torch.manual_seed(3)
+        xt, ts = DDPM_forward_timesteps(x0.to(dt), 4, 5, sched)
+        out[f"xt_{name}"] = xt
+        out["timesteps"] = ts
+    vae = diffusers.AutoencoderKL(**TINY_VAE).eval()
+    fill_deterministic(vae, seed=1)
+    frames = torch.randn(1, 2, 3, 32, 32, generator=g).clamp(-1, 1)
+    with torch.no_grad():
+        lat = tensor_to_vae_latent(frames, vae)
+    out.update(x0=x0, frames=frames, latents=lat)
+    torch.save(out, os.path.join(HERE, "common_ref.pt"))
+    print("common golden:", out["xt_f32"].shape, lat.shape, float(lat.abs().mean()))
+
 
 if __name__ == "__main__":
     main()

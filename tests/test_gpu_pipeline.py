@@ -124,3 +124,50 @@ def test_full_loop(sched_name, steps):
     import numpy as np
     for a, b2 in zip(frames, ref_frames):
         assert np.array_equal(a, b2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_common_ddpm_forward_timesteps_bit_exact(dtype):
+    """utils/common.py:32-48 through aab_add_noise: same seed -> same torch.randn noise -> bit-identical x_t (the
+    kernel reproduces the three 16-bit roundings of repeat + scheduler.add_noise), same kept timesteps."""
+    from oracle.composition import DDIMScheduler as OSched, oracle_ddpm_forward_timesteps
+    from animate_anything_b200.schedulers import DDIMScheduler
+    from animate_anything_b200.common import DDPM_forward_timesteps
+    osched, sched = OSched(**SCHED), DDIMScheduler(**SCHED)
+    osched.set_timesteps(25)
+    sched.set_timesteps(25)
+    g = torch.Generator().manual_seed(2)
+    for shape in ((1, 4, 1, 64, 64), (2, 4, 1, 24, 40), (1, 4, 6, 16, 16)):
+        x0 = torch.randn(*shape, generator=g).to(dtype).cuda()
+        torch.manual_seed(7)
+        xt, ts = DDPM_forward_timesteps(x0, 10, 16, sched)
+        torch.manual_seed(7)
+        ref, ots = oracle_ddpm_forward_timesteps(x0, 10, 16, osched)
+        assert xt.dtype == dtype and xt.shape == ref.shape
+        assert torch.equal(torch.as_tensor(ts).cpu(), torch.as_tensor(ots).cpu())
+        assert torch.equal(xt, ref), f"{shape} {dtype}: max diff {(xt.float() - ref.float()).abs().max().item()}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_common_tensor_to_vae_latent(dtype):
+    """utils/common.py:12-20 fused into the encoder tail: [b, f, 3, H, W] -> [b, 4, f, h, w] * 0.18215."""
+    from oracle.composition import AutoencoderKL as OVAE, oracle_encode_image
+    from animate_anything_b200.autoencoder_kl import AutoencoderKL
+    from animate_anything_b200.common import tensor_to_vae_latent
+    _no_tf32()
+    ovae, vae = _pair(OVAE, AutoencoderKL, VAE, dtype, seed=1)
+    g = torch.Generator().manual_seed(4)
+    frames = torch.randn(2, 3, 3, 64, 32, generator=g).clamp(-1, 1).to(dtype).cuda()
+    with torch.no_grad():
+        ref = oracle_encode_image(ovae, frames.float())
+        stock = oracle_encode_image(ovae.to(dtype), frames).float()
+    lat = tensor_to_vae_latent(frames, vae)
+    assert lat.shape == ref.shape == (2, 4, 3, 8, 4) and lat.dtype == dtype
+    e, es, sc = (lat.float() - ref).abs(), (stock - ref).abs(), ref.abs().mean().item()
+    print(f"tensor_to_vae_latent {dtype}: ref|mean|={sc:.4f} ours max={e.max().item():.3e} mean={e.mean().item():.3e} | "
+          f"stock max={es.max().item():.3e} mean={es.mean().item():.3e}")
+    assert e.mean().item() <= 1.5 * es.mean().item() + 2e-4 * sc
+    assert e.max().item() <= 2.5 * es.max().item() + 2e-3 * sc
+    # frame chunking path (f > frame_chunk) gives the same latents
+    vae.frame_chunk = 2
+    assert torch.equal(tensor_to_vae_latent(frames, vae), lat)

@@ -55,6 +55,27 @@ def test_sampling_loop_matches_reference_pipeline():
     assert torch.allclose(lat2, gold["latents_dpm"], rtol=1e-4, atol=1e-5)
 
 
+def test_common_functions_match_reference_utils():
+    """oracle restatements of utils/common.py (DDPM_forward_timesteps :32-48, tensor_to_vae_latent :12-20) against the
+    outputs of the verbatim reference functions (tests/golden/make_golden.py::common_golden)."""
+    from oracle.composition import oracle_ddpm_forward_timesteps, oracle_encode_image
+    gold = torch.load(os.path.join(HERE, "golden", "common_ref.pt"))
+    sched = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
+                          set_alpha_to_one=False, steps_offset=1)
+    sched.set_timesteps(10)
+    for name, dt in (("f32", torch.float32), ("bf16", torch.bfloat16), ("f16", torch.float16)):
+        torch.manual_seed(3)
+        xt, ts = oracle_ddpm_forward_timesteps(gold["x0"].to(dt), 4, 5, sched)
+        assert torch.equal(xt, gold[f"xt_{name}"]), name
+        assert torch.equal(torch.as_tensor(ts), torch.as_tensor(gold["timesteps"]))
+    pg = torch.load(os.path.join(HERE, "golden", "pipeline_tiny_ref.pt"))
+    vae = AutoencoderKL(**pg["vae_config"]).eval()
+    fill_deterministic(vae, seed=1)
+    with torch.no_grad():
+        lat = oracle_encode_image(vae, gold["frames"])
+    assert torch.allclose(lat, gold["latents"], rtol=1e-5, atol=1e-6)
+
+
 def test_shim_recalled_facts():
     """One assertion per RECALLED diffusers-0.24 fact that SURVEY.md 8(c) lists as most likely to be wrong."""
     from diffusers._impl import GEGLU, TemporalConvLayer, Timesteps, TimestepEmbedding, Upsample2D, ResnetBlock2D
