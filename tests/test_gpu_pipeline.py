@@ -171,3 +171,60 @@ def test_common_tensor_to_vae_latent(dtype):
     # frame chunking path (f > frame_chunk) gives the same latents
     vae.frame_chunk = 2
     assert torch.equal(tensor_to_vae_latent(frames, vae), lat)
+
+
+def test_eval_flow_like_train_eval():
+    """The sequence of train.py:731-770 `eval()` on small models: image -> VaeImageProcessor.preprocess ->
+    tensor_to_vae_latent -> DDPM_forward_timesteps(forward_t) -> pipeline(latents=, condition_latent=, mask=, motion=,
+    timesteps=kept) with DPM-Solver++ (what train.py:806 installs), against the same sequence on the fp32 oracle."""
+    import numpy as np
+    from oracle.composition import (AutoencoderKL as OVAE, DDIMScheduler as ODDIM, DPMSolverMultistepScheduler as ODPM,
+                                    OracleUNet3D, oracle_ddpm_forward_timesteps, oracle_encode_image,
+                                    oracle_sampling_loop)
+    from animate_anything_b200 import schedulers as S
+    from animate_anything_b200.autoencoder_kl import AutoencoderKL
+    from animate_anything_b200.common import DDPM_forward_timesteps, tensor_to_vae_latent
+    from animate_anything_b200.image_processor import VaeImageProcessor
+    from animate_anything_b200.pipeline import LatentToVideoPipeline
+    from animate_anything_b200.unet_3d_condition_mask import UNet3DConditionModel
+    _no_tf32()
+    dtype = torch.float16
+    ounet, unet = _pair(OracleUNet3D, UNet3DConditionModel, UNET, dtype, seed=0)
+    ovae, vae = _pair(OVAE, AutoencoderKL, VAE, dtype, seed=1)
+    osched = ODPM.from_config(ODDIM(**SCHED).config)
+    sched = S.DPMSolverMultistepScheduler.from_config(S.DDIMScheduler(**SCHED).config)
+    steps, forward_t, frames = 6, 4, 4
+    osched.set_timesteps(steps, device="cuda")
+    sched.set_timesteps(steps, device="cuda")
+    rng = np.random.default_rng(0)
+    img = rng.random((128, 128, 3)).astype(np.float32)                 # H, W, C in [0, 1]
+    inp = VaeImageProcessor().preprocess(img, 128, 128)                # [1, 3, 128, 128] in [-1, 1]
+    inp = inp.unsqueeze(0).to(dtype).cuda()                            # b f c h w (train.py:746)
+    cond = tensor_to_vae_latent(inp, vae)
+    torch.manual_seed(11)
+    init, ts = DDPM_forward_timesteps(cond, forward_t, frames, sched)
+    assert init.shape == (1, 4, frames, 16, 16) and len(ts) == forward_t
+    g = torch.Generator().manual_seed(5)
+    pe = torch.randn(1, 77, 128, generator=g).to(dtype).cuda()
+    ne = torch.randn(1, 77, 128, generator=g).to(dtype).cuda()
+    mask = (torch.rand(1, 1, 1, 16, 16, generator=g) > 0.4).to(dtype).cuda()
+    pipe = LatentToVideoPipeline(vae=vae, text_encoder=None, tokenizer=None, unet=unet, scheduler=sched)
+    video, lat = pipe(prompt_embeds=pe, negative_prompt_embeds=ne, latents=init, condition_latent=cond, mask=mask,
+                      motion=[5], guidance_scale=7.5, num_inference_steps=steps, timesteps=ts, return_dict=False)
+    assert len(video) == frames and video[0].shape == (128, 128, 3)
+    # the same sequence on the oracle: fp32 reference and stock 16-bit yard-stick, fed the same noise
+    torch.manual_seed(11)
+    noise = torch.randn(init.shape, dtype=dtype, device="cuda")
+    with torch.no_grad():
+        ocond = oracle_encode_image(ovae, inp.float())
+        oinit, ots = oracle_ddpm_forward_timesteps(ocond, forward_t, frames, osched, noise=noise.float())
+        assert [int(t) for t in ots] == [int(t) for t in ts]
+        _, ref = oracle_sampling_loop(ounet, osched, oinit, pe.float(), ne.float(), ocond, mask.float(), [5], 7.5, steps,
+                                      timesteps=ots)
+        osched2 = ODPM.from_config(ODDIM(**SCHED).config)
+        _, stock = oracle_sampling_loop(ounet.to(dtype), osched2, init, pe, ne, cond, mask, [5], 7.5, steps, timesteps=ots)
+    e, es, sc = (lat.float() - ref).abs(), (stock.float() - ref).abs(), ref.abs().mean().item()
+    print(f"eval flow: latents ref|mean|={sc:.4f} ours max={e.max().item():.3e} mean={e.mean().item():.3e} | "
+          f"stock fp16 max={es.max().item():.3e} mean={es.mean().item():.3e}")
+    assert e.mean().item() <= 3.0 * es.mean().item() + 5e-4 * sc
+    assert e.max().item() <= 4.0 * es.max().item() + 5e-3 * sc
