@@ -188,6 +188,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 
+// same, 16 columns -> 16 registers
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
 // Shared-memory matrix descriptor for a K-major operand tile stored as rows of 128 bytes (64 x 16-bit) with the
 // 128-byte swizzle that TMA SWIZZLE_128B produces.  8-row groups are 1024 B apart (SBO); LBO is unused for
 // swizzled K-major layouts.  Bits: [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1,
@@ -230,17 +241,32 @@ __host__ __device__ inline uint32_t make_idesc_f16(int is_bf16, int M, int N, in
 // ---------------------------------------------------------------- numeric helpers
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-// erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. below fp32 epsilon of the 16-bit-rounded result):
-// 1 rcp + 1 ex2 + 6 fma instead of libdevice erff's ~25 instructions with a branch.
+// MUFU without the denormal-scaling wrappers nvcc emits for non-ftz ex2/rcp (2 FSETP + 3 FMUL + FSEL per call)
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// x * sigmoid(x): 2 MUFU + 3 FP32 ops
+__device__ __forceinline__ float silu_fast_f(float x) { return x * rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
+// exact-erf GELU with erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, below the rounding of a 16-bit result):
+// 2 MUFU + 12 FP32 ops, branch-free (libdevice erff: ~25 instructions with a branch).
 __device__ __forceinline__ float gelu_fast_f(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  const float t = rcp_ftz(fmaf(0.3275911f, z, 1.0f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float e = 1.0f - poly * t * __expf(-z * z);      // erf(|x|/sqrt2)
-  return 0.5f * x + 0.5f * fabsf(x) * e;                  // 0.5*x*(1 + sign(x)*e)
+  const float ex = ex2_ftz((x * x) * -0.72134752044448170f);   // exp(-x^2 / 2)
+  const float e = fmaf(-(poly * t), ex, 1.0f);                  // erf(|x| / sqrt 2)
+  const float h = 0.5f * x;
+  return fmaf(fabsf(h), e, h);                                  // 0.5 x (1 + sign(x) e)
 }
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, bool bf16) {

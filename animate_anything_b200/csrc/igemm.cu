@@ -334,82 +334,105 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) rres[j4] = __ldg(rp + j4);
         }
-        float v[32];
-        float gt[GEGLU ? 32 : 1];
-        {
+        const bool last_read = (ci + NUM_EPI_GROUPS >= CPT || col + 32 * NUM_EPI_GROUPS >= p.n_out);
+        uint4 o[4];                               // the chunk's 32 outputs of this row, packed to 16 bits
+        float v[GEGLU ? 1 : 32];
+        if (GEGLU) {
+          // value and gate columns in two 16-column halves: 32 live accumulator registers instead of 64 (the 64-register
+          // version spilled inside this loop: 1.07 M local loads per launch, profiles/r01_ncu_full_summaries.md)
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t rv[16], rg[16];
+            tmem_ld_32x16(tmem_acc + cc + hf * 16, rv);
+            tmem_ld_32x16(tmem_acc + BN / 2 + cc + hf * 16, rg);
+            tmem_ld_wait();
+            if (hf == 1 && last_read) {
+              tc_fence_before();
+              mbar_arrive(&tempty_bar[as]);
+              released = true;
+            }
+            float vv[16], gg[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              vv[j] = __uint_as_float(rv[j]);
+              gg[j] = __uint_as_float(rg[j]);
+            }
+            if (p.bias != nullptr) {
+              const float4* bp = reinterpret_cast<const float4*>(p.bias + col + hf * 16);
+              const float4* gp = reinterpret_cast<const float4*>(p.bias + p.N / 2 + col + hf * 16);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 b = __ldg(bp + j4);
+                const float4 g = __ldg(gp + j4);
+                vv[j4 * 4 + 0] += b.x; vv[j4 * 4 + 1] += b.y; vv[j4 * 4 + 2] += b.z; vv[j4 * 4 + 3] += b.w;
+                gg[j4 * 4 + 0] += g.x; gg[j4 * 4 + 1] += g.y; gg[j4 * 4 + 2] += g.z; gg[j4 * 4 + 3] += g.w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) vv[j] *= gelu_fast_f(gg[j]);
+#pragma unroll
+            for (int j4 = 0; j4 < 2; ++j4) {
+              o[hf * 2 + j4].x = pack2(vv[j4 * 8 + 0], vv[j4 * 8 + 1], bf16);
+              o[hf * 2 + j4].y = pack2(vv[j4 * 8 + 2], vv[j4 * 8 + 3], bf16);
+              o[hf * 2 + j4].z = pack2(vv[j4 * 8 + 4], vv[j4 * 8 + 5], bf16);
+              o[hf * 2 + j4].w = pack2(vv[j4 * 8 + 6], vv[j4 * 8 + 7], bf16);
+            }
+          }
+        } else {
           uint32_t r[32];
           tmem_ld_32x32(tmem_acc + cc, r);
-          if (GEGLU) {
-            uint32_t r2[32];
-            tmem_ld_32x32(tmem_acc + BN / 2 + cc, r2);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) gt[j] = __uint_as_float(r2[j]);
-          } else {
-            tmem_ld_wait();
-          }
+          tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        }
-        if (ci + NUM_EPI_GROUPS >= CPT || col + 32 * NUM_EPI_GROUPS >= p.n_out) {
-          // last TMEM read of this group for this tile: give the accumulator stage back before the (slower) store path
-          tc_fence_before();
-          mbar_arrive(&tempty_bar[as]);
-          released = true;
+          if (last_read) {
+            // last TMEM read of this group for this tile: give the accumulator stage back before the (slower) store path
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[as]);
+            released = true;
+          }
         }
         if (!DIRECT) {
           // ---------------- fast path: n_out % 32 == 0, everything vectorised
-          if (p.bias != nullptr) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
+          if (!GEGLU) {
+            if (p.bias != nullptr) {
+              const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 b = __ldg(bp + j4);
-              v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
-            }
-          }
-          if (GEGLU) {
-            const float4* gp = reinterpret_cast<const float4*>(p.bias + p.N / 2 + col);
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.bias != nullptr) b = __ldg(gp + j4);
-              v[j4 * 4 + 0] *= gelu_fast_f(gt[j4 * 4 + 0] + b.x);
-              v[j4 * 4 + 1] *= gelu_fast_f(gt[j4 * 4 + 1] + b.y);
-              v[j4 * 4 + 2] *= gelu_fast_f(gt[j4 * 4 + 2] + b.z);
-              v[j4 * 4 + 3] *= gelu_fast_f(gt[j4 * 4 + 3] + b.w);
-            }
-          }
-          if (HAS_BIAS2 && bias2row != nullptr) {
-            const float4* bp = reinterpret_cast<const float4*>(bias2row + col);
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 b = __ldg(bp + j4);
-              v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
-            }
-          }
-          if (HAS_RES && resrow != nullptr) {
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const uint32_t w[4] = {rres[j4].x, rres[j4].y, rres[j4].z, rres[j4].w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = unpack2(w[e], bf16);
-                v[j4 * 8 + e * 2] += f.x;
-                v[j4 * 8 + e * 2 + 1] += f.y;
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 b = __ldg(bp + j4);
+                v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
               }
             }
-          }
-          if (HAS_SILU) {
+            if (HAS_BIAS2 && bias2row != nullptr) {
+              const float4* bp = reinterpret_cast<const float4*>(bias2row + col);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] * __fdividef(1.0f, 1.0f + __expf(-v[j]));
-          }
-          uint4 o[4];
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 b = __ldg(bp + j4);
+                v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
+              }
+            }
+            if (HAS_RES && resrow != nullptr) {
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            o[j4].x = pack2(v[j4 * 8 + 0], v[j4 * 8 + 1], bf16);
-            o[j4].y = pack2(v[j4 * 8 + 2], v[j4 * 8 + 3], bf16);
-            o[j4].z = pack2(v[j4 * 8 + 4], v[j4 * 8 + 5], bf16);
-            o[j4].w = pack2(v[j4 * 8 + 6], v[j4 * 8 + 7], bf16);
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const uint32_t w[4] = {rres[j4].x, rres[j4].y, rres[j4].z, rres[j4].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = unpack2(w[e], bf16);
+                  v[j4 * 8 + e * 2] += f.x;
+                  v[j4 * 8 + e * 2 + 1] += f.y;
+                }
+              }
+            }
+            if (HAS_SILU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = silu_fast_f(v[j]);
+            }
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              o[j4].x = pack2(v[j4 * 8 + 0], v[j4 * 8 + 1], bf16);
+              o[j4].y = pack2(v[j4 * 8 + 2], v[j4 * 8 + 3], bf16);
+              o[j4].z = pack2(v[j4 * 8 + 4], v[j4 * 8 + 5], bf16);
+              o[j4].w = pack2(v[j4 * 8 + 6], v[j4 * 8 + 7], bf16);
+            }
           }
           const long long tm1 = p.dbg ? clock64() : 0;
           if (leader) tma_store_wait_read<0>();    // the group's previous store has drained the staging buffer

@@ -211,7 +211,7 @@ __global__ void gn_apply_kernel(GnArgs a, const float* __restrict__ mean_rstd, c
         const float2 f = unpack2(w[e], bf);
         float v0 = fmaf(f.x, sc[2 * e], sf[2 * e]);
         float v1 = fmaf(f.y, sc[2 * e + 1], sf[2 * e + 1]);
-        if (silu) { v0 = silu_f(v0); v1 = silu_f(v1); }
+        if (silu) { v0 = silu_fast_f(v0); v1 = silu_fast_f(v1); }
         o[e] = pack2(v0, v1, bf);
       }
       *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y) + ((static_cast<long>(s) * a.rows + rk) * ldy + c0) * 2) =
