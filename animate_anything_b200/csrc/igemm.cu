@@ -318,6 +318,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
       w_tfull.wait(&tfull_bar[as], aph);
       tc_fence_after();
+#ifdef AAB_IGEMM_TRACE
+      if (p.dbg && blockIdx.x == 0 && leader && tl < 32) p.dbg[16 + 288 + eg * 64 + 2 * tl] = static_cast<unsigned long long>(clock64());
+#endif
       const uint32_t tmem_acc = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
       bool released = false;
 
@@ -473,6 +476,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tc_fence_before();
         mbar_arrive(&tempty_bar[as]);
       }
+#ifdef AAB_IGEMM_TRACE
+      if (p.dbg && blockIdx.x == 0 && leader && tl < 32) p.dbg[16 + 288 + eg * 64 + 2 * tl + 1] = static_cast<unsigned long long>(clock64());
+#endif
     }
     if (!DIRECT && leader) tma_store_wait_all<0>();
     if (leader && eg == 0) {

@@ -59,6 +59,31 @@ if "small" in sys.argv[1:]:
         print(f"{name:34s} {us:8.1f} us {flops / us / 1e6:6.0f} TFLOP/s  life {life:8.0f} clk  " +
               " ".join(f"{nm}={100 * c[i] / 148 / life:.0f}%" for i, nm in enumerate(NAMES) if nm != "-"), flush=True)
 
+    if "trace_smallk" in sys.argv[1:]:
+        # needs a library built with -DAAB_IGEMM_TRACE (AAB_LIB_PATH).  CTA 0 timeline for the epilogue-bound K=320 shape.
+        m, n, k = 139264, 320, 320
+        x, w, b, r = rnd(m, k), rnd(n, k), torch.randn(n, device="cuda"), rnd(m, n)
+        for bn, res in ((128, True), (128, False)):
+            fn = lambda: ops.linear(x, w, b, residual=(r if res else None), block_n=bn)
+            fn()
+            ops.IGEMM_DEBUG = torch.zeros(1024, device="cuda", dtype=torch.int64)
+            fn()
+            torch.cuda.synchronize()
+            c_ = ops.IGEMM_DEBUG.tolist()
+            ops.IGEMM_DEBUG = None
+            t0 = c_[16]
+            kpt = 5
+            ntile = 96 // kpt
+            print(f"== linear {m}x{n}x{k} res={res} bn{bn}: tile | first stage empty_ready | first full_ready | last issued | "
+                  f"epi g0 start/end | g1 | g2 | g3   (clk rel. to start)")
+            for tl in range(min(ntile, 19)):
+                it0, it1 = tl * kpt, tl * kpt + kpt - 1
+                e = c_[16 + it0] - t0
+                f_ = c_[16 + 96 + it0] - t0
+                i_ = c_[16 + 192 + it1] - t0
+                eg = [(c_[16 + 288 + g_ * 64 + 2 * tl] - t0, c_[16 + 288 + g_ * 64 + 2 * tl + 1] - t0) for g_ in range(4)]
+                print(f"   {tl:3d} {e:8d} {f_:8d} {i_:8d}   " + "  ".join(f"{a_:7d}/{b_:7d}" for a_, b_ in eg))
+        sys.exit(0)
     if "trace" in sys.argv[1:]:
         # per-k-block timestamps of CTA 0 (clock64): producer saw the stage empty / MMA warp saw it full / MMAs issued
         hw, c = 16, 1280
