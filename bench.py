@@ -76,12 +76,33 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def _oracle_unet_sample(threads):
+def _usable_cores():
+    """Host cores this process may actually use: affinity mask and cgroup CPU quota (os.cpu_count() reports the whole
+    host inside a container; 128 torch threads on a 16-core quota ran the oracle 14x SLOWER than 8 threads)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, -(-int(q) // int(per))))
+    except Exception:
+        pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0:
+            n = min(n, max(1, -(-q // per)))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def _oracle_unet_sample(threads=None):
     """Bounded CPU sample of the workload: one oracle UNet3D forward (fp32) for ONE batch element of the CFG pair.
-    Returns (seconds_per_full_forward_B1_T17, description)."""
+    Picks the thread count (<= usable cores) that runs a small calibration forward fastest, then the largest frame count
+    whose estimated time stays under ~25 s.  Returns (unet, fwd, frames_in_sample, description, threads_used)."""
     import torch
     from oracle.composition import OracleUNet3D
-    torch.set_num_threads(threads)
+    usable = threads or _usable_cores()
     torch.manual_seed(0)
     unet = OracleUNet3D(motion_mask=True, motion_strength=True).eval()
     g = torch.Generator().manual_seed(1)
@@ -95,13 +116,27 @@ def _oracle_unet_sample(threads):
         with torch.no_grad():
             unet(s, 500, e, c, m, motion=torch.tensor([4.0]))
         return time.perf_counter() - t0
+
+    best_t, best_n = None, usable
+    for n in sorted({usable, min(usable, 64), min(usable, 32), min(usable, 16), min(usable, 8)}, reverse=True):
+        torch.set_num_threads(n)
+        t = fwd(1, 16)                                  # T=2 at 16x16 latents: ~0.1 TFLOP, sub-second
+        if best_t is None or t < best_t:
+            best_t, best_n = t, n
+    torch.set_num_threads(best_n)
     cal = fwd(2, 32)                                    # calibration: T=3 at 32x32 (0.9 TFLOP)
     est_full = cal * (17 / 3) * 4
-    if est_full <= 40:
-        return unet, fwd, 16, "1 oracle UNet3D forward, fp32, B=1 (one CFG half), T=17, 64x64 latents"
-    f_small = 4
-    return unet, fwd, f_small, (f"1 oracle UNet3D forward, fp32, B=1, T={f_small + 1} of 17 frames, 64x64 latents; "
-                                f"scaled linearly in T (all ops but the 0.1%-FLOP temporal attention are linear in T)")
+    f_sample = 16
+    for f in (16, 4, 1):
+        f_sample = f
+        if est_full * (f + 1) / 17 <= 25:
+            break
+    if f_sample == 16:
+        desc = "1 oracle UNet3D forward, fp32, B=1 (one CFG half), T=17, 64x64 latents"
+    else:
+        desc = (f"1 oracle UNet3D forward, fp32, B=1, T={f_sample + 1} of 17 frames, 64x64 latents; scaled linearly in T "
+                f"(all ops but the 0.1%-FLOP temporal attention are linear in T)")
+    return unet, fwd, f_sample, desc + f"; {best_n} torch threads (fastest of the tried counts, {usable} usable cores)", best_n
 
 
 def cpu_frames_per_sec(sample_s, f_sample):
@@ -115,9 +150,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    unet, fwd, f_sample, desc = _oracle_unet_sample(threads)
-    for _ in range(min(args.warmup, 1)):
+    unet, fwd, f_sample, desc, threads = _oracle_unet_sample()
+    for _ in range(args.warmup):
         fwd(f_sample, LAT)
     times = [fwd(f_sample, LAT) for _ in range(max(1, args.steps))]
     t = sum(times) / len(times)
@@ -297,8 +331,7 @@ def run_product(args):
                 "igemm_ms_per_forward": tot_ms, "avg_launch_us": tot_ms * 1e3 / max(1, len(prof))}
         if world == 1 and not args.no_cpu_baseline:
             try:
-                threads = os.cpu_count() or 1
-                _, fwd, f_sample, desc = _oracle_unet_sample(threads)
+                _, fwd, f_sample, desc, threads = _oracle_unet_sample()
                 ts = fwd(f_sample, LAT)
                 cpu_base = {"value": cpu_frames_per_sec(ts, f_sample), "unit": UNIT, "cores": threads, "kind": "port",
                             "sample": desc + f" ({ts:.1f} s); x(17/T) x 2 (CFG) x 50 steps, extrapolated"}
