@@ -315,6 +315,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                   ? reinterpret_cast<const uint8_t*>(p.residual) + grow * p.ld_res * 2
                                   : nullptr;
       if (do_prefetch) prefetch_res_tile(static_cast<long>(tile) + gridDim.x);
+      // residual piece of this thread for the group's FIRST chunk of the tile: it does not depend on the accumulator, so
+      // it is requested before the wait for the main loop and its (DRAM/L2) latency -- ~2 K clk of a ~3 K clk chunk in
+      // the K=320 timelines (profiles/r01_igemm_smallk_timeline_res.log) -- hides behind that wait
+      uint4 rres[HAS_RES ? 4 : 1];
+      if (HAS_RES && resrow != nullptr && n0 + eg * 32 < p.n_out) {
+        const uint4* rp = reinterpret_cast<const uint4*>(resrow + (n0 + eg * 32) * 2);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) rres[j4] = __ldg(rp + j4);
+      }
 
       w_tfull.wait(&tfull_bar[as], aph);
       tc_fence_after();
@@ -330,9 +339,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int col = n0 + cc;                  // global output column of this 32-wide chunk
         if (col >= p.n_out) break;                // warp-uniform; later chunks of this group are out of range too
         const long long tm0 = p.dbg ? clock64() : 0;
-        // residual piece of this thread: issued first so that its (L2) latency hides behind the TMEM load
-        uint4 rres[HAS_RES ? 4 : 1];
-        if (HAS_RES && resrow != nullptr) {
+        if (HAS_RES && resrow != nullptr && ci != eg) {     // later chunks of the tile: requested here (L2-prefetched)
           const uint4* rp = reinterpret_cast<const uint4*>(resrow + col * 2);
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) rres[j4] = __ldg(rp + j4);
