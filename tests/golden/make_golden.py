@@ -80,6 +80,41 @@ def main():
     print("pipeline golden:", video.shape, latents.shape, float(latents.abs().mean()), float(latents_dpm.abs().mean()))
 
     common_golden(diffusers)
+    product_shape_goldens()
+
+
+SMALL = dict(sample_size=16, block_out_channels=(64, 128, 256, 256), attention_head_dim=64, cross_attention_dim=128,
+             motion_mask=True, motion_strength=True)
+
+
+def fp16_inputs(b, f, hw, lk, cdim, seed=1):
+    """Same draw as tests/test_gpu_unet.py::_inputs, rounded to fp16 so that the 16-bit product sees identical values."""
+    g = torch.Generator().manual_seed(seed)
+    d = dict(sample=torch.randn(b, 4, f, hw, hw, generator=g), cond=torch.randn(b, 4, 1, hw, hw, generator=g),
+             ehs=torch.randn(b, lk, cdim, generator=g), mask=(torch.rand(1, 1, 1, hw, hw, generator=g) > 0.5).float())
+    return {k: v.half().float() for k, v in d.items()}
+
+
+def product_shape_goldens():
+    """Verbatim reference UNet3DConditionModel at shapes the sm_100a product accepts (head_dim 64): the SMALL config of
+    the GPU tests and BASELINE config 1 on the full-size architecture.  Weights: fill_deterministic(seed 0) rounded to
+    fp16 (what tests/test_gpu_unet.py::_models loads into both sides); fp32 math."""
+    from models.unet_3d_condition_mask import UNet3DConditionModel            # verbatim reference
+    for name, cfg, shape in (("unet_small_ref.pt", SMALL, dict(b=2, f=4, hw=16, lk=77, cdim=128)),
+                             ("unet_config1_ref.pt", dict(sample_size=32, motion_mask=True, motion_strength=True),
+                              dict(b=1, f=8, hw=32, lk=77, cdim=1024))):
+        torch.manual_seed(0)
+        ref = UNet3DConditionModel(**cfg).eval()
+        fill_deterministic(ref, seed=0)
+        ref.load_state_dict({k: v.half().float() for k, v in ref.state_dict().items()})
+        inp = fp16_inputs(**shape)
+        with torch.no_grad():
+            out = ref(inp["sample"], 500, inp["ehs"], condition_latent=inp["cond"], mask=inp["mask"],
+                      motion=torch.tensor([4.0])).sample
+        torch.save({"config": cfg, "shape": shape, "timestep": 500, "motion": 4.0, "out": out,
+                    "n_keys": len(ref.state_dict())}, os.path.join(HERE, name))
+        print(name, tuple(out.shape), float(out.abs().mean()))
+        del ref
 
 
 def common_golden(diffusers):

@@ -144,3 +144,35 @@ def test_batch_invariance(dtype):
         one = ours(inp["sample"][i:i + 1], 500, inp["ehs"][i:i + 1], condition_latent=inp["cond"][i:i + 1],
                    mask=inp["mask"], motion=mot).sample
         assert torch.equal(one[0], both[i]), f"sample {i}: max diff {(one[0].float() - both[i].float()).abs().max()}"
+
+
+@pytest.mark.parametrize("name", ["unet_small_ref.pt", "unet_config1_ref.pt"])
+def test_unet_matches_reference_golden(name):
+    """The CUDA path against the committed output of the VERBATIM reference files (tests/golden/make_golden.py::
+    product_shape_goldens: fp32 on CPU, fp16-rounded weights and inputs): SMALL config and BASELINE config 1 at full
+    size.  Same yard-stick as _run_case (stock 16-bit torch execution of the op sequence)."""
+    gold = torch.load(os.path.join(HERE, "golden", name), map_location="cpu")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dtype = torch.float16
+    sh = gold["shape"]
+    oracle, ours = _models(dict(gold["config"]), dtype)
+    inp = _inputs(sh["b"], sh["f"], sh["hw"], sh["lk"], sh["cdim"], dtype)
+    mot = torch.tensor([gold["motion"]], device="cuda")
+    ref = gold["out"].cuda()
+    scale = ref.abs().mean().item()
+    out = ours(inp["sample"], gold["timestep"], inp["ehs"], condition_latent=inp["cond"], mask=inp["mask"], motion=mot).sample
+    with torch.no_grad():
+        o32 = oracle(inp["sample"].float(), gold["timestep"], inp["ehs"].float(), inp["cond"].float(), inp["mask"].float(),
+                     motion=mot)
+        stock = oracle.to(dtype)(inp["sample"], gold["timestep"], inp["ehs"], inp["cond"], inp["mask"], motion=mot).float()
+    e_or = (o32 - ref).abs().max().item()
+    e_ours = (out.float() - ref).abs()
+    e_stock = (stock - ref).abs()
+    print(f"{name}: golden|mean|={scale:.4f} fp32 oracle on GPU vs golden max={e_or:.3e} | ours max={e_ours.max().item():.4e} "
+          f"mean={e_ours.mean().item():.4e} | stock fp16 max={e_stock.max().item():.4e} mean={e_stock.mean().item():.4e}")
+    # cuDNN / cuBLAS fp32 (TF32 off) vs the CPU kernels: accumulation-order noise only
+    assert e_or <= 5e-3 * scale, "the fp32 oracle on the GPU must reproduce the CPU output of the reference files"
+    assert torch.isfinite(out).all()
+    assert e_ours.mean().item() <= 1.5 * e_stock.mean().item() + 2e-4 * scale
+    assert e_ours.max().item() <= 2.0 * e_stock.max().item() + 2e-3 * scale

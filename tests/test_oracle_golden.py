@@ -76,6 +76,27 @@ def test_common_functions_match_reference_utils():
     assert torch.allclose(lat, gold["latents"], rtol=1e-5, atol=1e-6)
 
 
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("name", ["unet_small_ref.pt", "unet_config1_ref.pt"])
+def test_oracle_matches_reference_at_product_shapes(name):
+    """The verbatim reference UNet at shapes the sm_100a product accepts (head_dim 64; BASELINE config 1 full size):
+    the same fixtures tests/test_gpu_unet.py compares the CUDA path with."""
+    from make_golden import fp16_inputs
+    gold = torch.load(os.path.join(HERE, "golden", name))
+    cfg = {k: v for k, v in gold["config"].items() if k != "sample_size"}
+    unet = OracleUNet3D(**cfg).eval()
+    fill_deterministic(unet, seed=0)
+    assert len(unet.state_dict()) == gold["n_keys"]
+    unet.load_state_dict({k: v.half().float() for k, v in unet.state_dict().items()})
+    inp = fp16_inputs(**gold["shape"])
+    with torch.no_grad():
+        out = unet(inp["sample"], gold["timestep"], inp["ehs"], inp["cond"], inp["mask"], motion=torch.tensor([gold["motion"]]))
+    err = float((out - gold["out"]).abs().max())
+    assert torch.allclose(out, gold["out"], rtol=1e-4, atol=2e-5), err
+
+
 def test_shim_recalled_facts():
     """One assertion per RECALLED diffusers-0.24 fact that SURVEY.md 8(c) lists as most likely to be wrong."""
     from diffusers._impl import GEGLU, TemporalConvLayer, Timesteps, TimestepEmbedding, Upsample2D, ResnetBlock2D
