@@ -1,0 +1,74 @@
+// Micro-benchmark: raw tcgen05.mma (kind::f16, cta_group::1, SS) issue rate per (M, N) -- how long does one K=16 step
+// take for M in {64, 128} and N in {64, 128, 256}?  Round-1 finding (profiles/r01_igemm_issue_trace.md): with M=128
+// the step costs ~128 clk whatever N.  This checks whether M=64 halves it (the premise of the transposed remainder
+// tile and of the transposed PV product planned in DESIGN.md section 7b).
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../../animate_anything_b200/csrc umma_rate.cu -o umma_rate
+#include "common.cuh"
+#include <cstdio>
+using namespace aab;
+
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(int M, int N, int reps, unsigned long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smA = smem;                 // 128 rows x 128 B (K-major, SWIZZLE_128B layout; content irrelevant, zeroed)
+  uint8_t* smB = smem + 16384;         // 256 rows x 128 B
+  __shared__ uint32_t slot;
+  __shared__ __align__(8) uint64_t bar;
+  for (int i = threadIdx.x; i < (16384 + 32768) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if ((threadIdx.x >> 5) == 0) {
+    tmem_alloc(&slot, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc_f16(1, M, N, 0, 0);
+    const uint32_t a_addr = smem_u32(smA), b_addr = smem_u32(smB);
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        umma_f16_ss(tmem, make_desc_kmajor_sw128(a_addr + k * 32), make_desc_kmajor_sw128(b_addr + k * 32), idesc,
+                    (r > 0 || k > 0) ? 1u : 0u);
+      }
+    }
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    out[0] = static_cast<unsigned long long>(t1 - t0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+int main() {
+  unsigned long long* d;
+  cudaMalloc(&d, 8);
+  const int smem = 16384 + 32768 + 1024;
+  cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int reps = 2048;   // x 4 instructions
+  for (int M : {128, 64}) {
+    for (int N : {256, 192, 128, 64, 32}) {
+      cudaMemset(d, 0, 8);
+      umma_rate_kernel<<<1, 128, smem>>>(M, N, reps, d);
+      cudaError_t e = cudaDeviceSynchronize();
+      unsigned long long c = 0;
+      cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+      const double per = double(c) / (reps * 4.0);
+      printf("M=%3d N=%3d  %7.1f clk per K=16 instruction  -> %7.0f FLOP/clk/SM  (%s)\n", M, N, per,
+             2.0 * M * N * 16 / per, cudaGetErrorString(e));
+    }
+  }
+  return 0;
+}
