@@ -1,13 +1,26 @@
 // Micro-benchmark: raw tcgen05.mma (kind::f16, cta_group::1, SS) issue rate per (M, N) -- how long does one K=16 step
 // take for M in {64, 128} and N in {64, 128, 256}?  Round-1 finding (profiles/r01_igemm_issue_trace.md): with M=128
 // the step costs ~128 clk whatever N.  This checks whether M=64 halves it (the premise of the transposed remainder
-// tile and of the transposed PV product planned in DESIGN.md section 7b).
+// tile and of the transposed PV product planned in DESIGN.md section 7b), and whether keeping A in tensor memory (TS mode,
+// floor N/2 cycles according to /opt/skills/guides/B300_MICROARCH.md) removes the flat ~128 clk of the SS mode.
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../../animate_anything_b200/csrc umma_rate.cu -o umma_rate
 #include "common.cuh"
 #include <cstdio>
 using namespace aab;
 
-__global__ void __launch_bounds__(128, 1) umma_rate_kernel(int M, int N, int reps, unsigned long long* out) {
+// A operand in tensor memory (TS mode): D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(int M, int N, int reps, int a_in_tmem, unsigned long long* out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;                 // 128 rows x 128 B (K-major, SWIZZLE_128B layout; content irrelevant, zeroed)
@@ -35,8 +48,11 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int M, int N, int rep
     for (int r = 0; r < reps; ++r) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        umma_f16_ss(tmem, make_desc_kmajor_sw128(a_addr + k * 32), make_desc_kmajor_sw128(b_addr + k * 32), idesc,
-                    (r > 0 || k > 0) ? 1u : 0u);
+        if (a_in_tmem)   // A (128 lanes x 8 columns of packed 16-bit pairs per K=16 step) at TMEM columns 256.., D at 0..255
+          umma_f16_ts(tmem, tmem + 256 + k * 8, make_desc_kmajor_sw128(b_addr + k * 32), idesc, (r > 0 || k > 0) ? 1u : 0u);
+        else
+          umma_f16_ss(tmem, make_desc_kmajor_sw128(a_addr + k * 32), make_desc_kmajor_sw128(b_addr + k * 32), idesc,
+                      (r > 0 || k > 0) ? 1u : 0u);
       }
     }
     umma_commit(&bar);
@@ -58,15 +74,16 @@ int main() {
   const int smem = 16384 + 32768 + 1024;
   cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int reps = 2048;   // x 4 instructions
+  for (int ts : {0, 1})
   for (int M : {128, 64}) {
     for (int N : {256, 192, 128, 64, 32}) {
       cudaMemset(d, 0, 8);
-      umma_rate_kernel<<<1, 128, smem>>>(M, N, reps, d);
+      umma_rate_kernel<<<1, 128, smem>>>(M, N, reps, ts, d);
       cudaError_t e = cudaDeviceSynchronize();
       unsigned long long c = 0;
       cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
       const double per = double(c) / (reps * 4.0);
-      printf("M=%3d N=%3d  %7.1f clk per K=16 instruction  -> %7.0f FLOP/clk/SM  (%s)\n", M, N, per,
+      printf("%s M=%3d N=%3d  %7.1f clk per K=16 instruction  -> %7.0f FLOP/clk/SM  (%s)\n", ts ? "A in TMEM" : "A in SMEM", M, N, per,
              2.0 * M * N * 16 / per, cudaGetErrorString(e));
     }
   }
