@@ -226,7 +226,7 @@ class LatentToVideoPipeline:
         (Text K/V projections are recomputed inside the captured step: 16 tiny GEMMs.)"""
         dev = buf[0].device
         key = (tuple(buf[0].shape), buf[0].dtype, tuple(ehs.shape), cfg, guidance, mask is not None,
-               motion_dev is not None, x0_hist is not None)
+               motion_dev is not None, x0_hist is not None, bool(self.share_cfg_prefix), id(self.cfg_group))
         st = self.__dict__.get("_gstate")
         if st is None or st["key"] != key:
             st = {"key": key}
