@@ -277,7 +277,10 @@ def _gn_workspace(device, nbytes):
     key = (device, torch.cuda.current_stream().cuda_stream)
     buf = _gn_ws.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.zeros(max(int(nbytes), 1 << 20), device=device, dtype=torch.uint8)
+        # 8 MiB covers every extent of the path (largest: VAE decoder, 8 frames x 1024 chunks = 4.2 MiB), so the buffer is
+        # never re-grown later -- in particular not in the middle of a CUDA-graph capture, where the old block could be
+        # handed to another tensor of the same capture while earlier captured kernels still point at it
+        buf = torch.zeros(max(int(nbytes), 8 << 20), device=device, dtype=torch.uint8)
         _gn_ws[key] = buf
     return buf
 
