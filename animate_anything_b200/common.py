@@ -34,10 +34,12 @@ def DDPM_forward(x0: torch.Tensor, step, num_frames: int, scheduler):
     shape = (x0.shape[0], x0.shape[1], num_frames, x0.shape[3], x0.shape[4])
     eps = torch.randn(shape, dtype=x0.dtype, device=x0.device)          # torch.randn_like(xt) in the reference
     alpha_vec = torch.prod(scheduler.alphas[t:])
-    # the reference multiplies an fp32 0-d tensor into the 16-bit latents: type promotion keeps the 16-bit dtype and
-    # rounds each product once, like add_noise
+    # the reference multiplies fp32 0-d tensors into the 16-bit latents: type promotion keeps the 16-bit dtype and casts
+    # the 0-d operands to it FIRST (sqrt in fp32, then one rounding), then each product and the sum round once
     a = alpha_vec.detach().to("cpu").float()
-    return ops.add_noise(x0, eps, float(torch.sqrt(a)), float(torch.sqrt(1 - a))), None
+    sa = float(torch.sqrt(a).to(x0.dtype))
+    sb = float(torch.sqrt(1 - a).to(x0.dtype))
+    return ops.add_noise(x0, eps, sa, sb), None
 
 
 def DDPM_forward_timesteps(x0: torch.Tensor, step: int, num_frames: int, scheduler):

@@ -139,6 +139,19 @@ def common_golden(diffusers):
     frames = torch.randn(1, 2, 3, 32, 32, generator=g).clamp(-1, 1)
     with torch.no_grad():
         lat = tensor_to_vae_latent(frames, vae)
+    # DDPM_forward_mask (:50-63) and DDPM_forward (:22-30): host logic around the same add_noise
+    from utils.common import DDPM_forward, DDPM_forward_mask
+    import numpy as np
+    rng = np.random.default_rng(5)
+    np_mask = (rng.random((64, 64)) > 0.5).astype(np.uint8) * 255
+    for name, dt in (("f32", torch.float32), ("bf16", torch.bfloat16)):
+        torch.manual_seed(4)
+        xm, tsm = DDPM_forward_mask(x0.to(dt), 4, 5, sched, np_mask)
+        out[f"xmask_{name}"] = xm
+        torch.manual_seed(6)
+        xf, _ = DDPM_forward(x0.to(dt), 4, 5, sched)
+        out[f"xfwd_{name}"] = xf
+    out["np_mask"] = torch.from_numpy(np_mask)
     out.update(x0=x0, frames=frames, latents=lat)
     torch.save(out, os.path.join(HERE, "common_ref.pt"))
     print("common golden:", out["xt_f32"].shape, lat.shape, float(lat.abs().mean()))
