@@ -160,8 +160,12 @@ class AutoencoderKL(ModelBase):
             return prep
         if p0.dtype not in (torch.float16, torch.bfloat16) or not p0.is_cuda:
             raise TypeError("AutoencoderKL must be fp16/bf16 on a CUDA device for the sm_100a path (no fallback)")
-        dt = p0.dtype
-        prep = E.Prepared(dt, p0.device)
+        prep = self._build_prepared(p0.dtype, p0.device)
+        self.__dict__["_aab_prepared"] = prep
+        return prep
+
+    def _build_prepared(self, dt, device) -> E.Prepared:
+        prep = E.Prepared(dt, device)
         with torch.no_grad():
             E.prepare_module(prep, self)
             own = {
@@ -177,7 +181,6 @@ class AutoencoderKL(ModelBase):
                                self.post_quant_conv.bias.detach().float().contiguous()),
             }
             prep.put(self, own)
-        self.__dict__["_aab_prepared"] = prep
         return prep
 
     # ------------------------------------------------------------------ engine pieces

@@ -754,13 +754,8 @@ extern "C" int aab_flash_attn_d64(const void* q, long ldq, long q_batch_stride, 
     if (r) return r;
     tmV = tmK;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(flash_attn_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES) !=
-        cudaSuccess)
-      return AAB_ERR_CUDA;
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (int r = ensure_dyn_smem(flash_attn_d64_kernel, FA_SMEM_BYTES, attr_done)) return r;
   FaParams p;
   p.Lq = lq;
   p.Lk = lk;
@@ -787,13 +782,8 @@ extern "C" int aab_flash_attn_d64(const void* q, long ldq, long q_batch_stride, 
     dim3 grid((lq + 255) / 256, heads, nb);
     flash_attn_d64_kernel<<<grid, FA_THREADS, FA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   } else {
-    static bool attr2 = false;
-    if (!attr2) {
-      if (cudaFuncSetAttribute(flash_attn_d64_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA2_SMEM_BYTES) !=
-          cudaSuccess)
-        return AAB_ERR_CUDA;
-      attr2 = true;
-    }
+    static std::atomic<unsigned long long> attr2_done{0};
+    if (int r = ensure_dyn_smem(flash_attn_d64_v2_kernel, FA2_SMEM_BYTES, attr2_done)) return r;
     dim3 grid((lq + 127) / 128, heads, nb);
     flash_attn_d64_v2_kernel<<<grid, FA2_THREADS, FA2_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   }
@@ -808,12 +798,9 @@ extern "C" int aab_temporal_attn_d64(const void* qkv, long ld, int q_col0, int k
   const long total = static_cast<long>(b) * hw * heads;
   const int grid = static_cast<int>((total + 3) / 4);
   const size_t smem = static_cast<size_t>(4) * TA_WARP_HALVES * sizeof(uint16_t);   // 54 KiB: Q, K, V padded to 32 rows
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(temporal_attn_d64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-    cudaFuncSetAttribute(temporal_attn_d64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_t{0}, attr_f{0};
+  if (int r = ensure_dyn_smem(temporal_attn_d64_kernel<true>, 65536, attr_t)) return r;
+  if (int r = ensure_dyn_smem(temporal_attn_d64_kernel<false>, 65536, attr_f)) return r;
   if (is_bf16)
     temporal_attn_d64_kernel<true><<<grid, 128, smem, stream>>>(qkv, ld, q_col0, k_col0, v_col0, out, ld_out, b, t, hw,
                                                                 heads, scale);

@@ -9,6 +9,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
 
 #define AAB_OK 0
 #define AAB_ERR_ARG 1
@@ -236,6 +237,20 @@ __host__ __device__ inline uint32_t make_idesc_f16(int is_bf16, int M, int N, in
   d |= static_cast<uint32_t>(N >> 3) << 17;
   d |= static_cast<uint32_t>(M >> 4) << 24;
   return d;
+}
+
+// ---------------------------------------------------------------- host: per-device opt-in to > 48 KiB dynamic smem
+// cudaFuncSetAttribute is a per-DEVICE setting: a process that drives several GPUs must opt in on each of them.
+// `done` is a per-kernel bitmask of device ordinals already configured (atomic: first calls may race across threads).
+template <typename Kernel>
+inline int ensure_dyn_smem(Kernel kernel, int bytes, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return AAB_ERR_CUDA;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return AAB_OK;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return AAB_ERR_CUDA;
+  done.fetch_or(bit, std::memory_order_release);
+  return AAB_OK;
 }
 
 // ---------------------------------------------------------------- numeric helpers

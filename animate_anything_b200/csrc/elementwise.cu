@@ -78,7 +78,7 @@ __global__ void timestep_embed_kernel(const float* __restrict__ t, int t_count, 
   const int j = i % dim;
   const int half = dim / 2;
   const int k = (j < half) ? j : j - half;
-  const float tv = t[t_count == 1 ? 0 : b];
+  const float tv = t[b % t_count];        // t_count in {1, B, B/2 (CFG pair: [uncond..., text...])}
   const float freq = expf(-9.210340371976184f * static_cast<float>(k) / static_cast<float>(half));
   const float a = tv * freq;
   const float v = (j < half) ? cosf(a) : sinf(a);
@@ -397,7 +397,9 @@ extern "C" int aab_unet_out_finalize(const float* y, int ldc, void* out, int b, 
 
 extern "C" int aab_timestep_embed(const float* t, int t_count, void* out, int b, int dim, int is_bf16, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (!t || !out || (dim & 1)) return AAB_ERR_ARG;
+  // one value per batch item, one shared value, or one per prompt under CFG (B = 2 x prompts); anything else would
+  // index out of bounds (the reference raises a broadcast error in that case)
+  if (!t || !out || (dim & 1) || t_count < 1 || b < 1 || (b % t_count) != 0) return AAB_ERR_ARG;
   const long total = static_cast<long>(b) * dim;
   if (is_bf16) timestep_embed_kernel<true><<<AAB_GRID(total, 128), 128, 0, stream>>>(t, t_count, out, b, dim);
   else timestep_embed_kernel<false><<<AAB_GRID(total, 128), 128, 0, stream>>>(t, t_count, out, b, dim);

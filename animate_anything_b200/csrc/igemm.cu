@@ -560,13 +560,8 @@ template <int BN, int EPI>
 static int launch_bn(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& d,
                      const CUtensorMap& r, const IgemmParams& p, int max_ctas, cudaStream_t stream) {
   using CF = Cfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(igemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES);
-    if (e != cudaSuccess) return AAB_ERR_CUDA;
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (int r = ensure_dyn_smem(igemm_kernel<BN, EPI>, CF::SMEM_BYTES, attr_done)) return r;
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;

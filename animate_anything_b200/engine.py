@@ -85,10 +85,18 @@ def prep_norm(norm):
     return _f32(norm.weight), _f32(norm.bias)
 
 
+_prepared_generation = 0
+
+
 class Prepared:
-    """Per-model cache: module -> dict of kernel-layout tensors."""
+    """Per-model cache: module -> dict of kernel-layout tensors.  `gen` is a process-wide generation number: anything
+    that holds raw pointers into these tensors (captured CUDA graphs) keys itself on it, because `id()` of a freed
+    object can be re-used."""
 
     def __init__(self, dtype, device):
+        global _prepared_generation
+        _prepared_generation += 1
+        self.gen = _prepared_generation
         self.dtype = dtype
         self.device = device
         self.m: Dict[int, dict] = {}

@@ -59,6 +59,33 @@ class ModelBase(nn.Module):
     def invalidate_prepared(self):
         self.__dict__["_aab_prepared"] = None
 
+    def prepare_to(self, device):
+        """Move a 16-bit model that still lives on the HOST to `device` with its kernel-layout weights converted on the
+        host first: every converted tensor and every parameter then reaches the GPU by a plain H2D memcpy, so no torch
+        cast / permute / cat kernel runs on the device at all (the lazy path, `_prepared()` on first use, converts on
+        the GPU with a few hundred small torch copy kernels).  Returns self."""
+        p0 = next(self.parameters())
+        if p0.is_cuda:
+            raise RuntimeError("prepare_to() converts on the host: call it before moving the model to the GPU")
+        if p0.dtype not in (torch.float16, torch.bfloat16):
+            raise TypeError("prepare_to() needs a 16-bit model (.to(torch.float16) / .to(torch.bfloat16) first)")
+        device = torch.device(device)
+        prep = self._build_prepared(p0.dtype, p0.device)
+
+        def mv(o):
+            if torch.is_tensor(o):
+                return o.to(device)
+            if isinstance(o, dict):
+                return {k: mv(v) for k, v in o.items()}
+            if isinstance(o, (list, tuple)):
+                return type(o)(mv(v) for v in o)
+            return o
+        prep.m = {k: mv(v) for k, v in prep.m.items()}
+        prep.device = device
+        nn.Module._apply(self, lambda t: t.to(device))             # bypass the cache invalidation of ModelBase._apply
+        self.__dict__["_aab_prepared"] = prep
+        return self
+
     @classmethod
     def from_config(cls, config, **overrides):
         sig = inspect.signature(cls.__init__).parameters

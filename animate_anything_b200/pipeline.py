@@ -41,7 +41,7 @@ class LatentToVideoPipeline:
     def __init__(self, vae, text_encoder, tokenizer, unet, scheduler):
         self.vae, self.text_encoder, self.tokenizer, self.unet, self.scheduler = vae, text_encoder, tokenizer, unet, scheduler
         self.vae_scale_factor = 2 ** (len(self.vae.config.block_out_channels) - 1) if vae is not None else 8
-        self.use_cuda_graph = False
+        self.use_cuda_graph = True     # replay the captured step (bit-identical to eager)
         self.share_cfg_prefix = True   # evaluate the text-independent prefix of the UNet once per CFG pair
         self.cfg_group = None          # torch.distributed group of size 2: CFG halves split over two GPUs (parallel.py)
         self.last_gpu_launches = 0
@@ -208,6 +208,12 @@ class LatentToVideoPipeline:
 
         if output_type == "pt":
             video = self.decode_latents(latents)
+        elif output_type == "latent":
+            video = latents
+        elif output_type == "u8":
+            # extension used by parallel.py / bench.py: the tensor2vid frames as ONE device tensor [f, H, b*W, 3] uint8
+            # (what "np" returns, before the D2H copy), ready for the NCCL all-gather
+            video = self.vae.decode_frames_uint8(latents)
         else:
             # decode_latents + tensor2vid fused on the device (uint8 frames, 4x less D2H traffic than the fp32 video)
             frames = self.vae.decode_frames_uint8(latents).cpu().numpy()
@@ -225,8 +231,13 @@ class LatentToVideoPipeline:
         inputs are copied into the captured static buffers, so a new call with the same shapes re-uses the graphs.
         (Text K/V projections are recomputed inside the captured step: 16 tiny GEMMs.)"""
         dev = buf[0].device
+        # the captured kernels hold raw pointers into the UNet's converted weights (`Prepared`): its generation number is
+        # part of the key, so `load_state_dict()` / `.to()` / `invalidate_prepared()` (which drop that cache) force a
+        # re-capture instead of replaying graphs over freed memory.  In-place edits of parameters (e.g. a LoRA merge)
+        # do not touch the cache: call `unet.invalidate_prepared()` after them.
         key = (tuple(buf[0].shape), buf[0].dtype, tuple(ehs.shape), cfg, guidance, mask is not None,
-               motion_dev is not None, x0_hist is not None, bool(self.share_cfg_prefix), id(self.cfg_group))
+               motion_dev is not None, x0_hist is not None, bool(self.share_cfg_prefix), id(self.cfg_group),
+               self.unet._prepared().gen)
         st = self.__dict__.get("_gstate")
         if st is None or st["key"] != key:
             st = {"key": key}

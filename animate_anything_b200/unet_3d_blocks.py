@@ -74,7 +74,7 @@ class UNetMidBlock3DCrossAttn(_Block):
             x = E.resnet_forward(ctx, resnet, x, g)
             if g.t > 1:
                 x = E.temporal_conv_forward(ctx, tconv, x, g)
-        return x
+        return x, g      # g changes when the shared CFG prefix ends inside this block (all-DownBlock3D configs)
 
 
 class CrossAttnDownBlock3D(_Block):

@@ -160,8 +160,13 @@ class UNet3DConditionModel(ModelBase):
                             f"Call .to(torch.float16) / .to(torch.bfloat16). There is no fp32/CPU fallback.")
         if not p0.is_cuda:
             raise RuntimeError("UNet3DConditionModel parameters must live on a CUDA device (no CPU fallback)")
-        dt = p0.dtype
-        prep = E.Prepared(dt, p0.device)
+        prep = self._build_prepared(p0.dtype, p0.device)
+        self.__dict__["_aab_prepared"] = prep
+        return prep
+
+    def _build_prepared(self, dt, device) -> E.Prepared:
+        """Kernel-layout copies of every weight (layout conversion only; runs wherever the parameters live)."""
+        prep = E.Prepared(dt, device)
         with torch.no_grad():
             E.prepare_module(prep, self)
             own = {}
@@ -181,11 +186,19 @@ class UNet3DConditionModel(ModelBase):
             own["temb_b"] = torch.cat(bs, dim=0).float().contiguous()
             own["temb_off"] = offs
             prep.put(self, own)
-        self.__dict__["_aab_prepared"] = prep
         return prep
 
     # ------------------------------------------------------------------ forward
-    def _time_embedding(self, prep, timestep, motion, b, device):
+    @staticmethod
+    def _check_per_batch(name, count, b, n_shared):
+        """The reference broadcasts a [1] or [B] tensor over the batch (:392-406 `timesteps.expand`) and raises on any
+        other length; under the shared CFG prefix the caller holds one value per prompt (B = 2 x prompts, batch ordered
+        [uncond..., text...]), which tiles over both halves."""
+        if count not in (1, b) and not (n_shared and count == n_shared):
+            raise ValueError(f"`{name}` has {count} values for a batch of {b}: expected 1 or {b}"
+                             + (f" (or {n_shared}, one per prompt)" if n_shared else ""))
+
+    def _time_embedding(self, prep, timestep, motion, b, device, n_shared=0):
         """reference :391-420.  Returns fp32 [B, sum(Cout)] = time_emb_proj_r(silu(emb)) for every resnet r."""
         own = prep.get(self)
         te = prep.get(self.time_embedding)
@@ -194,12 +207,14 @@ class UNet3DConditionModel(ModelBase):
             timestep = torch.tensor([float(timestep)], dtype=torch.float32, device=device)
         else:
             timestep = timestep.to(device=device, dtype=torch.float32).reshape(-1)
+        self._check_per_batch("timestep", timestep.numel(), b, n_shared)
         c0 = self.conv_in.out_channels
         t_emb = ops.timestep_embed(timestep, b, c0, dt)
         if self.motion_strength and motion is not None:
             if not torch.is_tensor(motion):
                 motion = torch.tensor(motion, dtype=torch.float32, device=device)
             motion = motion.to(device=device, dtype=torch.float32).reshape(-1)
+            self._check_per_batch("motion", motion.numel(), b, n_shared)
             m_emb = ops.timestep_embed(motion, b, c0, dt)
             t_emb = ops.linear(m_emb, te["cp"], None, residual=t_emb)         # sample + cond_proj(condition)
         h = ops.linear(t_emb, te["l1"][0], te["l1"][1], act=ops.ACT_SILU)
@@ -255,7 +270,7 @@ class UNet3DConditionModel(ModelBase):
         ctx.fuse_geglu = self.fuse_geglu
         ctx.temb_off = own["temb_off"]
         ctx.dup_pending = bool(_cfg_shared_prefix)
-        ctx.temb_all = self._time_embedding(prep, timestep, motion, b_full, dev)
+        ctx.temb_all = self._time_embedding(prep, timestep, motion, b_full, dev, b if _cfg_shared_prefix else 0)
         ehs = encoder_hidden_states
         if ehs.dtype != dt:
             ehs = ehs.to(dt)
@@ -285,7 +300,7 @@ class UNet3DConditionModel(ModelBase):
             g = g2
             if trace is not None:
                 trace.append((f"down_blocks.{i}", x, g))
-        x = self.mid_block.run(ctx, x, g)
+        x, g = self.mid_block.run(ctx, x, g)
         if trace is not None:
             trace.append(("mid_block", x, g))
         for i, blk in enumerate(self.up_blocks):

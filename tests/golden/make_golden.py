@@ -157,5 +157,72 @@ def common_golden(diffusers):
     print("common golden:", out["xt_f32"].shape, lat.shape, float(lat.abs().mean()))
 
 
+
+
+# ------------------------------------------------------------------------------------------------ benchmarked shapes
+def bf16_inputs(b, f, hw, lk, cdim, seed=1):
+    """Same draw as tests/test_gpu_unet.py::_inputs, rounded to bf16 (the benchmark dtype)."""
+    g = torch.Generator().manual_seed(seed)
+    d = dict(sample=torch.randn(b, 4, f, hw, hw, generator=g), cond=torch.randn(b, 4, 1, hw, hw, generator=g),
+             ehs=torch.randn(b, lk, cdim, generator=g), mask=(torch.rand(1, 1, 1, hw, hw, generator=g) > 0.5).float())
+    return {k: v.bfloat16().float() for k, v in d.items()}
+
+
+def config2_unet_golden():
+    """ONE forward of the verbatim reference UNet3DConditionModel at the BENCHMARKED configuration (BASELINE config 2:
+    CFG batch 2, 16 frames + condition frame, 64x64 latents, text [2,77,1024], mask, motion 4): fp32 math on
+    bf16-rounded weights and inputs.  ~44 TFLOP on the CPU (minutes)."""
+    import time
+    from models.unet_3d_condition_mask import UNet3DConditionModel            # verbatim reference
+    cfg = dict(sample_size=64, motion_mask=True, motion_strength=True)
+    shape = dict(b=2, f=16, hw=64, lk=77, cdim=1024)
+    torch.manual_seed(0)
+    ref = UNet3DConditionModel(**cfg).eval()
+    fill_deterministic(ref, seed=0)
+    ref.load_state_dict({k: v.bfloat16().float() for k, v in ref.state_dict().items()})
+    inp = bf16_inputs(**shape)
+    t0 = time.time()
+    with torch.no_grad():
+        out = ref(inp["sample"], 500, inp["ehs"], condition_latent=inp["cond"], mask=inp["mask"],
+                  motion=torch.tensor([4.0])).sample
+    torch.save({"config": cfg, "shape": shape, "timestep": 500, "motion": 4.0, "dtype": "bf16", "out": out,
+                "n_keys": len(ref.state_dict())}, os.path.join(HERE, "unet_config2_ref.pt"))
+    print(f"unet_config2_ref.pt {tuple(out.shape)} |mean|={float(out.abs().mean()):.4f} ({time.time() - t0:.0f} s)")
+
+
+def vae_fullsize_golden():
+    """Full-size SD VAE (block_out_channels 128/256/512/512) through the VERBATIM reference entry points:
+    `tensor_to_vae_latent` (utils/common.py:12-20) on one 512x512 frame and `LatentToVideoPipeline.decode_latents`
+    (inherited, called at models/pipeline.py:200) on two 64x64 latent frames.  fp32 math, bf16-rounded weights/inputs."""
+    import time
+    import types
+    import diffusers
+    sys.modules.setdefault("imageio", types.ModuleType("imageio"))
+    from models.pipeline import LatentToVideoPipeline                         # verbatim reference
+    from utils.common import tensor_to_vae_latent                             # verbatim reference
+    vae = diffusers.AutoencoderKL().eval()                                    # SD VAE defaults
+    fill_deterministic(vae, seed=1)
+    vae.load_state_dict({k: v.bfloat16().float() for k, v in vae.state_dict().items()})
+    g = torch.Generator().manual_seed(21)
+    frames = torch.randn(1, 1, 3, 512, 512, generator=g).clamp(-1, 1).bfloat16().float()
+    lat = torch.randn(1, 4, 2, 64, 64, generator=g).bfloat16().float()
+    pipe = LatentToVideoPipeline(vae=vae, text_encoder=None, tokenizer=None, unet=None, scheduler=None)
+    t0 = time.time()
+    with torch.no_grad():
+        enc = tensor_to_vae_latent(frames, vae)                               # [1, 4, 1, 64, 64]
+        video = pipe.decode_latents(lat)                                      # [1, 3, 2, 512, 512] fp32
+    torch.save({"seed": 21, "enc_latents": enc, "video_f16": video.half(), "video_abs_mean": float(video.abs().mean()),
+                "video_sum": float(video.double().sum()), "n_keys": len(vae.state_dict())},
+               os.path.join(HERE, "vae_fullsize_ref.pt"))
+    print(f"vae_fullsize_ref.pt enc {tuple(enc.shape)} |mean|={float(enc.abs().mean()):.4f} video {tuple(video.shape)} "
+          f"|mean|={float(video.abs().mean()):.4f} ({time.time() - t0:.0f} s)")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "benchmarked":
+        # python tests/golden/make_golden.py benchmarked   (only the two expensive fixtures, minutes of CPU)
+        import diffusers  # noqa: F401  (the shim)
+        vae_fullsize_golden()
+        config2_unet_golden()
+    else:
+        main()

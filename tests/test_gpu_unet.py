@@ -176,3 +176,27 @@ def test_unet_matches_reference_golden(name):
     assert torch.isfinite(out).all()
     assert e_ours.mean().item() <= 1.5 * e_stock.mean().item() + 2e-4 * scale
     assert e_ours.max().item() <= 2.0 * e_stock.max().item() + 2e-3 * scale
+
+
+def test_prepare_to_host_conversion_matches_lazy():
+    """`ModelBase.prepare_to` (weights converted to kernel layouts on the host, uploaded by memcpy) gives the same bits
+    as the lazy on-device conversion."""
+    from oracle.composition import OracleUNet3D, fill_deterministic
+    from animate_anything_b200.unet_3d_condition_mask import UNet3DConditionModel
+    dtype = torch.float16
+    sd = {k: v.to(dtype) for k, v in fill_deterministic(OracleUNet3D(**{k: v for k, v in SMALL.items()
+                                                                       if k != "sample_size"}).eval(), 0).state_dict().items()}
+    a = UNet3DConditionModel(**SMALL).eval()
+    a.load_state_dict(sd)
+    a = a.to(dtype).cuda()
+    b = UNet3DConditionModel(**SMALL).eval()
+    b.load_state_dict(sd)
+    b = b.to(dtype).prepare_to("cuda")
+    assert b.__dict__["_aab_prepared"] is not None and b.device.type == "cuda"
+    inp = _inputs(2, 4, 16, 77, SMALL["cross_attention_dim"], dtype)
+    mot = torch.tensor([4.0], device="cuda")
+    ya = a(inp["sample"], 500, inp["ehs"], condition_latent=inp["cond"], mask=inp["mask"], motion=mot).sample
+    yb = b(inp["sample"], 500, inp["ehs"], condition_latent=inp["cond"], mask=inp["mask"], motion=mot).sample
+    assert torch.equal(ya, yb)
+    with pytest.raises(ValueError):      # per-batch values: 1, B (reference broadcast rule) -- 3 values for batch 2 is an error
+        a(inp["sample"], torch.tensor([1.0, 2.0, 3.0]), inp["ehs"], condition_latent=inp["cond"], mask=inp["mask"], motion=mot)
