@@ -43,6 +43,7 @@ struct FaParams {
   int out_col0;
   float scale_log2;
   int is_bf16;
+  int causal;              // key j visible to query i iff j <= i (CLIP text tower); host guarantees Lq == Lk <= 128
 };
 
 __global__ void __launch_bounds__(FA_THREADS, 1)
@@ -193,9 +194,13 @@ flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       mbar_wait(&s_full[tile], jph);
       tc_fence_after();
       const int kbase = j * 128;
-      const int valid = p.Lk - kbase;               // keys of this block that exist (>= 128: no masking needed)
+      int valid = p.Lk - kbase;                     // keys of this block that exist (>= 128: no masking needed)
+      if (p.causal) {                               // per-row limit: keys kbase .. min(Lk, q) (one block: Lk <= 128)
+        const int vis = q0 + tile * 128 + row - kbase + 1;
+        valid = vis < valid ? vis : valid;
+      }
       float alpha, lsum = 0.f;
-      if (valid >= 128) {
+      if (valid >= 128 && !p.causal) {
         // ---------------- common case: no per-element predicates
         float mx = -INFINITY;
 #pragma unroll
@@ -737,6 +742,11 @@ extern "C" int aab_flash_attn_d64(const void* q, long ldq, long q_batch_stride, 
                                   void* out, long ld_out, long out_batch_stride, int out_col0, int nb, int nb_kv,
                                   int kv_batch_div, int heads, int lq, int lk, float scale, int is_bf16, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  // bit 1 of `is_bf16` selects the causal variant (CLIP text self-attention, transformers CLIPAttention with
+  // causal_attention_mask; reached from models/pipeline.py:136 _encode_prompt); one KV block only
+  const int causal = (is_bf16 >> 1) & 1;
+  is_bf16 &= 1;
+  if (causal && (lq != lk || lk > 128)) return AAB_ERR_ARG;
   if (!q || !kv || !out || lq < 1 || lk < 1 || heads < 1 || nb < 1 || kv_batch_div < 1) return AAB_ERR_ARG;
   if ((ldq % 8) || (ldkv % 8) || (ld_out % 8) || (out_col0 % 8)) return AAB_ERR_ARG;
   CUtensorMap tmQ, tmK, tmV;
@@ -770,6 +780,7 @@ extern "C" int aab_flash_attn_d64(const void* q, long ldq, long q_batch_stride, 
   p.out_col0 = out_col0;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.is_bf16 = is_bf16;
+  p.causal = causal;
   // Measured on B200 (nb=34, L=4096, 5 heads, bf16): v1 = 1.33 ms, v2 = 2.03 ms.  One softmax warpgroup per SM
   // (v2) cannot hide its own tcgen05.ld / MUFU latencies; two warpgroups (v1) do, even though they wait for the MMAs in
   // phase.  v1 is the default; AAB_FLASH_V2=1 selects v2 for experiments.
@@ -778,7 +789,7 @@ extern "C" int aab_flash_attn_d64(const void* q, long ldq, long q_batch_stride, 
     const char* e = getenv("AAB_FLASH_V2");
     use_v1 = (e && e[0] == '1') ? 0 : 1;
   }
-  if (use_v1) {       // two query tiles per CTA (two softmax warpgroups), S single-buffered
+  if (use_v1 || causal) {       // two query tiles per CTA (two softmax warpgroups), S single-buffered
     dim3 grid((lq + 255) / 256, heads, nb);
     flash_attn_d64_kernel<<<grid, FA_THREADS, FA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   } else {

@@ -256,6 +256,8 @@ inline int ensure_dyn_smem(Kernel kernel, int bytes, std::atomic<unsigned long l
 // ---------------------------------------------------------------- numeric helpers
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// transformers "quick_gelu" (OpenAI CLIP text towers): x * sigmoid(1.702 x)
+__device__ __forceinline__ float quick_gelu_f(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 // MUFU without the denormal-scaling wrappers nvcc emits for non-ftz ex2/rcp (2 FSETP + 3 FMUL + FSEL per call)
 __device__ __forceinline__ float ex2_ftz(float x) {
   float y;

@@ -85,6 +85,33 @@ __global__ void timestep_embed_kernel(const float* __restrict__ t, int t_count, 
   store_elem(out, i, v, BF16);
 }
 
+// CLIP text embeddings (transformers CLIPTextEmbeddings.forward, reached from models/pipeline.py:136 _encode_prompt):
+// out[r, :] = token_embedding[ids[r], :] + position_embedding[r % L, :], one 16-byte octet per thread.
+template <bool BF16>
+__global__ void embed_tokens_kernel(const long long* __restrict__ ids, const uint4* __restrict__ tok,
+                                    const uint4* __restrict__ pos, uint4* __restrict__ out, long rows, int L, int V8,
+                                    int vocab) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * V8) return;
+  const long r = i / V8;
+  const int o = static_cast<int>(i % V8);
+  long long id = ids[r];
+  if (id < 0) id = 0;
+  if (id >= vocab) id = vocab - 1;
+  const uint4 a = __ldg(tok + id * V8 + o);
+  const uint4 b = __ldg(pos + (r % L) * V8 + o);
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+  const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+  uint32_t w[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 fa = unpack2(aw[e], BF16);
+    const float2 fb = unpack2(bw[e], BF16);
+    w[e] = pack2(fa.x + fb.x, fa.y + fb.y, BF16);
+  }
+  out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // GEGLU fallback: out[r, j] = x[r, j] * gelu(x[r, nh + j])   (diffusers GEGLU.forward)
 template <bool BF16>
 __global__ void geglu_kernel(const void* __restrict__ x, long ldx, void* __restrict__ out, long ldo, long rows, int nh) {
@@ -403,6 +430,22 @@ extern "C" int aab_timestep_embed(const float* t, int t_count, void* out, int b,
   const long total = static_cast<long>(b) * dim;
   if (is_bf16) timestep_embed_kernel<true><<<AAB_GRID(total, 128), 128, 0, stream>>>(t, t_count, out, b, dim);
   else timestep_embed_kernel<false><<<AAB_GRID(total, 128), 128, 0, stream>>>(t, t_count, out, b, dim);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_embed_tokens(const long long* ids, const void* tok_emb, const void* pos_emb, void* out, long rows,
+                                int seq_len, int c, int vocab, int is_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!ids || !tok_emb || !pos_emb || !out || (c % 8) || seq_len < 1 || vocab < 1) return AAB_ERR_ARG;
+  const long total = rows * (c / 8);
+  if (is_bf16)
+    embed_tokens_kernel<true><<<AAB_GRID(total, 256), 256, 0, stream>>>(
+        ids, reinterpret_cast<const uint4*>(tok_emb), reinterpret_cast<const uint4*>(pos_emb),
+        reinterpret_cast<uint4*>(out), rows, seq_len, c / 8, vocab);
+  else
+    embed_tokens_kernel<false><<<AAB_GRID(total, 256), 256, 0, stream>>>(
+        ids, reinterpret_cast<const uint4*>(tok_emb), reinterpret_cast<const uint4*>(pos_emb),
+        reinterpret_cast<uint4*>(out), rows, seq_len, c / 8, vocab);
   AAB_LAUNCH_RET();
 }
 

@@ -62,6 +62,7 @@ struct WaitTimer {
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == AAB_ACT_SILU) return silu_f(x);
   if (act == AAB_ACT_GELU) return gelu_erf_f(x);
+  if (act == AAB_ACT_QUICK_GELU) return quick_gelu_f(x);
   return x;
 }
 
@@ -595,7 +596,7 @@ extern "C" int aab_igemm(const AabIgemmDesc* d, void* stream_) {
   if (bn == 32 || (d->ld_out % 8) != 0 || (n_out % 32) != 0 || (d->flags & AAB_F_OUT_F32)) direct = true;
   if (geglu && (bn < 128 || direct)) return AAB_ERR_ARG;   // output tile must cover whole 64-column store boxes
   if (d->residual && (d->ld_res % 8) != 0 && !direct) direct = true;
-  if (d->act == AAB_ACT_GELU && !geglu) direct = true;
+  if ((d->act == AAB_ACT_GELU || d->act == AAB_ACT_QUICK_GELU) && !geglu) direct = true;
   {   // the staged variants cover one extra term each (residual | per-sample bias | SiLU) and no output scaling
     const int extras = (d->residual ? 1 : 0) + (d->bias2 ? 1 : 0) + (d->act == AAB_ACT_SILU ? 1 : 0);
     if (!geglu && (extras > 1 || d->out_scale != 1.0f)) direct = true;

@@ -7,6 +7,7 @@
 #define AAB_ACT_NONE 0
 #define AAB_ACT_SILU 1
 #define AAB_ACT_GELU 2
+#define AAB_ACT_QUICK_GELU 3   /* x * sigmoid(1.702 x): transformers 'quick_gelu' (CLIP text MLP) */
 
 #define AAB_F_BF16 1      /* 16-bit type is bfloat16 (else float16) */
 #define AAB_F_DIRECT 2    /* epilogue stores straight to global memory instead of smem + TMA store */

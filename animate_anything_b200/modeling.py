@@ -34,6 +34,7 @@ def capture_config(obj, init, args, kwargs):
 class ModelBase(nn.Module):
     config_name = "config.json"
     weights_name = "diffusion_pytorch_model"
+    weights_bin_name = None            # file name of the pickle checkpoint when it is not weights_name + ".bin"
 
     @property
     def config(self):
@@ -105,7 +106,7 @@ class ModelBase(nn.Module):
             from safetensors.torch import load_file
             sd = load_file(st_path)
         else:
-            sd = torch.load(os.path.join(root, cls.weights_name + ".bin"), map_location="cpu")
+            sd = torch.load(os.path.join(root, cls.weights_bin_name or (cls.weights_name + ".bin")), map_location="cpu")
         if ignore_mismatched_sizes:
             own = model.state_dict()
             sd = {k: v for k, v in sd.items() if k in own and own[k].shape == v.shape}

@@ -12,12 +12,26 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_NONE, ACT_SILU, F_BF16, F_DIRECT, F_GEGLU, F_OUT_F32, IgemmDesc
+from ._lib import ACT_GELU, ACT_NONE, ACT_QUICK_GELU, ACT_SILU, F_BF16, F_DIRECT, F_GEGLU, F_OUT_F32, IgemmDesc
 
 NUM_SMS = 148
 IGEMM_DEBUG = None       # optional uint64[16] device tensor: per-role wait-cycle counters (tools/igemm_roles.py)
 IGEMM_DBG_FLAGS = 4096 if os.environ.get("AAB_IGEMM_NOPEEK") else 0     # tools/igemm_roles.py only: AAB_F_DBG_NO_MMA (64) / AAB_F_DBG_NO_LOAD (128); results are wrong by design
 IGEMM_PROFILE = None     # bench.py sets this to a list to time every implicit-GEMM launch with CUDA events
+KERNEL_PROFILE = None    # same for the other kernels: list of {"name", "bytes" (algorithmic HBM bytes), "flops", "ev"}
+
+
+def _profiled(name, nbytes, flops, fn):
+    """Run `fn` (one C-ABI call); when KERNEL_PROFILE is a list, bracket it with CUDA events on the launch stream."""
+    if KERNEL_PROFILE is None:
+        return fn()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    r = fn()
+    ev1.record()
+    KERNEL_PROFILE.append({"name": name, "bytes": float(nbytes), "flops": float(flops), "ev": (ev0, ev1)})
+    return r
 
 
 def _stream():
@@ -247,24 +261,28 @@ def tconv3(x: torch.Tensor, b: int, t: int, hw: int, w: torch.Tensor, bias=None,
 
 # ---------------------------------------------------------------------------------------------- attention
 def flash_attn_d64(q: torch.Tensor, q_col0: int, kv: torch.Tensor, k_col0: int, v_col0: int, nb: int, lq: int, lk: int,
-                   heads: int, kv_batch_div: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """q: [nb*lq, q_cols]; kv: [nb_kv*lk, kv_cols]; head h uses columns col0 + 64*h.  Returns [nb*lq, heads*64]."""
-    bf = _is_bf16(q)
+                   heads: int, kv_batch_div: int = 1, out: Optional[torch.Tensor] = None, causal: bool = False) -> torch.Tensor:
+    """q: [nb*lq, q_cols]; kv: [nb_kv*lk, kv_cols]; head h uses columns col0 + 64*h.  Returns [nb*lq, heads*64].
+    `causal` (lq == lk <= 128): key j is visible to query i iff j <= i (CLIP text tower)."""
+    bf = _is_bf16(q) | (2 if causal else 0)
     if out is None:
         out = torch.empty((nb * lq, heads * 64), device=q.device, dtype=q.dtype)
     nb_kv = kv.shape[0] // lk
-    _lib.call("aab_flash_attn_d64", _ptr(q), q.stride(0), lq * q.stride(0), q.shape[1], q_col0,
-              _ptr(kv), kv.stride(0), lk * kv.stride(0), kv.shape[1], k_col0, v_col0,
-              _ptr(out), out.stride(0), lq * out.stride(0), 0, nb, nb_kv, kv_batch_div, heads, lq, lk,
-              1.0 / math.sqrt(64.0), bf, _stream())
+    _profiled("flash_attn_d64", 2.0 * 64 * heads * (2 * nb * lq + 2 * nb_kv * lk), 4.0 * nb * heads * lq * lk * 64,
+              lambda: _lib.call("aab_flash_attn_d64", _ptr(q), q.stride(0), lq * q.stride(0), q.shape[1], q_col0,
+                                _ptr(kv), kv.stride(0), lk * kv.stride(0), kv.shape[1], k_col0, v_col0,
+                                _ptr(out), out.stride(0), lq * out.stride(0), 0, nb, nb_kv, kv_batch_div, heads, lq, lk,
+                                1.0 / math.sqrt(64.0), bf, _stream()))
     return out
 
 
 def temporal_attn_d64(qkv: torch.Tensor, b: int, t: int, hw: int, heads: int, q_col0: int, k_col0: int, v_col0: int):
     bf = _is_bf16(qkv)
     out = torch.empty((qkv.shape[0], heads * 64), device=qkv.device, dtype=qkv.dtype)
-    _lib.call("aab_temporal_attn_d64", _ptr(qkv), qkv.stride(0), q_col0, k_col0, v_col0, _ptr(out), out.stride(0), b, t,
-              hw, heads, 1.0 / math.sqrt(64.0), bf, _stream())
+    rows = qkv.shape[0]
+    _profiled("temporal_attn_d64", 2.0 * rows * heads * 64 * 4, 4.0 * b * hw * heads * t * t * 64,
+              lambda: _lib.call("aab_temporal_attn_d64", _ptr(qkv), qkv.stride(0), q_col0, k_col0, v_col0, _ptr(out),
+                                out.stride(0), b, t, hw, heads, 1.0 / math.sqrt(64.0), bf, _stream()))
     return out
 
 
@@ -296,16 +314,20 @@ def groupnorm(x: torch.Tensor, samples: int, rows: int, gamma: torch.Tensor, bet
     if need < 0:
         raise _lib.AabError("aab_groupnorm: unsupported channel count")
     ws = _gn_workspace(x.device, need)
-    _lib.call("aab_groupnorm", _ptr(x), x.stride(0), c1, _ptr(x2), 0 if x2 is None else x2.stride(0), c2, samples, rows,
-              groups, _ptr(gamma), _ptr(beta), eps, int(silu), _ptr(y), y.stride(0), _ptr(ws), bf, _stream())
+    # algorithmic bytes: one read + one write of the activation
+    _profiled("groupnorm", 2.0 * 2 * x.shape[0] * (c1 + c2), 0.0,
+              lambda: _lib.call("aab_groupnorm", _ptr(x), x.stride(0), c1, _ptr(x2), 0 if x2 is None else x2.stride(0), c2,
+                                samples, rows, groups, _ptr(gamma), _ptr(beta), eps, int(silu), _ptr(y), y.stride(0),
+                                _ptr(ws), bf, _stream()))
     return y
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
     bf = _is_bf16(x)
     y = torch.empty_like(x)
-    _lib.call("aab_layernorm", _ptr(x), x.stride(0), _ptr(y), y.stride(0), _ptr(gamma), _ptr(beta), x.shape[0], x.shape[1],
-              eps, bf, _stream())
+    _profiled("layernorm", 2.0 * 2 * x.shape[0] * x.shape[1], 0.0,
+              lambda: _lib.call("aab_layernorm", _ptr(x), x.stride(0), _ptr(y), y.stride(0), _ptr(gamma), _ptr(beta),
+                                x.shape[0], x.shape[1], eps, bf, _stream()))
     return y
 
 
@@ -344,6 +366,15 @@ def timestep_embed(t: torch.Tensor, b: int, dim: int, dtype) -> torch.Tensor:
     assert t.dtype == torch.float32 and t.is_cuda
     out = torch.empty((b, dim), device=t.device, dtype=dtype)
     _lib.call("aab_timestep_embed", _ptr(t), t.numel(), _ptr(out), b, dim, 1 if dtype == torch.bfloat16 else 0, _stream())
+    return out
+
+
+def embed_tokens(ids: torch.Tensor, tok_emb: torch.Tensor, pos_emb: torch.Tensor, seq_len: int) -> torch.Tensor:
+    """ids int64 [rows] -> tok_emb[ids] + pos_emb[row % seq_len]  as [rows, C] (CLIPTextEmbeddings)."""
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and tok_emb.is_contiguous() and pos_emb.is_contiguous()
+    out = torch.empty((ids.numel(), tok_emb.shape[1]), device=tok_emb.device, dtype=tok_emb.dtype)
+    _lib.call("aab_embed_tokens", _ptr(ids), _ptr(tok_emb), _ptr(pos_emb), _ptr(out), ids.numel(), seq_len,
+              tok_emb.shape[1], tok_emb.shape[0], _is_bf16(tok_emb), _stream())
     return out
 
 

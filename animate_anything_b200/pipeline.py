@@ -67,7 +67,7 @@ class LatentToVideoPipeline:
             from transformers import CLIPTokenizer
             tokenizer = CLIPTokenizer.from_pretrained(path, subfolder="tokenizer")
         if text_encoder is None and os.path.isdir(os.path.join(path, "text_encoder")):
-            from transformers import CLIPTextModel
+            from .clip_text import CLIPTextModel
             text_encoder = CLIPTextModel.from_pretrained(path, subfolder="text_encoder")
         return cls(vae=vae, text_encoder=text_encoder, tokenizer=tokenizer, unet=unet, scheduler=scheduler)
 
@@ -96,16 +96,32 @@ class LatentToVideoPipeline:
                 prompt_embeds.shape != negative_prompt_embeds.shape:
             raise ValueError("`prompt_embeds` and `negative_prompt_embeds` must have the same shape")
 
+    def _b200_text_encoder(self):
+        """The text encoder as an sm_100a `clip_text.CLIPTextModel`.  A `transformers.CLIPTextModel` handed in by the
+        caller (train.py:88,799 does exactly that) is mirrored once (same weights, dtype, device) so that prompt strings
+        never run a library GEMM / SDPA; the mirror is rebuilt if the caller swaps or moves the encoder."""
+        from .clip_text import CLIPTextModel
+        te = self.text_encoder
+        if te is None or isinstance(te, CLIPTextModel):
+            return te
+        p0 = next(te.parameters())
+        key = (id(te), p0.data_ptr(), p0.dtype, p0.device)
+        cached = self.__dict__.get("_te_mirror")
+        if cached is None or cached[0] != key:
+            cached = (key, CLIPTextModel.from_hf(te))
+            self.__dict__["_te_mirror"] = cached
+        return cached[1]
+
     def _encode_prompt(self, prompt, device, num_images_per_prompt, do_cfg, negative_prompt=None, prompt_embeds=None,
                        negative_prompt_embeds=None, lora_scale=None):
         """diffusers TextToVideoSDPipeline._encode_prompt: CLIP text states; under CFG returns cat([negative, positive]).
-        The CLIP forward itself is a library call (SURVEY.md 8f.2 'next')."""
+        The CLIP forward runs on the sm_100a kernels (clip_text.py)."""
         def embed(texts):
             if self.text_encoder is None or self.tokenizer is None:
                 raise ValueError("prompt strings need a text_encoder/tokenizer; pass prompt_embeds instead")
             tok = self.tokenizer(texts, padding="max_length", max_length=self.tokenizer.model_max_length,
                                  truncation=True, return_tensors="pt")
-            return self.text_encoder(tok.input_ids.to(device))[0]
+            return self._b200_text_encoder()(tok.input_ids.to(device))[0]
         if prompt_embeds is None:
             prompt_embeds = embed([prompt] if isinstance(prompt, str) else prompt)
         dtype = self.unet.dtype

@@ -202,10 +202,163 @@ def synth_inputs(rank, pinned=True):
     return d
 
 
+def _stack_inputs(n_prompts, dev=None, pinned=False):
+    import torch
+    per = [synth_inputs(i, pinned=False) for i in range(n_prompts)]
+    d = {k: torch.cat([p[k] for p in per]) for k in per[0] if k != "mask"}
+    d["mask"] = per[0]["mask"]
+    if pinned:
+        d = {k: v.pin_memory() for k, v in d.items()}
+    if dev is not None:
+        d = {k: v.to(dev) for k, v in d.items()}
+    return d
+
+
+def _ev_ms(fn, reps=1, warm=1):
+    """CUDA-event time of fn() on the current stream, ms per call."""
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def parity_check(pipe, devin, dev, kw):
+    """2 DDIM steps of the BENCHMARKED configuration (same weights, same inputs, graph replay as timed) against the fp32
+    oracle and the stock bf16 torch execution on the same GPU.  Returns the dict stored under config.parity_check and
+    the (bf16) oracle modules for the torch-eager leg."""
+    import torch
+    from oracle.composition import (AutoencoderKL as OVAE, DDIMScheduler as ODDIM, OracleUNet3D, oracle_sampling_loop)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    with torch.device(dev):
+        ounet = OracleUNet3D(motion_mask=True, motion_strength=True).eval()
+        ovae = OVAE().eval()
+    ounet.load_state_dict({k: v.float() for k, v in pipe.unet.state_dict().items()})
+    ovae.load_state_dict({k: v.float() for k, v in pipe.vae.state_dict().items()})
+    kw2 = dict(kw, num_inference_steps=2)
+    video, lat = pipe(prompt_embeds=devin["prompt_embeds"], negative_prompt_embeds=devin["negative_prompt_embeds"],
+                      latents=devin["latents"], condition_latent=devin["condition_latent"], mask=devin["mask"], **kw2)
+    f32 = {k: v.float() for k, v in devin.items()}
+    _, rl = oracle_sampling_loop(ounet, ODDIM(**SCHED), f32["latents"], f32["prompt_embeds"],
+                                 f32["negative_prompt_embeds"], f32["condition_latent"], f32["mask"], [4], GUIDANCE, 2,
+                                 vae=None)
+    ounet, ovae = ounet.to(torch.bfloat16), ovae.to(torch.bfloat16)
+    _, sl = oracle_sampling_loop(ounet, ODDIM(**SCHED), devin["latents"], devin["prompt_embeds"],
+                                 devin["negative_prompt_embeds"], devin["condition_latent"], devin["mask"], [4],
+                                 GUIDANCE, 2, vae=None)
+    # VAE decode compared on IDENTICAL latents (the product's): a random-init decoder amplifies the few-percent latent
+    # difference of two bf16 loops into decorrelated pixels, which would say nothing about the decoder kernels
+    from oracle.composition import oracle_decode_latents
+    with torch.no_grad():
+        sv = oracle_decode_latents(ovae, lat)
+        rv = oracle_decode_latents(ovae.float(), lat.float())
+    ovae = ovae.to(torch.bfloat16)
+
+    def rel(a, b):
+        return float((a.float() - b.float()).abs().max() / b.float().abs().mean())
+
+    def relmean(a, b):
+        return float((a.float() - b.float()).abs().mean() / b.float().abs().mean())
+    res = {"what": "2 DDIM steps (CFG 9) of config 2 (bf16, CUDA-graph replay) vs the fp32 oracle on the same GPU, same "
+                   "random-init weights and inputs; video = VAE decode of the SAME (product) latents by both; 'stock' = "
+                   "the same ops through cuDNN/cuBLAS/SDPA in bf16",
+           "latents_max_err_over_mean_ref": rel(lat, rl), "latents_mean_err_over_mean_ref": relmean(lat, rl),
+           "video_max_err_over_mean_ref": rel(video, rv), "video_mean_err_over_mean_ref": relmean(video, rv),
+           "stock_latents_max_err_over_mean_ref": rel(sl, rl), "stock_latents_mean_err_over_mean_ref": relmean(sl, rl),
+           "stock_video_max_err_over_mean_ref": rel(sv, rv), "stock_video_mean_err_over_mean_ref": relmean(sv, rv)}
+    res["ok"] = bool(res["latents_mean_err_over_mean_ref"] <= 2.0 * res["stock_latents_mean_err_over_mean_ref"] + 1e-3
+                     and res["video_mean_err_over_mean_ref"] <= 2.0 * res["stock_video_mean_err_over_mean_ref"] + 1e-3)
+    return res, ounet, ovae
+
+
+def torch_eager_leg(ounet, ovae, devin, dev, e2e_value):
+    """The comparison the north star names: the reference's op sequence through stock torch (cuDNN / cuBLAS / SDPA) in
+    bf16 on the SAME GPU (the oracle modules; real diffusers is not installable).  Outside the timed region."""
+    import torch
+    from oracle.composition import DDIMScheduler as ODDIM, oracle_decode_latents, oracle_sampling_loop
+    sample = devin["latents"].expand(2, -1, -1, -1, -1).contiguous()
+    cond2 = torch.cat([devin["condition_latent"]] * 2)
+    ehs = torch.cat([devin["negative_prompt_embeds"], devin["prompt_embeds"]])
+    mot = torch.tensor([4.0], device=dev)
+    with torch.no_grad():
+        unet_ms = _ev_ms(lambda: ounet(sample, 500, ehs, cond2, devin["mask"], motion=mot), reps=3, warm=1)
+        vae_ms = _ev_ms(lambda: oracle_decode_latents(ovae, devin["latents"]), reps=2, warm=1)
+        clip_ms = _ev_ms(lambda: oracle_sampling_loop(ounet, ODDIM(**SCHED), devin["latents"], devin["prompt_embeds"],
+                                                      devin["negative_prompt_embeds"], devin["condition_latent"],
+                                                      devin["mask"], [4], GUIDANCE, STEPS_DDIM, vae=ovae), reps=1, warm=0)
+    fps = FRAMES / (clip_ms / 1e3)
+    return {"what": "oracle modules (the reference's op sequence) in bf16 through stock torch on the same GPU, device-"
+                    "resident inputs, 1 clip", "unet_fwd_ms": unet_ms, "vae_decode_16f_ms": vae_ms,
+            "clip_s": clip_ms / 1e3, "frames_per_s": fps, "this_repo_e2e_over_torch_eager": e2e_value / fps}
+
+
+def kernel_rooflines(pipe, devin, dev):
+    """Per-kernel CUDA-event timing of ONE eager UNet forward (config 2): tensor roofline of the implicit GEMM (dominant)
+    and of flash attention, HBM roofline of the norm / temporal-attention kernels (algorithmic bytes)."""
+    import torch
+    from animate_anything_b200 import ops
+    peak_tf, peak_hbm, peak_src = _peaks()
+    sample = devin["latents"].expand(2, -1, -1, -1, -1)
+    cond2 = torch.cat([devin["condition_latent"]] * 2)
+    ehs = torch.cat([devin["negative_prompt_embeds"], devin["prompt_embeds"]])
+    tt = torch.tensor([500.0], device=dev)
+    mot = torch.tensor([4.0], device=dev)
+
+    def fwd():
+        pipe.unet(sample, tt, ehs, condition_latent=cond2, mask=devin["mask"], motion=mot, _raw_eps=True)
+    unet_ms = _ev_ms(fwd, reps=3, warm=2)
+    ops.IGEMM_PROFILE = []
+    fwd()
+    torch.cuda.synchronize()
+    prof = ops.IGEMM_PROFILE
+    ops.IGEMM_PROFILE = None
+    tot_ms = sum(p["ev"][0].elapsed_time(p["ev"][1]) for p in prof)
+    tot_fl = sum(p["flops"] for p in prof)
+    achieved = tot_fl / (tot_ms * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("igemm_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roof = {"bound": "tensor", "kernel": "aab::igemm_kernel (tcgen05 implicit GEMM, all launches of one UNet forward)",
+            "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+            "peak_source": peak_src, "launches": len(prof), "algorithmic_tflop_per_forward": tot_fl / 1e12,
+            "igemm_ms_per_forward": tot_ms, "avg_launch_us": tot_ms * 1e3 / max(1, len(prof))}
+    ops.KERNEL_PROFILE = []
+    fwd()
+    torch.cuda.synchronize()
+    kp = ops.KERNEL_PROFILE
+    ops.KERNEL_PROFILE = None
+    other = {}
+    for name in sorted({p["name"] for p in kp}):
+        sel = [p for p in kp if p["name"] == name]
+        ms = sum(p["ev"][0].elapsed_time(p["ev"][1]) for p in sel)
+        by = sum(p["bytes"] for p in sel)
+        fl = sum(p["flops"] for p in sel)
+        ent = {"launches": len(sel), "ms_per_forward": ms, "algorithmic_GB": by / 1e9}
+        if name == "flash_attn_d64":
+            ent.update(bound="tensor", achieved=fl / (ms * 1e-3) / 1e12, peak=peak_tf, unit="TFLOP/s")
+        else:
+            ent.update(bound="hbm", achieved=by / (ms * 1e-3) / 1e9, peak=peak_hbm, unit="GB/s")
+        ent["frac"] = ent["achieved"] / ent["peak"]
+        other[name] = ent
+    roof["other_kernels"] = other
+    return roof, unet_ms
+
+
 def run_product(args):
     import torch
     import torch.distributed as dist
-    from animate_anything_b200 import _lib, ops
+    from animate_anything_b200 import _lib
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -217,25 +370,44 @@ def run_product(args):
     dtype = torch.bfloat16
     pipe = build_models(dev, dtype)
     pipe.use_cuda_graph = not args.no_graph
-    host = synth_inputs(rank)
-    devin = {k: v.to(dev) for k, v in host.items()}
-    kw = dict(motion=[4], guidance_scale=GUIDANCE, num_inference_steps=STEPS_DDIM, output_type="pt", return_dict=False)
-    gather_buf = None
-    if world > 1:
-        gather_buf = torch.empty((world, 3, FRAMES, HW, HW), dtype=torch.uint8, device=dev)
-
-    def one_clip(inp):
-        video, lat = pipe(prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
-                          latents=inp["latents"], condition_latent=inp["condition_latent"], mask=inp["mask"], **kw)
-        if world > 1:     # the one collective of the path: all-gather of the decoded frames (uint8, 12.6 MB per clip)
-            u8 = video[0].mul(127.5).add_(127.5).clamp_(0, 255).to(torch.uint8)
-            dist.all_gather_into_tensor(gather_buf, u8.unsqueeze(0).contiguous())
-        return video, lat
+    latency = args.mode == "latency" and world > 1
+    kw = dict(motion=[4], guidance_scale=GUIDANCE, num_inference_steps=STEPS_DDIM, return_dict=False)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if latency:
+        # BASELINE config 3 ("CFG batch=8 = 4 prompts x cond/uncond, sharded across 8 GPUs"): N=2 -> ONE clip with its CFG
+        # halves on two GPUs; N=4 -> 4 prompts, pairs co-located; N=8 -> 4 prompts, one batch element per GPU.
+        from animate_anything_b200.parallel import LatencyShardedPipeline
+        n_prompts = 1 if world == 2 else 4
+        if world not in (2, 4, 8):
+            raise SystemExit("--mode latency supports 2, 4 or 8 GPUs")
+        host = _stack_inputs(n_prompts, pinned=True)
+        devin = {k: v.to(dev) for k, v in host.items()}
+        runner = LatencyShardedPipeline(pipe, n_prompts)
+        clips_per_step = n_prompts
+
+        def one_clip(inp):
+            return runner(inp["prompt_embeds"], inp["negative_prompt_embeds"], inp["latents"], inp["condition_latent"],
+                          mask=inp["mask"], **{k: v for k, v in kw.items() if k != "return_dict"})
+    else:
+        host = synth_inputs(rank)
+        devin = {k: v.to(dev) for k, v in host.items()}
+        clips_per_step = world
+        gather_buf = torch.empty((world, FRAMES, HW, HW, 3), dtype=torch.uint8, device=dev) if world > 1 else None
+
+        def one_clip(inp):
+            # N = 1: float video on the device ("pt"); N > 1: uint8 frames from the fused decoder tail, then the one
+            # collective of the path: all-gather of the decoded frames (12.6 MB per clip)
+            video, lat = pipe(prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
+                              latents=inp["latents"], condition_latent=inp["condition_latent"], mask=inp["mask"],
+                              output_type="pt" if world == 1 else "u8", **kw)
+            if world > 1:
+                dist.all_gather_into_tensor(gather_buf, video.unsqueeze(0))
+            return video, lat
 
     for _ in range(args.warmup):
         one_clip(devin)
@@ -263,20 +435,24 @@ def run_product(args):
         launches = launches + (per_step or 0) * STEPS_DDIM * args.steps
     finite = bool(torch.isfinite(lat.float()).all().item())
 
-    # ---- e2e: the call a user makes — pinned HOST inputs copied in every step, default output (uint8 numpy frames, i.e.
-    # decode + tensor2vid fused on the device, then one D2H read of the frames) returned on the host every step
+    # ---- e2e: the call a user makes -- pinned HOST inputs copied in every step, the decoded uint8 frames (decode +
+    # tensor2vid fused on the device) read back to the host every step
     h2d = sum(v.numel() * v.element_size() for v in host.values())
-    d2h = FRAMES * HW * HW * 3
-    kw_np = dict(kw)
-    kw_np["output_type"] = "np"
+    d2h = FRAMES * HW * HW * 3 * (clips_per_step if latency else 1)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for _ in range(args.steps):
         inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        frames, _ = pipe(prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
-                         latents=inp["latents"], condition_latent=inp["condition_latent"], mask=inp["mask"], **kw_np)
-        assert len(frames) == FRAMES and frames[0].dtype.name == "uint8"
+        if latency:
+            frames, _ = one_clip(inp)
+            frames_host = frames.cpu()
+            assert frames_host.shape[:2] == (clips_per_step, FRAMES) and frames_host.dtype == torch.uint8
+        else:
+            frames, _ = pipe(prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
+                             latents=inp["latents"], condition_latent=inp["condition_latent"], mask=inp["mask"],
+                             output_type="np", **kw)
+            assert len(frames) == FRAMES and frames[0].dtype.name == "uint8"
     e3.record()
     barrier()
     sampler.stop_flag = True
@@ -284,75 +460,125 @@ def run_product(args):
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    total_frames = FRAMES * world * args.steps
+    total_frames = FRAMES * clips_per_step * args.steps
     value = total_frames / t_dev.item()
     e2e_v = total_frames / t_e2e.item()
 
-    roof = None
-    unet_ms = None
-    cpu_base = None
-    if rank == 0:
-        # ---- per-kernel timing of one eager UNet forward: every tcgen05 implicit-GEMM launch with CUDA events
-        peak_tf, peak_hbm, peak_src = _peaks()
+    lat_info = None
+    if latency:
+        lat_info = latency_breakdown(pipe, runner, devin, dev, rank, world, lat, video, kw, t_dev.item() / args.steps)
+
+    roof = unet_ms = cpu_base = parity = eager = vae_ms = None
+    if rank == 0 and not latency:
+        saved_graph = pipe.use_cuda_graph
         pipe.use_cuda_graph = False
-        sample = devin["latents"].expand(2, -1, -1, -1, -1)
-        cond2 = torch.cat([devin["condition_latent"]] * 2)
-        ehs = torch.cat([devin["negative_prompt_embeds"], devin["prompt_embeds"]])
-        tt = torch.tensor([500.0], device=dev)
-        mot = torch.tensor([4.0], device=dev)
-        for _ in range(2):
-            pipe.unet(sample, tt, ehs, condition_latent=cond2, mask=devin["mask"], motion=mot, _raw_eps=True)
-        torch.cuda.synchronize()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(3):
-            pipe.unet(sample, tt, ehs, condition_latent=cond2, mask=devin["mask"], motion=mot, _raw_eps=True)
-        f1.record()
-        torch.cuda.synchronize()
-        unet_ms = f0.elapsed_time(f1) / 3
-        ops.IGEMM_PROFILE = []
-        pipe.unet(sample, tt, ehs, condition_latent=cond2, mask=devin["mask"], motion=mot, _raw_eps=True)
-        torch.cuda.synchronize()
-        prof = ops.IGEMM_PROFILE
-        ops.IGEMM_PROFILE = None
-        tot_ms = sum(p["ev"][0].elapsed_time(p["ev"][1]) for p in prof)
-        tot_fl = sum(p["flops"] for p in prof)
-        achieved = tot_fl / (tot_ms * 1e-3) / 1e12
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tp):
+        roof, unet_ms = kernel_rooflines(pipe, devin, dev)
+        vae_ms = _ev_ms(lambda: pipe.vae.decode_frames_uint8(devin["latents"]), reps=3, warm=1)
+        pipe.use_cuda_graph = saved_graph
+        if world == 1 and not args.no_parity:
             try:
-                traffic = json.load(open(tp)).get("igemm_dram_bytes_per_launch")
-            except Exception:
-                traffic = None
-        roof = {"bound": "tensor", "kernel": "aab::igemm_kernel (tcgen05 implicit GEMM, all launches of one UNet forward)",
-                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
-                "peak_source": peak_src, "launches": len(prof), "algorithmic_tflop_per_forward": tot_fl / 1e12,
-                "igemm_ms_per_forward": tot_ms, "avg_launch_us": tot_ms * 1e3 / max(1, len(prof))}
+                parity, ounet, ovae = parity_check(pipe, devin, dev, dict(kw, output_type="pt"))
+                eager = torch_eager_leg(ounet, ovae, devin, dev, e2e_v / world)
+                del ounet, ovae
+            except Exception as ex:      # the oracle is a checker; never let it break the bench line
+                parity = {"ok": None, "failed": repr(ex)}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 _, fwd, f_sample, desc, threads = _oracle_unet_sample()
                 ts = fwd(f_sample, LAT)
                 cpu_base = {"value": cpu_frames_per_sec(ts, f_sample), "unit": UNIT, "cores": threads, "kind": "port",
                             "sample": desc + f" ({ts:.1f} s); x(17/T) x 2 (CFG) x 50 steps, extrapolated"}
-            except Exception as ex:      # the oracle is a checker; never let it break the bench line
+            except Exception as ex:
                 cpu_base = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+    if rank == 0:
+        if latency:
+            workload = (f"config3 ({clips_per_step} prompt(s) x cond/uncond, 16x512x512, 50 DDIM steps, CFG 9) on {world} "
+                        f"GPUs: " + ("CFG halves of ONE clip on two GPUs (per-step all-gather of the fp32 noise prediction)"
+                                     if world == 2 else "pairs co-located, no per-step traffic" if world == 4 else
+                                     "one batch element per GPU (pair exchange per step)") +
+                        "; VAE decode frame-sharded inside a pair; one NCCL all-gather of uint8 frames")
+            par = {2: "cfg2", 4: "prompts4", 8: "prompts4 x cfg2"}[world]
+        else:
+            workload = ("config2: LatentToVideoPipeline.__call__ 16x512x512, 50 DDIM steps, CFG 9, random-init UNet3D "
+                        "(1.41B) + SD VAE, 1 clip per GPU")
+            par = f"clips x{world} (prompt-sharded), 1 NCCL all-gather of frames" if world > 1 else "single GPU"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": t_dev.item() / args.steps * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": "config2: LatentToVideoPipeline.__call__ 16x512x512, 50 DDIM steps, CFG 9, "
-                                       "random-init UNet3D (1.41B) + SD VAE, 1 clip per GPU",
+                "scaling": "strong" if latency else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "mode": args.mode if world > 1 else "throughput",
+                "config": {"workload": workload,
                            "l2_policy": "working set per UNet forward (2.8 GB weights + activations) >> 126 MB L2",
-                           "cuda_graph": not args.no_graph, "finite_output": finite,
-                           "parallelism": f"clips x{world} (prompt-sharded), 1 NCCL all-gather of frames" if world > 1
-                           else "single GPU"},
-                "unet_fwd_ms_per_step": unet_ms, "clocks": sampler.summary(),
+                           "cuda_graph": not args.no_graph, "finite_output": finite, "parallelism": par,
+                           "parity_check": parity},
+                "unet_fwd_ms_per_step": unet_ms, "vae_decode_16f_ms": vae_ms, "clocks": sampler.summary(),
                 "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_base}
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_base, "torch_eager_gpu": eager}
+        if lat_info is not None:
+            line["latency"] = lat_info
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def latency_breakdown(pipe, runner, devin, dev, rank, world, lat_split, frames_split, kw, clip_s):
+    """Names the limiter of the split run with numbers (rank 0, CUDA events): the UNet half forward, the per-step
+    all-gather of the noise prediction, the fused CFG+scheduler step, the sharded VAE decode, the frame all-gather; and
+    checks the split result against the same clip computed on ONE GPU (rank 0 alone), bit for bit."""
+    import torch
+    import torch.distributed as dist
+    from animate_anything_b200 import ops
+    info = {"clip_latency_s": clip_s, "clips_in_flight": runner.n_prompts, "ranks_per_prompt": runner.ranks_per_prompt}
+    i = runner.prompt
+    one = {k: (v if k == "mask" else v[i: i + 1]) for k, v in devin.items()}
+    tt = torch.tensor([500.0], device=dev)
+    mot = torch.tensor([4.0], device=dev)
+    graph = pipe.use_cuda_graph
+    if runner.ranks_per_prompt == 2:
+        pair = runner.pair
+        r = dist.get_rank(pair)
+        ehs = (one["negative_prompt_embeds"], one["prompt_embeds"])[r]
+        pipe.use_cuda_graph = False
+
+        def half():
+            return pipe.unet(one["latents"], tt, ehs, condition_latent=one["condition_latent"], mask=one["mask"],
+                             motion=mot, _raw_eps=True)
+        info["unet_half_fwd_ms"] = _ev_ms(half, reps=3, warm=2)
+        eps_half, _ = half()
+        buf = torch.empty((2,) + tuple(eps_half.shape), dtype=eps_half.dtype, device=dev)
+        info["eps_allgather_us"] = 1e3 * _ev_ms(lambda: dist.all_gather_into_tensor(buf, eps_half.unsqueeze(0), group=pair),
+                                                reps=20, warm=3)
+        info["eps_allgather_bytes"] = int(buf.numel() * buf.element_size())
+        f = lat_split.shape[2]
+        info["vae_decode_half_ms"] = _ev_ms(lambda: pipe.vae.decode_frames_uint8(lat_split[:, :, : f // 2].contiguous()),
+                                            reps=2, warm=1)
+    fr = torch.empty((world,) + tuple(frames_split.shape[1:]), dtype=torch.uint8, device=dev) \
+        if runner.ranks_per_prompt == 1 else torch.empty((world, FRAMES // 2, HW, HW, 3), dtype=torch.uint8, device=dev)
+    src = fr[0].clone()
+    info["frames_allgather_ms"] = _ev_ms(lambda: dist.all_gather_into_tensor(fr, src.unsqueeze(0)), reps=5, warm=2)
+    info["frames_allgather_bytes"] = int(fr.numel())
+    # the same clip(s) on ONE GPU: rank 0 alone, the others wait at the barrier
+    saved = pipe.cfg_group
+    pipe.cfg_group = None
+    pipe.use_cuda_graph = graph
+    dist.barrier()
+    if rank == 0:
+        kw1 = {k: v for k, v in kw.items() if k != "return_dict"}
+
+        def single():
+            return pipe(prompt_embeds=one["prompt_embeds"], negative_prompt_embeds=one["negative_prompt_embeds"],
+                        latents=one["latents"], condition_latent=one["condition_latent"], mask=one["mask"],
+                        output_type="u8", return_dict=False, **kw1)
+        single()
+        ms = _ev_ms(single, reps=1, warm=0)
+        f1, l1 = single()
+        info["one_gpu_clip_s"] = ms / 1e3
+        info["speedup_vs_one_gpu_same_clips"] = (ms / 1e3) * runner.n_prompts / clip_s
+        info["latents_bit_identical_to_1gpu"] = bool(torch.equal(l1, lat_split))
+        info["frames_bit_identical_to_1gpu"] = bool(torch.equal(f1, frames_split[0]))
+    dist.barrier()
+    pipe.cfg_group = saved
+    return info
 
 
 def main():
@@ -363,6 +589,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="disable CUDA-graph replay of the denoising step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity check and the torch-eager leg")
+    ap.add_argument("--mode", default="throughput", choices=["throughput", "latency"],
+                    help="N>1 only. throughput (default, what the driver's scaling run uses): one clip per GPU. latency: "
+                         "BASELINE config 3 -- N=2 one clip with its CFG halves on two GPUs; N=4 four prompts, pairs "
+                         "co-located; N=8 four prompts, one batch element per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

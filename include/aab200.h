@@ -31,7 +31,10 @@ int aab_igemm(const AabIgemmDesc* desc, void* stream);
 /* Spatial self-attention / text cross-attention, head_dim 64, flash-style on tcgen05
  * (diffusers AttnProcessor2_0 -> F.scaled_dot_product_attention; installed by train.py:124-138, blocks built at
  * models/unet_3d_blocks.py:287-296,446-456,681-691).  q: [nb*lq, ldq] with head h at columns q_col0 + 64 h;
- * k, v: columns k_col0 / v_col0 of kv [nb_kv*lk, ldkv]; query batch b reads kv batch b / kv_batch_div. */
+ * k, v: columns k_col0 / v_col0 of kv [nb_kv*lk, ldkv]; query batch b reads kv batch b / kv_batch_div.
+ * `is_bf16` bit 0: bfloat16 (else float16); bit 1: causal mask (key j visible to query i iff j <= i; needs lq == lk <= 128):
+ * the CLIP text tower's self-attention (transformers CLIPAttention + causal_attention_mask), reached from
+ * models/pipeline.py:136 `_encode_prompt`. */
 int aab_flash_attn_d64(const void* q, long ldq, long q_batch_stride, int q_cols, int q_col0, const void* kv, long ldkv,
                        long kv_batch_stride, int kv_cols, int k_col0, int v_col0, void* out, long ld_out,
                        long out_batch_stride, int out_col0, int nb, int nb_kv, int kv_batch_div, int heads, int lq, int lk,
@@ -67,6 +70,11 @@ int aab_unet_out_finalize(const float* y, int ldc, void* out, int b, int t, int 
 
 /* Sinusoidal timestep / motion embedding, flip_sin_to_cos=True, shift 0 (models/unet_3d_condition_mask.py:146,156,408,415). */
 int aab_timestep_embed(const float* t, int t_count, void* out, int b, int dim, int is_bf16, void* stream);
+
+/* CLIP text embeddings (transformers CLIPTextEmbeddings.forward; models/pipeline.py:136 _encode_prompt):
+ * out[r, :] = tok_emb[ids[r], :] + pos_emb[r % seq_len, :]; ids int64 [rows], 16-bit tables, c % 8 == 0. */
+int aab_embed_tokens(const long long* ids, const void* tok_emb, const void* pos_emb, void* out, long rows, int seq_len,
+                     int c, int vocab, int is_bf16, void* stream);
 
 /* Unfused fallbacks / helpers: GEGLU gate (diffusers GEGLU.forward), nearest 2x upsample (Upsample2D), copies. */
 int aab_geglu(const void* x, long ldx, void* out, long ldo, long rows, int nh, int is_bf16, void* stream);
