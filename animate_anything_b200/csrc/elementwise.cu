@@ -148,6 +148,46 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
   y[i] = __ldg(&x[((nn * H + (oy >> 1)) * W + (ox >> 1)) * V + v]);
 }
 
+// nearest-neighbour resize to an arbitrary output size (diffusers Upsample2D with `output_size`, i.e.
+// F.interpolate(x, size=(OH, OW), mode="nearest"): src = min(floor(dst * (in / out)), in - 1) with the scale in fp32, as ATen
+// computes it).  Reached when the latent size is not a multiple of 8 (models/unet_3d_condition_mask.py:377-383,486-491).
+__global__ void upsample_nearest_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long n, int H, int W, int OH,
+                                        int OW, int V) {
+  const long total = n * OH * OW * V;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int v = i % V;
+  long r = i / V;
+  const int ox = r % OW;
+  r /= OW;
+  const int oy = r % OH;
+  const long nn = r / OH;
+  const float sh = static_cast<float>(H) / static_cast<float>(OH);
+  const float sw = static_cast<float>(W) / static_cast<float>(OW);
+  int sy = static_cast<int>(floorf(static_cast<float>(oy) * sh));
+  int sx = static_cast<int>(floorf(static_cast<float>(ox) * sw));
+  sy = sy < H - 1 ? sy : H - 1;
+  sx = sx < W - 1 ? sx : W - 1;
+  y[i] = __ldg(&x[((nn * H + sy) * W + sx) * V + v]);
+}
+
+// zero padding at the bottom / right: [N, H, W, C] -> [N, H + ph, W + pw, C].  Makes an odd-sized activation even so that the
+// stride-2 convolution can use its space-to-depth view; the added zeros are exactly the conv's own zero padding.
+__global__ void pad_br_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long n, int H, int W, int PH, int PW, int V) {
+  const long total = n * PH * PW * V;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int v = i % V;
+  long r = i / V;
+  const int ox = r % PW;
+  r /= PW;
+  const int oy = r % PH;
+  const long nn = r / PH;
+  uint4 val = make_uint4(0, 0, 0, 0);
+  if (oy < H && ox < W) val = __ldg(&x[((nn * H + oy) * W + ox) * V + v]);
+  y[i] = val;
+}
+
 // strided 16-bit copy of a [rows, cols] block (used for K/V^T staging and channel concat fallbacks)
 __global__ void copy2d_kernel(const uint16_t* __restrict__ src, long lds, uint16_t* __restrict__ dst, long ldd, long rows,
                               int cols) {
@@ -464,6 +504,24 @@ extern "C" int aab_upsample2x(const void* x, void* y, long n, int h, int w, int 
   const long total = n * 2 * h * 2 * w * (c / 8);
   upsample2x_kernel<<<AAB_GRID(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x),
                                                                reinterpret_cast<uint4*>(y), n, h, w, c / 8);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_upsample_nearest(const void* x, void* y, long n, int h, int w, int oh, int ow, int c, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !y || (c % 8) || h < 1 || w < 1 || oh < 1 || ow < 1) return AAB_ERR_ARG;
+  const long total = n * oh * ow * (c / 8);
+  upsample_nearest_kernel<<<AAB_GRID(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x),
+                                                                     reinterpret_cast<uint4*>(y), n, h, w, oh, ow, c / 8);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_pad_br(const void* x, void* y, long n, int h, int w, int ph, int pw, int c, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !y || (c % 8) || ph < h || pw < w) return AAB_ERR_ARG;
+  const long total = n * ph * pw * (c / 8);
+  pad_br_kernel<<<AAB_GRID(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), n,
+                                                           h, w, ph, pw, c / 8);
   AAB_LAUNCH_RET();
 }
 

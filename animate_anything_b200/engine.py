@@ -43,7 +43,8 @@ class Geo:
         return self.b * self.t * self.h * self.w
 
     def down(self):
-        return Geo(self.b, self.t, self.h // 2, self.w // 2)
+        # conv 3x3, stride 2, padding 1: ceil(h / 2)
+        return Geo(self.b, self.t, (self.h + 1) // 2, (self.w + 1) // 2)
 
     def up(self):
         return Geo(self.b, self.t, self.h * 2, self.w * 2)
@@ -279,11 +280,22 @@ def temporal_transformer_forward(ctx: Ctx, m: L.TransformerTemporalModel, x: tor
 
 
 def downsample_forward(ctx: Ctx, m: L.Downsample2D, x: torch.Tensor, g: Geo, pad_mode="sym"):
+    """Downsample2D: conv 3x3 stride 2.  Odd H / W (latent sizes that are not multiples of 8) are zero-padded to even
+    first: for padding 1 the extra row / column is the conv's own zero padding, so the result is unchanged."""
     p = ctx.prep.get(m)
-    return ops.conv3x3_stride2(x.view(g.n, g.h, g.w, m.channels), p["c"][0], p["c"][1], pad_mode=pad_mode)
+    x4 = x.view(g.n, g.h, g.w, m.channels)
+    if (g.h | g.w) & 1:
+        if pad_mode != "sym":
+            raise NotImplementedError("VAE encoder needs even feature-map sizes (image height/width multiples of 8)")
+        x4 = ops.pad_to_even(x4)
+    out = ops.conv3x3_stride2(x4, p["c"][0], p["c"][1], pad_mode=pad_mode)
+    return out
 
 
-def upsample_forward(ctx: Ctx, m: L.Upsample2D, x: torch.Tensor, g: Geo):
+def upsample_forward(ctx: Ctx, m: L.Upsample2D, x: torch.Tensor, g: Geo, size=None):
+    """Upsample2D: nearest x2 (or to `size` = (h, w): the reference's `upsample_size` path,
+    models/unet_3d_condition_mask.py:486-491) then conv 3x3."""
     p = ctx.prep.get(m)
-    up = ops.upsample2x(x.view(g.n, g.h, g.w, m.channels))
+    x4 = x.view(g.n, g.h, g.w, m.channels)
+    up = ops.upsample2x(x4) if size is None or tuple(size) == (2 * g.h, 2 * g.w) else ops.upsample_nearest(x4, *size)
     return ops.conv3x3(up, p["c"][0], p["c"][1])

@@ -392,6 +392,25 @@ def upsample2x(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def upsample_nearest(x: torch.Tensor, oh: int, ow: int) -> torch.Tensor:
+    """F.interpolate(size=(oh, ow), mode="nearest") on channels-last [N, H, W, C]."""
+    n, h, w, c = x.shape
+    y = torch.empty((n, oh, ow, c), device=x.device, dtype=x.dtype)
+    _lib.call("aab_upsample_nearest", _ptr(x), _ptr(y), n, h, w, oh, ow, c, _stream())
+    return y
+
+
+def pad_to_even(x: torch.Tensor) -> torch.Tensor:
+    """[N, H, W, C] -> zero-padded at the bottom / right to even H, W (no-op when already even)."""
+    n, h, w, c = x.shape
+    ph, pw = h + (h & 1), w + (w & 1)
+    if (ph, pw) == (h, w):
+        return x
+    y = torch.empty((n, ph, pw, c), device=x.device, dtype=x.dtype)
+    _lib.call("aab_pad_br", _ptr(x), _ptr(y), n, h, w, ph, pw, c, _stream())
+    return y
+
+
 def dup_rows(x: torch.Tensor) -> torch.Tensor:
     """[R, C] -> [2R, C] with both halves equal to x (CFG pair sharing its prefix)."""
     assert x.is_contiguous()

@@ -46,6 +46,26 @@ class _Base:
         args.update({k: v for k, v in kw.items() if k in sig})
         return cls(**args)
 
+    @classmethod
+    def from_pretrained(cls, path, subfolder=None, **kw):
+        """diffusers SchedulerMixin.from_pretrained (train.py:87 `DDPMScheduler.from_pretrained(path, subfolder="scheduler")`):
+        reads `scheduler_config.json`; keys the class does not know (and `_class_name` etc.) are ignored."""
+        import json
+        import os
+        root = os.path.join(path, subfolder) if subfolder else path
+        with open(os.path.join(root, "scheduler_config.json")) as f:
+            cfg = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
+        return cls.from_config(cfg, **kw)
+
+    def save_pretrained(self, path):
+        import json
+        import os
+        os.makedirs(path, exist_ok=True)
+        cfg = {k: (list(v) if isinstance(v, tuple) else v) for k, v in self.config.items()}
+        cfg["_class_name"] = type(self).__name__
+        with open(os.path.join(path, "scheduler_config.json"), "w") as f:
+            json.dump(cfg, f, indent=2)
+
     def _init_tables(self):
         c = self.config
         # float32 tables like diffusers (torch.linspace(..., dtype=float32)) so that indices/values agree

@@ -175,7 +175,7 @@ class CrossAttnUpBlock3D(_Block):
         self.upsamplers = (nn.ModuleList([Upsample2D(out_channels, use_conv=True, out_channels=out_channels)])
                            if add_upsample else None)
 
-    def run(self, ctx, x, g, skips):
+    def run(self, ctx, x, g, skips, upsample_size=None):
         for resnet, tconv, attn, tattn in zip(self.resnets, self.temp_convs, self.attentions, self.temp_attentions):
             skip, sg = skips.pop()
             assert (sg.h, sg.w) == (g.h, g.w)
@@ -188,8 +188,8 @@ class CrossAttnUpBlock3D(_Block):
             if g.t > 1:
                 x = E.temporal_transformer_forward(ctx, tattn, x, g)
         if self.upsamplers is not None:
-            x = E.upsample_forward(ctx, self.upsamplers[0], x, g)
-            g = g.up()
+            x = E.upsample_forward(ctx, self.upsamplers[0], x, g, size=upsample_size)
+            g = g.up() if upsample_size is None else E.Geo(g.b, g.t, upsample_size[0], upsample_size[1])
         return x, g
 
 
@@ -210,7 +210,7 @@ class UpBlock3D(_Block):
         self.upsamplers = (nn.ModuleList([Upsample2D(out_channels, use_conv=True, out_channels=out_channels)])
                            if add_upsample else None)
 
-    def run(self, ctx, x, g, skips):
+    def run(self, ctx, x, g, skips, upsample_size=None):
         for resnet, tconv in zip(self.resnets, self.temp_convs):
             skip, sg = skips.pop()
             assert (sg.h, sg.w) == (g.h, g.w)
@@ -220,8 +220,8 @@ class UpBlock3D(_Block):
             if g.t > 1:
                 x = E.temporal_conv_forward(ctx, tconv, x, g)
         if self.upsamplers is not None:
-            x = E.upsample_forward(ctx, self.upsamplers[0], x, g)
-            g = g.up()
+            x = E.upsample_forward(ctx, self.upsamplers[0], x, g, size=upsample_size)
+            g = g.up() if upsample_size is None else E.Geo(g.b, g.t, upsample_size[0], upsample_size[1])
         return x, g
 
 

@@ -262,9 +262,9 @@ class UNet3DConditionModel(ModelBase):
         b_full = 2 * b if _cfg_shared_prefix else b
         if _cfg_shared_prefix and encoder_hidden_states.shape[0] != b_full:
             raise ValueError("_cfg_shared_prefix needs encoder_hidden_states of batch 2 x sample batch")
-        if any(s % (2 ** self.num_upsamplers) != 0 for s in (h, w)):
-            raise NotImplementedError("latent height/width must be multiples of 8 (the reference's "
-                                      "`forward_upsample_size` interpolation path is not implemented)")
+        # reference :377-383: when the latent size is not a multiple of 2**num_upsamplers the upsamplers interpolate to
+        # the size of the matching skip tensor instead of x2
+        forward_upsample_size = any(s % (2 ** self.num_upsamplers) != 0 for s in (h, w))
         g = E.Geo(b, f + 1, h, w)
         ctx = E.Ctx(prep, g)
         ctx.fuse_geglu = self.fuse_geglu
@@ -304,7 +304,13 @@ class UNet3DConditionModel(ModelBase):
         if trace is not None:
             trace.append(("mid_block", x, g))
         for i, blk in enumerate(self.up_blocks):
-            x, g = blk.run(ctx, x, g, skips)
+            is_final_block = i == len(self.up_blocks) - 1
+            n_res = len(blk.resnets)
+            up_size = None
+            if not is_final_block and forward_upsample_size:       # reference :486-491: size of the next block's first skip
+                sg = skips[-n_res - 1][1]
+                up_size = (sg.h, sg.w)
+            x, g = blk.run(ctx, x, g, skips, upsample_size=up_size)
             if trace is not None:
                 trace.append((f"up_blocks.{i}", x, g))
 

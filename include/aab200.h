@@ -79,6 +79,10 @@ int aab_embed_tokens(const long long* ids, const void* tok_emb, const void* pos_
 /* Unfused fallbacks / helpers: GEGLU gate (diffusers GEGLU.forward), nearest 2x upsample (Upsample2D), copies. */
 int aab_geglu(const void* x, long ldx, void* out, long ldo, long rows, int nh, int is_bf16, void* stream);
 int aab_upsample2x(const void* x, void* y, long n, int h, int w, int c, void* stream);
+/* Upsample2D with output_size (F.interpolate(size=, mode="nearest")) and bottom/right zero padding to even sizes for the
+ * stride-2 conv: the latent-size-not-a-multiple-of-8 path, models/unet_3d_condition_mask.py:377-383,486-491. */
+int aab_upsample_nearest(const void* x, void* y, long n, int h, int w, int oh, int ow, int c, void* stream);
+int aab_pad_br(const void* x, void* y, long n, int h, int w, int ph, int pw, int c, void* stream);
 int aab_copy2d(const void* src, long lds, void* dst, long ldd, long rows, int cols, void* stream);
 /* dst[0:bytes] = dst[bytes:2*bytes] = src: batch duplication for the shared CFG prefix (torch.cat([latents] * 2), models/pipeline.py:165) */
 int aab_dup_rows(const void* src, void* dst, long bytes, void* stream);

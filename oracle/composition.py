@@ -61,7 +61,7 @@ class _OBlock(nn.Module):
             h = self.temp_attentions[i](h, num_frames=nf).sample
         return h
 
-    def forward(self, h, temb, ehs, nf, skips: Optional[List[torch.Tensor]] = None):
+    def forward(self, h, temb, ehs, nf, skips: Optional[List[torch.Tensor]] = None, upsample_size=None):
         if self.kind == "mid":
             h = self.resnets[0](h, temb)
             h = self.temp_convs[0](h, num_frames=nf)
@@ -87,7 +87,7 @@ class _OBlock(nn.Module):
                 produced.append(h)
             return h, produced
         if self.upsamplers is not None:
-            h = self.upsamplers[0](h)
+            h = self.upsamplers[0](h, upsample_size)
         return h
 
 
@@ -167,8 +167,14 @@ class OracleUNet3D(nn.Module):
             x, produced = blk(x, emb, ehs, nf)
             skips.extend(produced)
         x = self.mid_block(x, emb, ehs, nf)
-        for blk in self.up_blocks:
-            x = blk(x, emb, ehs, nf, skips)
+        # models/unet_3d_condition_mask.py:377-383,486-491: latent sizes that are not multiples of 2**num_upsamplers make
+        # every non-final up block interpolate to the size of the next skip tensor instead of x2
+        fwd_size = any(s % (2 ** (len(self.up_blocks) - 1)) != 0 for s in (hh, ww))
+        for i, blk in enumerate(self.up_blocks):
+            up_size = None
+            if i < len(self.up_blocks) - 1 and fwd_size:
+                up_size = skips[-len(blk.resnets) - 1].shape[2:]
+            x = blk(x, emb, ehs, nf, skips, upsample_size=up_size)
         x = self.conv_out(self.conv_act(self.conv_norm_out(x)))
         x = x.reshape(b, nf, -1, hh, ww).permute(0, 2, 1, 3, 4)
         return x[:, :, 1:]

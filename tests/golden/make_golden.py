@@ -81,6 +81,7 @@ def main():
 
     common_golden(diffusers)
     product_shape_goldens()
+    oddsize_unet_golden()
 
 
 SMALL = dict(sample_size=16, block_out_channels=(64, 128, 256, 256), attention_head_dim=64, cross_attention_dim=128,
@@ -218,8 +219,32 @@ def vae_fullsize_golden():
           f"|mean|={float(video.abs().mean()):.4f} ({time.time() - t0:.0f} s)")
 
 
+def oddsize_unet_golden():
+    """Verbatim reference UNet at a latent size that is NOT a multiple of 8 (15 x 17: what train.py:738-742 produces for
+    most prompt images): exercises `forward_upsample_size` (models/unet_3d_condition_mask.py:377-383,486-491) and the odd
+    stride-2 convolutions.  SMALL config, fp16-rounded weights and inputs, fp32 math."""
+    from models.unet_3d_condition_mask import UNet3DConditionModel            # verbatim reference
+    torch.manual_seed(0)
+    ref = UNet3DConditionModel(**SMALL).eval()
+    fill_deterministic(ref, seed=0)
+    ref.load_state_dict({k: v.half().float() for k, v in ref.state_dict().items()})
+    g = torch.Generator().manual_seed(2)
+    inp = dict(sample=torch.randn(1, 4, 3, 15, 17, generator=g), cond=torch.randn(1, 4, 1, 15, 17, generator=g),
+               ehs=torch.randn(1, 77, 128, generator=g), mask=(torch.rand(1, 1, 1, 15, 17, generator=g) > 0.5).float())
+    inp = {k: v.half().float() for k, v in inp.items()}
+    with torch.no_grad():
+        out = ref(inp["sample"], 321, inp["ehs"], condition_latent=inp["cond"], mask=inp["mask"],
+                  motion=torch.tensor([5.0])).sample
+    torch.save({"config": SMALL, "inputs": {k: v.half() for k, v in inp.items()}, "timestep": 321, "motion": 5.0,
+                "out": out}, os.path.join(HERE, "unet_small_oddsize_ref.pt"))
+    print("unet_small_oddsize_ref.pt", tuple(out.shape), float(out.abs().mean()))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "benchmarked":
+    if len(sys.argv) > 1 and sys.argv[1] == "oddsize":
+        import diffusers  # noqa: F401  (the shim)
+        oddsize_unet_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "benchmarked":
         # python tests/golden/make_golden.py benchmarked   (only the two expensive fixtures, minutes of CPU)
         import diffusers  # noqa: F401  (the shim)
         vae_fullsize_golden()

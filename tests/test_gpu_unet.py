@@ -200,3 +200,25 @@ def test_prepare_to_host_conversion_matches_lazy():
     assert torch.equal(ya, yb)
     with pytest.raises(ValueError):      # per-batch values: 1, B (reference broadcast rule) -- 3 values for batch 2 is an error
         a(inp["sample"], torch.tensor([1.0, 2.0, 3.0]), inp["ehs"], condition_latent=inp["cond"], mask=inp["mask"], motion=mot)
+
+
+def test_unet_odd_latent_size_upsample_size_path():
+    """Latent 15 x 17 (not a multiple of 8): the reference's `forward_upsample_size` interpolation (:377-383,486-491) and
+    odd stride-2 convolutions, against the verbatim-reference golden."""
+    from util import assert_vs_stock, record_parity
+    gold = torch.load(os.path.join(HERE, "golden", "unet_small_oddsize_ref.pt"), map_location="cpu")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dtype = torch.float16
+    oracle, ours = _models(dict(gold["config"]), dtype)
+    inp = {k: v.to(dtype).cuda() for k, v in gold["inputs"].items()}
+    mot = torch.tensor([gold["motion"]], device="cuda")
+    ref = gold["out"].cuda()
+    out = ours(inp["sample"], gold["timestep"], inp["ehs"], condition_latent=inp["cond"], mask=inp["mask"], motion=mot).sample
+    with torch.no_grad():
+        o32 = oracle(inp["sample"].float(), gold["timestep"], inp["ehs"].float(), inp["cond"].float(), inp["mask"].float(),
+                     motion=mot)
+        stock = oracle.to(dtype)(inp["sample"], gold["timestep"], inp["ehs"], inp["cond"], inp["mask"], motion=mot).float()
+    assert (o32 - ref).abs().max().item() <= 5e-3 * ref.abs().mean().item()
+    assert out.shape == ref.shape == (1, 4, 3, 15, 17)
+    assert_vs_stock(record_parity("unet SMALL fp16 odd 15x17", "output (golden)", out, ref, stock))

@@ -119,3 +119,33 @@ def test_shim_recalled_facts():
     assert torch.allclose(up(z), up.conv(F.interpolate(z, scale_factor=2.0, mode="nearest")))
     r = ResnetBlock2D(in_channels=32, out_channels=32, temb_channels=8).eval()
     assert r.conv_shortcut is None and r.norm1.eps == 1e-6
+
+
+def test_oracle_matches_reference_at_odd_latent_size():
+    """`forward_upsample_size` path (models/unet_3d_condition_mask.py:377-383,486-491): 15 x 17 latents."""
+    gold = torch.load(os.path.join(HERE, "golden", "unet_small_oddsize_ref.pt"))
+    cfg = {k: v for k, v in gold["config"].items() if k != "sample_size"}
+    m = fill_deterministic(OracleUNet3D(**cfg).eval(), seed=0)
+    m.load_state_dict({k: v.half().float() for k, v in m.state_dict().items()})
+    i = {k: v.float() for k, v in gold["inputs"].items()}
+    with torch.no_grad():
+        out = m(i["sample"], gold["timestep"], i["ehs"], i["cond"], i["mask"], motion=torch.tensor([gold["motion"]]))
+    assert torch.allclose(out, gold["out"], rtol=1e-5, atol=1e-6), float((out - gold["out"]).abs().max())
+
+
+def test_oracle_vae_matches_reference_entry_points_full_size():
+    """Full-size SD VAE: oracle helpers vs the verbatim `tensor_to_vae_latent` / `decode_latents` fixture (bf16-rounded
+    weights and inputs, fp32 math; ~15 s of CPU)."""
+    from oracle.composition import oracle_decode_latents, oracle_encode_image
+    gold = torch.load(os.path.join(HERE, "golden", "vae_fullsize_ref.pt"))
+    vae = fill_deterministic(AutoencoderKL().eval(), seed=1)
+    vae.load_state_dict({k: v.bfloat16().float() for k, v in vae.state_dict().items()})
+    g = torch.Generator().manual_seed(gold["seed"])
+    frames = torch.randn(1, 1, 3, 512, 512, generator=g).clamp(-1, 1).bfloat16().float()
+    lat = torch.randn(1, 4, 2, 64, 64, generator=g).bfloat16().float()
+    with torch.no_grad():
+        enc = oracle_encode_image(vae, frames)
+        vid = oracle_decode_latents(vae, lat[:, :, :1])
+    assert torch.allclose(enc, gold["enc_latents"], rtol=1e-5, atol=1e-6)
+    ref = gold["video_f16"][:, :, :1].float()
+    assert (vid - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()          # fixture stored in fp16
