@@ -21,7 +21,7 @@ IGEMM_PROFILE = None     # bench.py sets this to a list to time every implicit-G
 KERNEL_PROFILE = None    # same for the other kernels: list of {"name", "bytes" (algorithmic HBM bytes), "flops", "ev"}
 
 
-def _profiled(name, nbytes, flops, fn):
+def _profiled(name, nbytes, flops, fn, shape=None):
     """Run `fn` (one C-ABI call); when KERNEL_PROFILE is a list, bracket it with CUDA events on the launch stream."""
     if KERNEL_PROFILE is None:
         return fn()
@@ -30,7 +30,7 @@ def _profiled(name, nbytes, flops, fn):
     ev0.record()
     r = fn()
     ev1.record()
-    KERNEL_PROFILE.append({"name": name, "bytes": float(nbytes), "flops": float(flops), "ev": (ev0, ev1)})
+    KERNEL_PROFILE.append({"name": name, "bytes": float(nbytes), "flops": float(flops), "ev": (ev0, ev1), "shape": shape})
     return r
 
 
@@ -272,7 +272,7 @@ def flash_attn_d64(q: torch.Tensor, q_col0: int, kv: torch.Tensor, k_col0: int, 
               lambda: _lib.call("aab_flash_attn_d64", _ptr(q), q.stride(0), lq * q.stride(0), q.shape[1], q_col0,
                                 _ptr(kv), kv.stride(0), lk * kv.stride(0), kv.shape[1], k_col0, v_col0,
                                 _ptr(out), out.stride(0), lq * out.stride(0), 0, nb, nb_kv, kv_batch_div, heads, lq, lk,
-                                1.0 / math.sqrt(64.0), bf, _stream()))
+                                1.0 / math.sqrt(64.0), bf, _stream()), shape=(nb, heads, lq, lk))
     return out
 
 
@@ -282,7 +282,8 @@ def temporal_attn_d64(qkv: torch.Tensor, b: int, t: int, hw: int, heads: int, q_
     rows = qkv.shape[0]
     _profiled("temporal_attn_d64", 2.0 * rows * heads * 64 * 4, 4.0 * b * hw * heads * t * t * 64,
               lambda: _lib.call("aab_temporal_attn_d64", _ptr(qkv), qkv.stride(0), q_col0, k_col0, v_col0, _ptr(out),
-                                out.stride(0), b, t, hw, heads, 1.0 / math.sqrt(64.0), bf, _stream()))
+                                out.stride(0), b, t, hw, heads, 1.0 / math.sqrt(64.0), bf, _stream()),
+              shape=(b, t, hw, heads))
     return out
 
 
@@ -318,7 +319,7 @@ def groupnorm(x: torch.Tensor, samples: int, rows: int, gamma: torch.Tensor, bet
     _profiled("groupnorm", 2.0 * 2 * x.shape[0] * (c1 + c2), 0.0,
               lambda: _lib.call("aab_groupnorm", _ptr(x), x.stride(0), c1, _ptr(x2), 0 if x2 is None else x2.stride(0), c2,
                                 samples, rows, groups, _ptr(gamma), _ptr(beta), eps, int(silu), _ptr(y), y.stride(0),
-                                _ptr(ws), bf, _stream()))
+                                _ptr(ws), bf, _stream()), shape=(samples, rows, c1 + c2, int(silu)))
     return y
 
 
@@ -327,7 +328,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     y = torch.empty_like(x)
     _profiled("layernorm", 2.0 * 2 * x.shape[0] * x.shape[1], 0.0,
               lambda: _lib.call("aab_layernorm", _ptr(x), x.stride(0), _ptr(y), y.stride(0), _ptr(gamma), _ptr(beta),
-                                x.shape[0], x.shape[1], eps, bf, _stream()))
+                                x.shape[0], x.shape[1], eps, bf, _stream()), shape=tuple(x.shape))
     return y
 
 

@@ -264,3 +264,53 @@ def fill_deterministic(model: nn.Module, seed: int = 0, scale: float = 0.05):
         new[k] = t.to(v.dtype)
     model.load_state_dict(new)
     return model
+
+
+# ---------------------------------------------------------------------------------------------- SVD path (config 4)
+from diffusers._svd import (AutoencoderKLTemporalDecoder, EulerDiscreteScheduler,  # noqa: E402,F401
+                            UNetSpatioTemporalConditionModel)
+
+SVD_SCHED = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", prediction_type="v_prediction",
+                 interpolation_type="linear", use_karras_sigmas=True, sigma_min=0.002, sigma_max=700.0,
+                 timestep_spacing="leading", timestep_type="continuous", steps_offset=1)
+
+
+@torch.no_grad()
+def oracle_svd_sampling_loop(unet, scheduler, vae, image_embeddings, image_latents, mask, latents, num_inference_steps=25,
+                             min_guidance_scale=1.0, max_guidance_scale=3.0, fps=6, motion_bucket_id=127,
+                             noise_aug_strength=0.02, decode_chunk_size=None, decode=True):
+    """Restates the loop of MaskStableVideoDiffusionPipeline.__call__ (models/pipeline.py:375-459) from the point where the
+    image has been encoded: `image_embeddings` [B, 1, D] (CLIP image embedding, positive half), `image_latents` [B, 4, h, w]
+    (`vae.encode(image + noise).latent_dist.mode()`, NOT scaled), `mask` [1, h, w], `latents` [B, F, 4, h, w] unit
+    noise.  Classifier-free guidance with zeroed negative conditioning (:343,_encode_vae_image), per-frame guidance
+    scale linspace(min, max, F) (:405-408), 9-channel input cat([mask, latents, image_latents], dim=2) (:422), Euler
+    step (:439), chunked temporal-VAE decode (:456).  Returns (frames [B, 3, F, H, W] fp32 or None, latents)."""
+    b, nf = latents.shape[:2]
+    cfg = max_guidance_scale > 1.0
+    emb = torch.cat([torch.zeros_like(image_embeddings), image_embeddings]) if cfg else image_embeddings
+    il = torch.cat([torch.zeros_like(image_latents), image_latents]) if cfg else image_latents
+    il = il.unsqueeze(1).repeat(1, nf, 1, 1, 1)
+    m = mask[None, None].repeat(2, nf, 1, 1, 1).reshape(2, nf, 1, *mask.shape[-2:])      # '1 h w -> 2 f 1 h w'
+    ids = torch.tensor([[fps, motion_bucket_id, noise_aug_strength]], dtype=emb.dtype).repeat(b, 1)
+    ids = (torch.cat([ids, ids]) if cfg else ids).to(latents.device)
+    scheduler.set_timesteps(num_inference_steps, device=latents.device)
+    latents = latents * scheduler.init_noise_sigma
+    gs = torch.linspace(min_guidance_scale, max_guidance_scale, nf).unsqueeze(0).to(latents.device, latents.dtype)
+    gs = gs.repeat(b, 1)[:, :, None, None, None]
+    for t in scheduler.timesteps:
+        x = torch.cat([latents] * 2) if cfg else latents
+        x = scheduler.scale_model_input(x, t)
+        x = torch.cat([m.to(x.dtype), x, il], dim=2)
+        pred = unet(x, t, encoder_hidden_states=emb, added_time_ids=ids, return_dict=False)[0]
+        if cfg:
+            pu, pc = pred.chunk(2)
+            pred = pu + gs * (pc - pu)
+        latents = scheduler.step(pred, t, latents).prev_sample
+    if not decode:
+        return None, latents
+    chunk = decode_chunk_size or nf
+    z = latents.flatten(0, 1) / vae.config.scaling_factor
+    frames = torch.cat([vae.decode(z[i: i + chunk], num_frames=z[i: i + chunk].shape[0]).sample
+                        for i in range(0, z.shape[0], chunk)], dim=0)
+    frames = frames.reshape(-1, nf, *frames.shape[1:]).permute(0, 2, 1, 3, 4).float()
+    return frames, latents

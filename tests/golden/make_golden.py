@@ -82,6 +82,7 @@ def main():
     common_golden(diffusers)
     product_shape_goldens()
     oddsize_unet_golden()
+    svd_goldens()
 
 
 SMALL = dict(sample_size=16, block_out_channels=(64, 128, 256, 256), attention_head_dim=64, cross_attention_dim=128,
@@ -240,8 +241,54 @@ def oddsize_unet_golden():
     print("unet_small_oddsize_ref.pt", tuple(out.shape), float(out.abs().mean()))
 
 
+SVD_TINY = dict(in_channels=9, block_out_channels=(64, 128, 128, 128), num_attention_heads=(1, 2, 2, 2),
+                cross_attention_dim=64, addition_time_embed_dim=32, projection_class_embeddings_input_dim=96, num_frames=5,
+                sample_size=8)
+SVD_TINY_VAE = dict(block_out_channels=(32, 32, 64, 64), layers_per_block=1)
+
+
+class SvdImageEncoderStub(torch.nn.Module):
+    """Stand-in for the CLIP vision tower of the SVD pipeline (outside the hot path): mean colour -> Linear(3, D)."""
+
+    def __init__(self, dim=64):
+        super().__init__()
+        self.p = torch.nn.Linear(3, dim)
+
+    def forward(self, x):
+        return self.p(x.mean(dim=(2, 3)))
+
+
+def svd_goldens():
+    """config 4 (SVD path): the VERBATIM `MaskStableVideoDiffusionPipeline.__call__` (models/pipeline.py:223-466) on tiny
+    random-init models over the SVD shim (oracle/shim/diffusers/_svd.py: leaf level restated from memory, unpinned), plus
+    one UNetSpatioTemporalConditionModel forward at a head-dim-64 small config for the sm_100a parity test."""
+    import diffusers
+    from models.pipeline import MaskStableVideoDiffusionPipeline                 # verbatim reference
+    from oracle.composition import SVD_SCHED
+    unet = fill_deterministic(diffusers.UNetSpatioTemporalConditionModel(**SVD_TINY).eval(), 0)
+    vae = fill_deterministic(diffusers.AutoencoderKLTemporalDecoder(**SVD_TINY_VAE).eval(), 1)
+    enc = fill_deterministic(SvdImageEncoderStub().eval(), 2)
+    sched = diffusers.EulerDiscreteScheduler(**SVD_SCHED)
+    pipe = MaskStableVideoDiffusionPipeline(vae=vae, image_encoder=enc, unet=unet, scheduler=sched)
+    g = torch.Generator().manual_seed(0)
+    img = torch.randn(1, 3, 64, 128, generator=g).clamp(-1, 1)
+    mask = (torch.rand(1, 8, 16, generator=g) > 0.5).float()
+    lat0 = torch.randn(1, 5, 4, 8, 16, generator=g)
+    kw = dict(height=64, width=128, num_frames=5, num_inference_steps=3, decode_chunk_size=3, noise_aug_strength=0.0,
+              latents=lat0, mask=mask, return_dict=False)
+    frames = pipe(img, output_type="pt", **kw)
+    lat = pipe(img, output_type="latent", **kw)
+    torch.save({"unet_config": SVD_TINY, "vae_config": SVD_TINY_VAE, "image": img, "mask": mask, "latents_in": lat0,
+                "frames": torch.stack(frames), "latents": lat, "timesteps": sched.timesteps.clone(),
+                "sigmas": sched.sigmas.clone(), "n_unet_keys": len(unet.state_dict())},
+               os.path.join(HERE, "svd_pipeline_tiny_ref.pt"))
+    print("svd_pipeline_tiny_ref.pt", tuple(frames[0].shape), tuple(lat.shape), float(lat.abs().mean()))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "oddsize":
+    if len(sys.argv) > 1 and sys.argv[1] == "svd":
+        svd_goldens()
+    elif len(sys.argv) > 1 and sys.argv[1] == "oddsize":
         import diffusers  # noqa: F401  (the shim)
         oddsize_unet_golden()
     elif len(sys.argv) > 1 and sys.argv[1] == "benchmarked":

@@ -149,3 +149,29 @@ def test_oracle_vae_matches_reference_entry_points_full_size():
     assert torch.allclose(enc, gold["enc_latents"], rtol=1e-5, atol=1e-6)
     ref = gold["video_f16"][:, :, :1].float()
     assert (vid - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()          # fixture stored in fp16
+
+
+def test_svd_loop_matches_reference_pipeline():
+    """config 4: `oracle_svd_sampling_loop` vs the verbatim MaskStableVideoDiffusionPipeline.__call__ fixture
+    (models/pipeline.py:223-466: CFG with zeroed negatives, per-frame guidance vector, 9-channel input, Euler steps,
+    chunked temporal-VAE decode)."""
+    from make_golden import SvdImageEncoderStub
+    from oracle.composition import (AutoencoderKLTemporalDecoder, EulerDiscreteScheduler, SVD_SCHED,
+                                    UNetSpatioTemporalConditionModel, oracle_svd_sampling_loop)
+    gold = torch.load(os.path.join(HERE, "golden", "svd_pipeline_tiny_ref.pt"))
+    unet = fill_deterministic(UNetSpatioTemporalConditionModel(**gold["unet_config"]).eval(), 0)
+    assert len(unet.state_dict()) == gold["n_unet_keys"]
+    vae = fill_deterministic(AutoencoderKLTemporalDecoder(**gold["vae_config"]).eval(), 1)
+    enc = fill_deterministic(SvdImageEncoderStub().eval(), 2)
+    sched = EulerDiscreteScheduler(**SVD_SCHED)
+    with torch.no_grad():
+        emb = enc(gold["image"]).unsqueeze(1)
+        il = vae.encode(gold["image"]).latent_dist.mode()
+    frames, lat = oracle_svd_sampling_loop(unet, sched, vae, emb, il, gold["mask"], gold["latents_in"],
+                                           num_inference_steps=3, noise_aug_strength=0.0, decode_chunk_size=3)
+    assert torch.allclose(sched.timesteps, gold["timesteps"]) and torch.allclose(sched.sigmas, gold["sigmas"])
+    assert torch.allclose(lat, gold["latents"], rtol=1e-5, atol=1e-5), float((lat - gold["latents"]).abs().max())
+    # reference returns tensor2vid(frames): (x / 2 + 0.5).clamp(0, 1) per batch item, [F, 3, H, W]
+    want = gold["frames"][0]
+    got = (frames[0].permute(1, 0, 2, 3) / 2 + 0.5).clamp(0, 1)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-5), float((got - want).abs().max())

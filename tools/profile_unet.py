@@ -37,6 +37,29 @@ if mode == "ncu":
     fwd()
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
+elif mode == "kernels":
+    # per-shape CUDA-event timing of the non-GEMM kernels of one forward (algorithmic bytes -> GB/s, flops -> TFLOP/s)
+    ops.KERNEL_PROFILE = []
+    fwd()
+    torch.cuda.synchronize()
+    kp = ops.KERNEL_PROFILE
+    ops.KERNEL_PROFILE = None
+    agg = {}
+    for p in kp:
+        key = (p["name"], p["shape"])
+        a = agg.setdefault(key, {"n": 0, "ms": 0.0, "bytes": 0.0, "flops": 0.0})
+        a["n"] += 1
+        a["ms"] += p["ev"][0].elapsed_time(p["ev"][1])
+        a["bytes"] += p["bytes"]
+        a["flops"] += p["flops"]
+    print("| kernel | shape | launches | ms total | us / launch | algorithmic GB/s | TFLOP/s |")
+    print("|---|---|---|---|---|---|---|")
+    tot = {}
+    for (name, shape), a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        tot[name] = tot.get(name, 0.0) + a["ms"]
+        print(f"| {name} | {shape} | {a['n']} | {a['ms']:.3f} | {1e3 * a['ms'] / a['n']:.1f} | "
+              f"{a['bytes'] / a['ms'] / 1e6:.0f} | {a['flops'] / a['ms'] / 1e9:.0f} |")
+    print("totals (ms):", {k: round(v, 3) for k, v in tot.items()})
 elif mode == "vae_time":
     lat = inp["latents"]
     for _ in range(2):
