@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("AAB_LIB_PATH") or os.path.join(_HERE, "libaab200.so")
 
 MAX_TAPS = 9
 ACT_NONE, ACT_SILU, ACT_GELU, ACT_QUICK_GELU = 0, 1, 2, 3
-F_BF16, F_DIRECT, F_OUT_F32, F_GEGLU = 1, 2, 4, 8
+F_BF16, F_DIRECT, F_OUT_F32, F_GEGLU, F_SCALE_ACC = 1, 2, 4, 8, 16
 
 
 class IgemmDesc(C.Structure):
@@ -62,6 +62,12 @@ _SIGS = {
     "aab_timestep_embed": [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p],
     "aab_embed_tokens": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int,
                          C.c_void_p],
+    "aab_image_to_nhwc16": [C.c_void_p, C.c_long, C.c_long, C.c_long, C.c_long, C.c_void_p, C.c_long, C.c_int, C.c_int,
+                            C.c_int, C.c_int, C.c_void_p],
+    "aab_add_rowvec": [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_long, C.c_int, C.c_long, C.c_int,
+                       C.c_int, C.c_int, C.c_int, C.c_void_p],
+    "aab_axpby": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_float, C.c_float, C.c_int, C.c_void_p],
+    "aab_svd_out_finalize": [C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p],
     "aab_geglu": [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_long, C.c_int, C.c_int, C.c_void_p],
     "aab_upsample2x": [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p],
     "aab_upsample_nearest": [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],

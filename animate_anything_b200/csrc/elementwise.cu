@@ -291,6 +291,103 @@ __global__ void image_to_nhwc8_kernel(const void* __restrict__ img, long sn, lon
       make_uint4(pack2(v[0], v[1], BF16), pack2(v[2], v[3], BF16), pack2(v[4], v[5], BF16), pack2(v[6], v[7], BF16));
 }
 
+// SVD UNet input (models/pipeline.py:422 cat([mask, latents, image_latents], dim=2) -> conv_in of
+// UNetSpatioTemporalConditionModel): x [N, C, H, W] (strided, 16-bit, C <= 16) -> channels-last [N, H, W, 16] zero padded
+template <bool BF16>
+__global__ void image_to_nhwc16_kernel(const void* __restrict__ img, long sn, long sc, long sy, long sx,
+                                       void* __restrict__ out, long N, int C, int H, int W) {
+  const long total = N * H * W * 2;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int half = i & 1;
+  long r = i >> 1;
+  const int x = r % W;
+  r /= W;
+  const int y = r % H;
+  const long nn = r / H;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = half * 8 + j;
+    v[j] = (c < C) ? load_elem(img, nn * sn + c * sc + y * sy + x * sx, BF16) : 0.f;
+  }
+  reinterpret_cast<uint4*>(out)[i] =
+      make_uint4(pack2(v[0], v[1], BF16), pack2(v[2], v[3], BF16), pack2(v[4], v[5], BF16), pack2(v[6], v[7], BF16));
+}
+
+// out[r, :] = x[r, :] + vec[idx(r), :]   (out may alias x; 16-bit x / out, fp32 vec rows of `cols` values)
+//   mode 0: idx = (r / rows_per_vec) % mod   -- per-sample / per-frame vectors: the single-key cross-attention of the SVD
+//           transformer blocks (one image embedding per sample => softmax over ONE key is 1, the attention output is
+//           to_out(to_v(context)) for every token) and the frame position embedding of TransformerSpatioTemporalModel
+//   mode 1: rows are (b, f, s) with S = rows_per_vec, F = mod2; idx = (b * S + s) % mod -- the (h*w, batch)-ordered
+//           `time_context` of diffusers' TransformerSpatioTemporalModel.forward read by (batch, h*w)-ordered tokens
+template <bool BF16>
+__global__ void add_rowvec_kernel(const void* x, long ldx, void* out, long ldo, const float* __restrict__ vec, long ldv, long rows,
+                                  int cols, long rows_per_vec, int mod, int mode, int mod2) {
+  const int V = cols >> 3;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * V) return;
+  const long r = i / V;
+  const int c = static_cast<int>(i % V) * 8;
+  long idx;
+  if (mode == 0) {
+    idx = (r / rows_per_vec) % mod;
+  } else {
+    const long s = r % rows_per_vec;
+    const long b = r / (rows_per_vec * mod2);
+    idx = (b * rows_per_vec + s) % mod;
+  }
+  const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(x) + (r * ldx + c) * 2);
+  uint4* px = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out) + (r * ldo + c) * 2);
+  const float4 a = __ldg(reinterpret_cast<const float4*>(vec + idx * ldv + c));
+  const float4 b4 = __ldg(reinterpret_cast<const float4*>(vec + idx * ldv + c) + 1);
+  const float add[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = unpack2(w[e], BF16);
+    o[e] = pack2(f.x + add[2 * e], f.y + add[2 * e + 1], BF16);
+  }
+  *px = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// out = a * x + b * y with torch's 16-bit roundings of each product and of the sum (diffusers AlphaBlender.forward:
+// `alpha * x_spatial + (1 - alpha) * x_temporal`)
+template <bool BF16>
+__global__ void axpby_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, uint4* __restrict__ out, long n16,
+                             float a, float b) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n16) return;
+  const uint4 ux = __ldg(x + i), uy = __ldg(y + i);
+  const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w};
+  const uint32_t wy[4] = {uy.x, uy.y, uy.z, uy.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 fx = unpack2(wx[e], BF16);
+    const float2 fy = unpack2(wy[e], BF16);
+    o[e] = pack2(round16(a * fx.x, BF16) + round16(b * fy.x, BF16), round16(a * fx.y, BF16) + round16(b * fy.y, BF16), BF16);
+  }
+  out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// conv_out result [B*F*H*W, ldc] fp32 (4 valid channels) -> [B, F, 4, H, W] 16-bit
+// (UNetSpatioTemporalConditionModel.forward tail: sample.reshape(batch, frames, C, H, W))
+template <bool BF16>
+__global__ void svd_out_finalize_kernel(const float* __restrict__ y, int ldc, void* __restrict__ out, long BF, int H, int W) {
+  const long total = BF * 4 * H * W;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = i % W;
+  long r = i / W;
+  const int yy = r % H;
+  r /= H;
+  const int c = r % 4;
+  const long n = r / 4;
+  store_elem(out, i, y[((n * H + yy) * W + x) * ldc + c], BF16);
+}
+
 // encoder tail: conv_out result [N, h, w, ldm] (8 ch) -> quant_conv (1x1, 8->8) -> moments [N, 8, h, w] (NCHW, 16-bit)
 // (AutoencoderKL.encode: `moments = self.quant_conv(h)`; DiagonalGaussianDistribution.mode() is channels 0..3)
 template <bool BF16>
@@ -573,6 +670,56 @@ extern "C" int aab_image_to_nhwc8(const void* img, long sn, long sc, long sy, lo
   const long total = n * h * w;
   if (is_bf16) image_to_nhwc8_kernel<true><<<AAB_GRID(total, 256), 256, 0, stream>>>(img, sn, sc, sy, sx, out, n, c, h, w);
   else image_to_nhwc8_kernel<false><<<AAB_GRID(total, 256), 256, 0, stream>>>(img, sn, sc, sy, sx, out, n, c, h, w);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_image_to_nhwc16(const void* img, long sn, long sc, long sy, long sx, void* out, long n, int c, int h, int w,
+                                   int is_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!img || !out || c > 16 || c < 1) return AAB_ERR_ARG;
+  const long total = n * h * w * 2;
+  if (is_bf16) image_to_nhwc16_kernel<true><<<AAB_GRID(total, 256), 256, 0, stream>>>(img, sn, sc, sy, sx, out, n, c, h, w);
+  else image_to_nhwc16_kernel<false><<<AAB_GRID(total, 256), 256, 0, stream>>>(img, sn, sc, sy, sx, out, n, c, h, w);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_add_rowvec(const void* x, long ldx, void* out, long ldo, const float* vec, long ldv, long rows, int cols,
+                              long rows_per_vec, int mod, int mode, int mod2, int is_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !out || !vec || (cols % 8) || (ldx % 8) || (ldo % 8) || (ldv % 4) || rows_per_vec < 1 || mod < 1 ||
+      (mode == 1 && mod2 < 1))
+    return AAB_ERR_ARG;
+  const long total = rows * (cols / 8);
+  if (is_bf16)
+    add_rowvec_kernel<true><<<AAB_GRID(total, 256), 256, 0, stream>>>(x, ldx, out, ldo, vec, ldv, rows, cols, rows_per_vec, mod,
+                                                                     mode, mod2);
+  else
+    add_rowvec_kernel<false><<<AAB_GRID(total, 256), 256, 0, stream>>>(x, ldx, out, ldo, vec, ldv, rows, cols, rows_per_vec, mod,
+                                                                      mode, mod2);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_axpby(const void* x, const void* y, void* out, long n_elems, float a, float b, int is_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !y || !out || (n_elems % 8)) return AAB_ERR_ARG;
+  const long n16 = n_elems / 8;
+  if (is_bf16)
+    axpby_kernel<true><<<AAB_GRID(n16, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x),
+                                                                 reinterpret_cast<const uint4*>(y),
+                                                                 reinterpret_cast<uint4*>(out), n16, a, b);
+  else
+    axpby_kernel<false><<<AAB_GRID(n16, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x),
+                                                                  reinterpret_cast<const uint4*>(y),
+                                                                  reinterpret_cast<uint4*>(out), n16, a, b);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_svd_out_finalize(const float* y, int ldc, void* out, long bf, int h, int w, int is_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!y || !out || ldc < 4) return AAB_ERR_ARG;
+  const long total = bf * 4 * h * w;
+  if (is_bf16) svd_out_finalize_kernel<true><<<AAB_GRID(total, 256), 256, 0, stream>>>(y, ldc, out, bf, h, w);
+  else svd_out_finalize_kernel<false><<<AAB_GRID(total, 256), 256, 0, stream>>>(y, ldc, out, bf, h, w);
   AAB_LAUNCH_RET();
 }
 

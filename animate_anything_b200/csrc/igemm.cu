@@ -470,8 +470,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               float x = v[j];
               if (p.bias != nullptr) x += __ldg(p.bias + col + j);
               if (bias2row != nullptr) x += __ldg(bias2row + col + j);
-              if (resrow != nullptr) x += load_elem(resrow, col + j, bf16);
-              x = apply_act(x, p.act) * p.out_scale;
+              if (p.flags & AAB_F_SCALE_ACC) {
+                x = apply_act(x, p.act) * p.out_scale;
+                if (resrow != nullptr) x += load_elem(resrow, col + j, bf16);
+              } else {
+                if (resrow != nullptr) x += load_elem(resrow, col + j, bf16);
+                x = apply_act(x, p.act) * p.out_scale;
+              }
               if (rvalid) {
                 if (p.flags & AAB_F_OUT_F32) reinterpret_cast<float*>(p.out)[grow * p.ld_out + col + j] = x;
                 else store_elem(p.out, grow * p.ld_out + col + j, x, bf16);
@@ -596,6 +601,7 @@ extern "C" int aab_igemm(const AabIgemmDesc* d, void* stream_) {
   if (bn == 32 || (d->ld_out % 8) != 0 || (n_out % 32) != 0 || (d->flags & AAB_F_OUT_F32)) direct = true;
   if (geglu && (bn < 128 || direct)) return AAB_ERR_ARG;   // output tile must cover whole 64-column store boxes
   if (d->residual && (d->ld_res % 8) != 0 && !direct) direct = true;
+  if (d->flags & AAB_F_SCALE_ACC) direct = true;
   if ((d->act == AAB_ACT_GELU || d->act == AAB_ACT_QUICK_GELU) && !geglu) direct = true;
   {   // the staged variants cover one extra term each (residual | per-sample bias | SiLU) and no output scaling
     const int extras = (d->residual ? 1 : 0) + (d->bias2 ? 1 : 0) + (d->act == AAB_ACT_SILU ? 1 : 0);

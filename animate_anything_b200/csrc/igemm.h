@@ -16,6 +16,7 @@
 #define AAB_F_DBG_NO_PEEK 4096 /* diagnostics only: blocking full-barrier wait before every k-block (the pre-peek issue loop) */
 #define AAB_F_DBG_NO_SYNC 256 /* diagnostics only: with NO_LOAD, the MMA warp neither waits for stages nor commits them -> raw tcgen05.mma issue rate */
 #define AAB_F_DBG_NO_LOAD 128 /* diagnostics only (wrong results): no TMA loads, stages are always full -> pure MMA + epilogue rate */
+#define AAB_F_SCALE_ACC 16 /* out = act(acc + bias + bias2) * out_scale + residual (scale BEFORE the residual; direct store only) */
 #define AAB_F_GEGLU 8     /* B rows [0,N/2) are values, [N/2,N) gates: out = value * gelu(gate), N/2 columns */
 
 #ifdef __cplusplus

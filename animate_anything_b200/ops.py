@@ -12,7 +12,8 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_NONE, ACT_QUICK_GELU, ACT_SILU, F_BF16, F_DIRECT, F_GEGLU, F_OUT_F32, IgemmDesc
+from ._lib import (ACT_GELU, ACT_NONE, ACT_QUICK_GELU, ACT_SILU, F_BF16, F_DIRECT, F_GEGLU, F_OUT_F32, F_SCALE_ACC,
+                   IgemmDesc)
 
 NUM_SMS = 148
 IGEMM_DEBUG = None       # optional uint64[16] device tensor: per-role wait-cycle counters (tools/igemm_roles.py)
@@ -102,7 +103,7 @@ def igemm(a: torch.Tensor, a_dims, a_strides, w: torch.Tensor, n: int, kc: int, 
           out: Optional[torch.Tensor] = None, ld_out: Optional[int] = None, *, bias=None, bias2=None, rows_per_bias2=1,
           residual=None, ld_res=None, act=ACT_NONE, out_scale=1.0, geglu=False, out_f32=False, a2=None, a2_dims=None,
           a2_strides=None, kc1=0, ld_b=None, b_batch=0, b_batch_stride=0, b_batch_dim=-1, block_n=None, direct=False,
-          max_ctas=0, out_rows=None):
+          max_ctas=0, out_rows=None, scale_acc=False):
     """Generic launch of the implicit-GEMM kernel. `taps` is a list of 5-int offsets (channel, pix0..pix3)."""
     bf = _is_bf16(a)
     n_out = n // 2 if geglu else n
@@ -165,7 +166,8 @@ def igemm(a: torch.Tensor, a_dims, a_strides, w: torch.Tensor, n: int, kc: int, 
         d.residual = None
     d.out_scale = out_scale
     d.act = act
-    flags = (F_BF16 if bf else 0) | (F_GEGLU if geglu else 0) | (F_OUT_F32 if out_f32 else 0) | (F_DIRECT if direct else 0)
+    flags = ((F_BF16 if bf else 0) | (F_GEGLU if geglu else 0) | (F_OUT_F32 if out_f32 else 0) | (F_DIRECT if direct else 0) |
+             (F_SCALE_ACC if scale_acc else 0))
     d.flags = flags | IGEMM_DBG_FLAGS
     if block_n is None:
         if n_out < 64 and not geglu:
@@ -441,6 +443,40 @@ def image_to_nhwc8(img: torch.Tensor) -> torch.Tensor:
     out = torch.empty((n, h, w, 8), device=img.device, dtype=img.dtype)
     _lib.call("aab_image_to_nhwc8", _ptr(img), img.stride(0), img.stride(1), img.stride(2), img.stride(3), _ptr(out), n, c,
               h, w, _is_bf16(img), _stream())
+    return out
+
+
+def image_to_nhwc16(img: torch.Tensor) -> torch.Tensor:
+    """[N, C<=16, H, W] (any strides) -> channels-last [N, H, W, 16], zero padded."""
+    n, c, h, w = img.shape
+    out = torch.empty((n, h, w, 16), device=img.device, dtype=img.dtype)
+    _lib.call("aab_image_to_nhwc16", _ptr(img), img.stride(0), img.stride(1), img.stride(2), img.stride(3), _ptr(out), n, c,
+              h, w, _is_bf16(img), _stream())
+    return out
+
+
+def add_rowvec(x: torch.Tensor, vec: torch.Tensor, rows_per_vec: int, mod: int, mode: int = 0, mod2: int = 1,
+               inplace: bool = False) -> torch.Tensor:
+    """x[r] + vec[idx(r)] (fp32 vec rows).  mode 0: idx = (r // rows_per_vec) % mod; mode 1 (rows (b, f, s),
+    S = rows_per_vec, F = mod2): idx = (b * S + s) % mod."""
+    assert vec.dtype == torch.float32 and vec.stride(-1) == 1
+    out = x if inplace else torch.empty((x.shape[0], x.shape[1]), device=x.device, dtype=x.dtype)
+    _lib.call("aab_add_rowvec", _ptr(x), x.stride(0), _ptr(out), out.stride(0), _ptr(vec), vec.stride(0), x.shape[0],
+              x.shape[1], rows_per_vec, mod, mode, mod2, _is_bf16(x), _stream())
+    return out
+
+
+def axpby(x: torch.Tensor, y: torch.Tensor, a: float, b: float) -> torch.Tensor:
+    assert x.is_contiguous() and y.is_contiguous() and x.shape == y.shape
+    out = torch.empty_like(x)
+    _lib.call("aab_axpby", _ptr(x), _ptr(y), _ptr(out), x.numel(), float(a), float(b), _is_bf16(x), _stream())
+    return out
+
+
+def svd_out_finalize(y: torch.Tensor, b: int, f: int, h: int, w: int, dtype) -> torch.Tensor:
+    out = torch.empty((b, f, 4, h, w), device=y.device, dtype=dtype)
+    _lib.call("aab_svd_out_finalize", _ptr(y), y.stride(0), _ptr(out), b * f, h, w, 1 if dtype == torch.bfloat16 else 0,
+              _stream())
     return out
 
 

@@ -517,8 +517,20 @@ def run_product(args):
             line["latency"] = lat_info
         print(json.dumps(line), flush=True)
     if world > 1:
+        # orderly shutdown: captured graphs hold NCCL kernels of the pair communicators -- drop them before the process
+        # group goes away; a watchdog ends the process if the teardown still blocks (the result line is already out)
+        import gc
         dist.barrier()
+        torch.cuda.synchronize()
+        pipe.__dict__.pop("_gstate", None)
+        gc.collect()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        wd = threading.Timer(20.0, lambda: os._exit(0))
+        wd.daemon = True
+        wd.start()
         dist.destroy_process_group()
+        wd.cancel()
 
 
 def latency_breakdown(pipe, runner, devin, dev, rank, world, lat_split, frames_split, kw, clip_s):

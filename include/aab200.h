@@ -76,6 +76,18 @@ int aab_timestep_embed(const float* t, int t_count, void* out, int b, int dim, i
 int aab_embed_tokens(const long long* ids, const void* tok_emb, const void* pos_emb, void* out, long rows, int seq_len,
                      int c, int vocab, int is_bf16, void* stream);
 
+/* SVD path (config 4; models/pipeline.py:223-466 driving diffusers' UNetSpatioTemporalConditionModel):
+ * 9-channel UNet input [N, C<=16, H, W] -> channels-last padded to 16 (:422 cat([mask, latents, image_latents], dim=2));
+ * out[r] = x[r] + vec[idx(r)], out may alias x (single-key cross-attention = per-sample vector; frame position embedding; mode 1 = the
+ * (h*w, batch)-ordered time_context quirk of TransformerSpatioTemporalModel.forward);
+ * AlphaBlender a*x + b*y with torch's 16-bit roundings; conv_out -> [B, F, 4, H, W]. */
+int aab_image_to_nhwc16(const void* img, long sn, long sc, long sy, long sx, void* out, long n, int c, int h, int w,
+                        int is_bf16, void* stream);
+int aab_add_rowvec(const void* x, long ldx, void* out, long ldo, const float* vec, long ldv, long rows, int cols,
+                   long rows_per_vec, int mod, int mode, int mod2, int is_bf16, void* stream);
+int aab_axpby(const void* x, const void* y, void* out, long n_elems, float a, float b, int is_bf16, void* stream);
+int aab_svd_out_finalize(const float* y, int ldc, void* out, long bf, int h, int w, int is_bf16, void* stream);
+
 /* Unfused fallbacks / helpers: GEGLU gate (diffusers GEGLU.forward), nearest 2x upsample (Upsample2D), copies. */
 int aab_geglu(const void* x, long ldx, void* out, long ldo, long rows, int nh, int is_bf16, void* stream);
 int aab_upsample2x(const void* x, void* y, long n, int h, int w, int c, void* stream);
