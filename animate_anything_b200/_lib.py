@@ -74,7 +74,7 @@ _SIGS = {
     "aab_pad_br": [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
     "aab_copy2d": [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_long, C.c_int, C.c_void_p],
     "aab_dup_rows": [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p],
-    "aab_transpose": [C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p],
+    "aab_transpose": [C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
     "aab_cfg_scheduler_step": [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
     "aab_image_to_nhwc8": [C.c_void_p, C.c_long, C.c_long, C.c_long, C.c_long, C.c_void_p, C.c_long, C.c_int, C.c_int,
@@ -93,7 +93,7 @@ _SIGS = {
 EXPORTS = tuple(_SIGS.keys())
 
 _launch_count = 0
-_KERNELS_PER_CALL = {"aab_groupnorm": 2}     # stats + apply (plus a memset node)
+_KERNELS_PER_CALL = {}     # every C-ABI call launches exactly one kernel (GroupNorm is one fused cooperative kernel since round 2)
 
 
 def load():

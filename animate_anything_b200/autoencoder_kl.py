@@ -190,18 +190,17 @@ class AutoencoderKL(ModelBase):
         p = ctx.prep.get(attn)
         c = attn.inner_dim
         n, l = g.n, g.hw
-        if l % 8:
-            raise NotImplementedError("VAE attention needs H*W % 8 == 0")
+        lp = (l + 7) // 8 * 8            # K of the P.V GEMM padded with zero probabilities / zero V columns when H*W % 8 != 0
         hn = ops.groupnorm(x, n, l, p["gn"][0], p["gn"][1], 1e-6, False, 32)
         qkv = ops.linear(hn, p["qkv"], p["qkv_b"])                       # [n*l, 3c]
         q, k = qkv[:, :c], qkv[:, c:2 * c]
         s = ops.igemm(q, (c, l, n, 1, 1), (1, 3 * c, l * 3 * c, 0, 0), k, l, c, (l, n, 1, 1), (128, 1, 1, 1),
                       [[0, 0, 0, 0, 0]], ld_b=3 * c, b_batch=n, b_batch_stride=l * 3 * c, b_batch_dim=1, out_f32=True,
                       out_scale=1.0 / math.sqrt(c))
-        pr = ops.softmax_rows(s, x.dtype)                                 # [n*l, l]
-        vt = ops.transpose_batched(qkv, 2 * c, n, l, c)                   # [n, c, l]
-        o = ops.igemm(pr, (l, l, n, 1, 1), (1, l, l * l, 0, 0), vt, c, l, (l, n, 1, 1), (128, 1, 1, 1),
-                      [[0, 0, 0, 0, 0]], ld_b=l, b_batch=n, b_batch_stride=c * l, b_batch_dim=1)
+        pr = ops.softmax_rows(s, x.dtype, pad_to=lp)                      # [n*l, lp]
+        vt = ops.transpose_batched(qkv, 2 * c, n, l, c, ld=lp)            # [n, c, lp]
+        o = ops.igemm(pr, (lp, l, n, 1, 1), (1, lp, l * lp, 0, 0), vt, c, lp, (l, n, 1, 1), (128, 1, 1, 1),
+                      [[0, 0, 0, 0, 0]], ld_b=lp, b_batch=n, b_batch_stride=c * lp, b_batch_dim=1)
         return ops.linear(o, p["o"][0], p["o"][1], residual=x, out_scale=1.0 / attn.rescale_output_factor)
 
     def _mid(self, ctx, mid: UNetMidBlock2D, x, g):

@@ -209,9 +209,10 @@ __global__ void dup_rows_kernel(const uint4* __restrict__ src, uint4* __restrict
   dst[i + n16] = v;
 }
 
-// batched transpose: src [nb][rows][lds] (cols used) -> dst [nb][cols][rows]
+// batched transpose: src [nb][rows][lds] (cols used) -> dst [nb][cols][ldd]; dst columns rows..ldd-1 are zero-filled
+// (ldd = rows rounded up to a multiple of 8 so that the result can be a TMA operand when rows % 8 != 0)
 __global__ void transpose_kernel(const uint16_t* __restrict__ src, long lds, long src_batch, uint16_t* __restrict__ dst,
-                                 int rows, int cols) {
+                                 int rows, int cols, int ldd) {
   __shared__ uint16_t tile[32][33];
   const int b = blockIdx.z;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -222,7 +223,7 @@ __global__ void transpose_kernel(const uint16_t* __restrict__ src, long lds, lon
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int c = c0 + j, r = r0 + threadIdx.x;
-    if (r < rows && c < cols) dst[(static_cast<long>(b) * cols + c) * rows + r] = tile[threadIdx.x][j];
+    if (r < ldd && c < cols) dst[(static_cast<long>(b) * cols + c) * ldd + r] = (r < rows) ? tile[threadIdx.x][j] : uint16_t(0);
   }
 }
 
@@ -639,12 +640,13 @@ extern "C" int aab_dup_rows(const void* src, void* dst, long bytes, void* stream
   AAB_LAUNCH_RET();
 }
 
-extern "C" int aab_transpose(const void* src, long lds, long src_batch, void* dst, int nb, int rows, int cols,
+extern "C" int aab_transpose(const void* src, long lds, long src_batch, void* dst, int nb, int rows, int cols, int ldd,
                              void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  dim3 grid((cols + 31) / 32, (rows + 31) / 32, nb);
+  if (!src || !dst || ldd < rows) return AAB_ERR_ARG;
+  dim3 grid((cols + 31) / 32, (ldd + 31) / 32, nb);
   transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(reinterpret_cast<const uint16_t*>(src), lds, src_batch,
-                                                     reinterpret_cast<uint16_t*>(dst), rows, cols);
+                                                     reinterpret_cast<uint16_t*>(dst), rows, cols, ldd);
   AAB_LAUNCH_RET();
 }
 

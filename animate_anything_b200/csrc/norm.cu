@@ -220,6 +220,240 @@ __global__ void gn_apply_kernel(GnArgs a, const float* __restrict__ mean_rstd, c
   }
 }
 
+// ------------------------------------------------------------------------------------------------ fused GroupNorm
+// ONE launch instead of two (statistics + apply).  Measured in round 2 (profiles/r02_kernels_by_shape.md): a GroupNorm call
+// on an 11 MB tensor took 21 us against 1.7 us of HBM time -- two launches, two tails, and the serial "last CTA reduces the
+// partials" step in between; 166 calls per UNet forward made that fixed cost ~3 ms.  Here a co-resident (cooperatively
+// launched) grid walks the same fixed row partition twice:
+//   phase 1: per-chunk (sum, sumsq) partials -> workspace; the last CTA of a SAMPLE (ticket) reduces that sample's partials in
+//            index order, publishes mean / rstd and raises the sample's flag (release);
+//   phase 2: every CTA waits for the flag of its chunk's sample (acquire; other samples keep streaming meanwhile) and
+//            normalises its chunk -- the re-read hits the 126 MB L2, only the write goes to HBM.
+// Bitwise reproducibility and batch invariance are unchanged: the partition depends on (rows, C) only, partials are
+// combined in fixed order, which CTA computed a partial does not matter.
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void gn_fused_kernel(GnArgs a, double* __restrict__ partial /* [S][chunks][G][2] */,
+                                float* __restrict__ mean_rstd /* [S][G][2] */, unsigned int* __restrict__ ticket /* [S] */,
+                                unsigned int* __restrict__ flag /* [S] */, unsigned int* __restrict__ done /* [S] */,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+                                void* __restrict__ y, long ldy, float eps, int chunks, int total_chunks) {
+  extern __shared__ float sh[];   // [rpi][C] sums, [rpi][C] squares (phase 1) / fp64 reduction scratch (finalize)
+  __shared__ bool is_last;
+  const int C = a.C1 + a.C2;
+  const int V = C >> 3;
+  const int oct = threadIdx.x % V;
+  const int rsub = threadIdx.x / V;
+  const int rpi = blockDim.x / V;
+  const bool bf = a.bf16 != 0;
+  const int c0 = oct * 8;
+  const int cpg = C / a.groups;
+  const uint8_t* base;
+  long ld;
+  int cc;
+  if (c0 < a.C1) { base = reinterpret_cast<const uint8_t*>(a.x1); ld = a.ld1; cc = c0; }
+  else { base = reinterpret_cast<const uint8_t*>(a.x2); ld = a.ld2; cc = c0 - a.C1; }
+  float* shs = sh;
+  float* shq = sh + rpi * C;
+
+  // ------------------------------------------------------------------ phase 1: statistics
+  for (int ch = blockIdx.x; ch < total_chunks; ch += gridDim.x) {
+    const int s = ch / chunks;
+    const int cix = ch - s * chunks;
+    const long r0 = static_cast<long>(cix) * a.rows_per_cta;
+    long r1 = r0 + a.rows_per_cta;
+    if (r1 > a.rows) r1 = a.rows;
+    float sum[8], sq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
+    for (long r = r0 + rsub; r < r1; r += 8 * rpi) {
+      uint4 u[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const long rk = r + static_cast<long>(k) * rpi;
+        u[k] = make_uint4(0, 0, 0, 0);
+        if (rk < r1) u[k] = ldg16(base + ((static_cast<long>(s) * a.rows + rk) * ld + cc) * 2);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack2(w[e], bf);
+          sum[2 * e] += f.x; sq[2 * e] += f.x * f.x;
+          sum[2 * e + 1] += f.y; sq[2 * e + 1] += f.y * f.y;
+        }
+      }
+    }
+    __syncthreads();                      // previous iteration's readers of sh are done
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      shs[rsub * C + c0 + j] = sum[j];
+      shq[rsub * C + c0 + j] = sq[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < a.groups) {
+      const int g = threadIdx.x;
+      float fs0 = 0.f, fs1 = 0.f, fq0 = 0.f, fq1 = 0.f;
+      for (int r = 0; r < rpi; ++r) {
+        int c = g * cpg;
+        for (; c + 1 < (g + 1) * cpg; c += 2) {
+          fs0 += shs[r * C + c];
+          fs1 += shs[r * C + c + 1];
+          fq0 += shq[r * C + c];
+          fq1 += shq[r * C + c + 1];
+        }
+        if (c < (g + 1) * cpg) {
+          fs0 += shs[r * C + c];
+          fq0 += shq[r * C + c];
+        }
+      }
+      double* pp = partial + ((static_cast<long>(s) * chunks + cix) * a.groups + g) * 2;
+      pp[0] = static_cast<double>(fs0) + static_cast<double>(fs1);
+      pp[1] = static_cast<double>(fq0) + static_cast<double>(fq1);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int t = atomicAdd(&ticket[s], 1u);
+      is_last = (t == static_cast<unsigned int>(chunks - 1));
+      if (is_last) ticket[s] = 0;          // self-reset for the next launch
+    }
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      const int P = blockDim.x / a.groups;                 // >= 1 (host guarantees blockDim >= groups)
+      double* red = reinterpret_cast<double*>(sh);
+      const int g = threadIdx.x % a.groups;
+      const int part = threadIdx.x / a.groups;
+      if (part < P) {
+        double ds[8], dq[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ds[k] = dq[k] = 0.0;
+        const double* pp = partial + (static_cast<long>(s) * chunks * a.groups + g) * 2;
+        for (int c1 = part; c1 < chunks; c1 += 8 * P) {
+          double2 v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int c2 = c1 + k * P;
+            v[k] = make_double2(0.0, 0.0);
+            if (c2 < chunks) v[k] = __ldcg(reinterpret_cast<const double2*>(pp + static_cast<long>(c2) * a.groups * 2));
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            ds[k] += v[k].x;
+            dq[k] += v[k].y;
+          }
+        }
+        red[(part * a.groups + g) * 2] = ((ds[0] + ds[1]) + (ds[2] + ds[3])) + ((ds[4] + ds[5]) + (ds[6] + ds[7]));
+        red[(part * a.groups + g) * 2 + 1] = ((dq[0] + dq[1]) + (dq[2] + dq[3])) + ((dq[4] + dq[5]) + (dq[6] + dq[7]));
+      }
+      __syncthreads();
+      if (threadIdx.x < a.groups) {
+        double ds = 0.0, dq = 0.0;
+        for (int q = 0; q < P; ++q) {
+          ds += red[(q * a.groups + g) * 2];
+          dq += red[(q * a.groups + g) * 2 + 1];
+        }
+        const double n = static_cast<double>(a.rows) * cpg;
+        const double m = ds / n;
+        double var = dq / n - m * m;
+        if (var < 0) var = 0;
+        mean_rstd[(static_cast<long>(s) * a.groups + g) * 2] = static_cast<float>(m);
+        mean_rstd[(static_cast<long>(s) * a.groups + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      }
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) st_release_u32(&flag[s], 1u);
+    }
+  }
+
+  // ------------------------------------------------------------------ phase 2: apply (+ SiLU)
+  float* sc_sh = sh;            // [C] scale, [C] shift of the current sample (recomputed when the sample changes)
+  float* sf_sh = sh + C;
+  int cur_s = -1;
+  for (int ch = blockIdx.x; ch < total_chunks; ch += gridDim.x) {
+    const int s = ch / chunks;
+    const int cix = ch - s * chunks;
+    if (s != cur_s) {
+      __syncthreads();                    // everyone is done with the previous sample's scale / shift (and with `red`)
+      if (threadIdx.x == 0) {
+        unsigned int spins = 0;
+        while (ld_acquire_u32(&flag[s]) == 0u) {
+          __nanosleep(32);
+          if (++spins > (1u << 26)) {
+            printf("aab: groupnorm flag timeout sample %d block %d\n", s, blockIdx.x);
+            __trap();
+          }
+        }
+      }
+      __syncthreads();
+      for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float m = __ldcg(&mean_rstd[(static_cast<long>(s) * a.groups + g) * 2]);
+        const float rstd = __ldcg(&mean_rstd[(static_cast<long>(s) * a.groups + g) * 2 + 1]);
+        const float gm = gamma[c];
+        sc_sh[c] = rstd * gm;
+        sf_sh[c] = beta[c] - m * rstd * gm;
+      }
+      __syncthreads();
+      cur_s = s;
+    }
+    float sc[8], sf[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = sc_sh[c0 + j];
+      sf[j] = sf_sh[c0 + j];
+    }
+    const long r0 = static_cast<long>(cix) * a.rows_per_cta;
+    long r1 = r0 + a.rows_per_cta;
+    if (r1 > a.rows) r1 = a.rows;
+    for (long r = r0 + rsub; r < r1; r += 4 * rpi) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long rk = r + static_cast<long>(k) * rpi;
+        u[k] = make_uint4(0, 0, 0, 0);
+        if (rk < r1) u[k] = ldg16(base + ((static_cast<long>(s) * a.rows + rk) * ld + cc) * 2);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long rk = r + static_cast<long>(k) * rpi;
+        if (rk >= r1) break;
+        const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack2(w[e], bf);
+          float v0 = fmaf(f.x, sc[2 * e], sf[2 * e]);
+          float v1 = fmaf(f.y, sc[2 * e + 1], sf[2 * e + 1]);
+          if (silu) { v0 = silu_fast_f(v0); v1 = silu_fast_f(v1); }
+          o[e] = pack2(v0, v1, bf);
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y) + ((static_cast<long>(s) * a.rows + rk) * ldy + c0) * 2) =
+            make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    // the last chunk of a sample to be applied lowers the flag again for the next launch (nobody can still wait on it:
+    // every chunk of the sample has passed its wait)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int d = atomicAdd(&done[s], 1u);
+      if (d == static_cast<unsigned int>(chunks - 1)) {
+        done[s] = 0;
+        flag[s] = 0;
+      }
+    }
+  }
+}
+
 // One warp handles R consecutive rows at a time (all loads of the R rows are issued before any reduction, so that
 // enough bytes are in flight per SM); OPL = 16-byte octets per lane = ceil(C/8/32).  C % 8 == 0, C <= 2048.
 template <int OPL, int R>
@@ -296,7 +530,7 @@ layernorm_kernel(const void* __restrict__ x, long ldx, void* __restrict__ y, lon
 }
 
 // row softmax: fp32 scores [rows][L] -> 16-bit probabilities (VAE mid-block attention, upcast_softmax semantics)
-__global__ void softmax_rows_kernel(const float* __restrict__ s, long lds, void* __restrict__ p, long ldp, int L,
+__global__ void softmax_rows_kernel(const float* __restrict__ s, long lds, void* __restrict__ p, long ldp, int L, int Lpad,
                                     int bf16) {
   __shared__ float red[32];
   const long row = blockIdx.x;
@@ -320,6 +554,8 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, long lds, void*
   for (int i = 0; i < (blockDim.x >> 5); ++i) sum += red[i];
   const float inv = 1.f / sum;
   for (int i = threadIdx.x; i < L; i += blockDim.x) store_elem(p, row * ldp + i, __expf(sr[i] - mx) * inv, bf16 != 0);
+  // columns L .. Lpad-1 (K padding of the following P.V GEMM when L % 8 != 0) are zero
+  for (int i = L + threadIdx.x; i < Lpad; i += blockDim.x) store_elem(p, row * ldp + i, 0.f, bf16 != 0);
 }
 
 }  // namespace aab
@@ -352,12 +588,12 @@ static int gn_launch_cfg(int C, long samples, long rows, int* threads, int* rows
   return AAB_OK;
 }
 
-// Workspace layout (bytes): [0, 4*samples) tickets (must be zero before the first use; self-resetting afterwards),
-// then mean/rstd floats [samples*groups*2], then double partials [samples*chunks*groups*2].
+// Workspace layout (bytes): [0, 12*samples) tickets | flags | done counters (must be zero before the first use; self-
+// resetting afterwards), then mean/rstd floats [samples*groups*2], then double partials [samples*chunks*groups*2].
 extern "C" long aab_groupnorm_workspace_bytes(long samples, long rows, int c, int groups) {
   int threads, rpc, chunks;
   if (gn_launch_cfg(c, samples, rows, &threads, &rpc, &chunks)) return -1;
-  long off = ((samples * 4 + 255) / 256) * 256;
+  long off = ((samples * 12 + 255) / 256) * 256;
   off += ((samples * groups * 2 * 4 + 255) / 256) * 256;
   off += samples * chunks * groups * 2 * 8;
   return off;
@@ -380,7 +616,9 @@ extern "C" int aab_groupnorm(const void* x1, long ld1, int c1, const void* x2, l
   a.rows_per_cta = rpc; a.bf16 = is_bf16;
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   unsigned int* ticket = reinterpret_cast<unsigned int*>(ws);
-  long off = ((samples * 4 + 255) / 256) * 256;
+  unsigned int* flag = ticket + samples;
+  unsigned int* done = flag + samples;
+  long off = ((samples * 12 + 255) / 256) * 256;
   float* mean_rstd = reinterpret_cast<float*>(ws + off);
   off += ((samples * groups * 2 * 4 + 255) / 256) * 256;
   double* partial = reinterpret_cast<double*>(ws + off);
@@ -389,10 +627,36 @@ extern "C" int aab_groupnorm(const void* x1, long ld1, int c1, const void* x2, l
   const size_t smem_red = static_cast<size_t>(threads / groups) * groups * 2 * sizeof(double);
   if (smem_red > smem) smem = smem_red;
   if (smem > 48 * 1024 || threads < groups) return AAB_ERR_ARG;
-  dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(samples));
-  gn_stats_kernel<<<grid, threads, smem, stream>>>(a, partial, mean_rstd, ticket, eps);
-  gn_apply_kernel<<<grid, threads, 0, stream>>>(a, mean_rstd, gamma, beta, silu, y, ldy);
-  return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
+  static int two_pass = -1;               // AAB_GN_TWO_PASS=1: the round-1 pair of kernels (A/B measurements)
+  if (two_pass < 0) {
+    const char* e = getenv("AAB_GN_TWO_PASS");
+    two_pass = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (two_pass) {
+    dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(samples));
+    gn_stats_kernel<<<grid, threads, smem, stream>>>(a, partial, mean_rstd, ticket, eps);
+    gn_apply_kernel<<<grid, threads, 0, stream>>>(a, mean_rstd, gamma, beta, silu, y, ldy);
+    return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
+  }
+  // fused kernel: the grid must be co-resident (CTAs of phase 2 wait for flags raised by other CTAs) -> cooperative launch,
+  // sized from the occupancy of this (threads, smem) configuration on the current device
+  size_t smem2 = static_cast<size_t>(2) * C * sizeof(float);      // phase-2 scale / shift
+  if (smem2 > smem) smem = smem2;
+  int dev = 0, sms = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return AAB_ERR_CUDA;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel, threads, smem) != cudaSuccess || per_sm < 1)
+    return AAB_ERR_CUDA;
+  if (per_sm > 8) per_sm = 8;
+  const long total_chunks = static_cast<long>(chunks) * samples;
+  long grid_l = static_cast<long>(per_sm) * sms;
+  if (grid_l > total_chunks) grid_l = total_chunks;
+  int chunks_i = chunks, total_i = static_cast<int>(total_chunks);
+  void* args[] = {&a, &partial, &mean_rstd, &ticket, &flag, &done, const_cast<float**>(&gamma), const_cast<float**>(&beta),
+                  &silu, &y, &ldy, &eps, &chunks_i, &total_i};
+  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(gn_fused_kernel),
+                                              dim3(static_cast<unsigned>(grid_l)), dim3(threads), args, smem, stream);
+  return e == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }
 
 template <int OPL, int R>
@@ -419,7 +683,8 @@ extern "C" int aab_layernorm(const void* x, long ldx, void* y, long ldy, const f
 extern "C" int aab_softmax_rows(const float* s, long lds, void* p, long ldp, long rows, int l, int is_bf16,
                                 void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (!s || !p) return AAB_ERR_ARG;
-  softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(s, lds, p, ldp, l, is_bf16);
+  if (!s || !p || ldp < l) return AAB_ERR_ARG;
+  // the probability rows are `ldp` wide: columns l..ldp-1 are written as zeros
+  softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(s, lds, p, ldp, l, static_cast<int>(ldp), is_bf16);
   return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }

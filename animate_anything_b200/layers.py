@@ -18,12 +18,12 @@ class _ParamsOnly(nn.Module):
 
 
 class TimestepEmbedding(_ParamsOnly):
-    def __init__(self, in_channels, time_embed_dim, act_fn="silu", cond_proj_dim=None):
+    def __init__(self, in_channels, time_embed_dim, act_fn="silu", cond_proj_dim=None, out_dim=None):
         super().__init__()
         assert act_fn in ("silu", "swish")
         self.linear_1 = nn.Linear(in_channels, time_embed_dim)
         self.cond_proj = nn.Linear(cond_proj_dim, in_channels, bias=False) if cond_proj_dim is not None else None
-        self.linear_2 = nn.Linear(time_embed_dim, time_embed_dim)
+        self.linear_2 = nn.Linear(time_embed_dim, out_dim if out_dim is not None else time_embed_dim)
 
 
 class ResnetBlock2D(_ParamsOnly):

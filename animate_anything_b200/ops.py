@@ -334,8 +334,9 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return y
 
 
-def softmax_rows(s: torch.Tensor, dtype) -> torch.Tensor:
-    p = torch.empty(s.shape, device=s.device, dtype=dtype)
+def softmax_rows(s: torch.Tensor, dtype, pad_to: Optional[int] = None) -> torch.Tensor:
+    """fp32 scores [rows, L] -> 16-bit probabilities [rows, pad_to or L]; columns beyond L are zeros (K padding)."""
+    p = torch.empty((s.shape[0], pad_to or s.shape[1]), device=s.device, dtype=dtype)
     _lib.call("aab_softmax_rows", _ptr(s), s.stride(0), _ptr(p), p.stride(0), s.shape[0], s.shape[1],
               1 if dtype == torch.bfloat16 else 0, _stream())
     return p
@@ -422,11 +423,12 @@ def dup_rows(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def transpose_batched(src: torch.Tensor, col0: int, nb: int, rows: int, cols: int) -> torch.Tensor:
-    """src [nb*rows, ld] -> dst [nb, cols, rows] taking columns col0..col0+cols."""
-    dst = torch.empty((nb, cols, rows), device=src.device, dtype=src.dtype)
+def transpose_batched(src: torch.Tensor, col0: int, nb: int, rows: int, cols: int, ld: Optional[int] = None) -> torch.Tensor:
+    """src [nb*rows, ld_src] -> dst [nb, cols, ld or rows] taking columns col0..col0+cols; dst columns >= rows are zeros."""
+    ld = ld or rows
+    dst = torch.empty((nb, cols, ld), device=src.device, dtype=src.dtype)
     base = C.c_void_p(src.data_ptr() + col0 * 2)
-    _lib.call("aab_transpose", base, src.stride(0), rows * src.stride(0), _ptr(dst), nb, rows, cols, _stream())
+    _lib.call("aab_transpose", base, src.stride(0), rows * src.stride(0), _ptr(dst), nb, rows, cols, ld, _stream())
     return dst
 
 

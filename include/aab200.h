@@ -98,7 +98,7 @@ int aab_pad_br(const void* x, void* y, long n, int h, int w, int ph, int pw, int
 int aab_copy2d(const void* src, long lds, void* dst, long ldd, long rows, int cols, void* stream);
 /* dst[0:bytes] = dst[bytes:2*bytes] = src: batch duplication for the shared CFG prefix (torch.cat([latents] * 2), models/pipeline.py:165) */
 int aab_dup_rows(const void* src, void* dst, long bytes, void* stream);
-int aab_transpose(const void* src, long lds, long src_batch, void* dst, int nb, int rows, int cols, void* stream);
+int aab_transpose(const void* src, long lds, long src_batch, void* dst, int nb, int rows, int cols, int ldd, void* stream);
 
 /* Classifier-free guidance + scheduler step + layout shuffles in one kernel (models/pipeline.py:180-192):
  * eps = e_u + g (e_t - e_u); x0 = k0 x + k1 eps; x' = k2 x + k3 eps + k4 x0 + k5 x0_prev.  coef: device [steps][6]. */

@@ -34,6 +34,38 @@ def test_groupnorm(dtype, samples, rows, c, silu):
     check(f"groupnorm s{samples} r{rows} c{c} {dtype}", y, ref, *TOL[dtype])
 
 
+@pytest.mark.parametrize("samples,rows,c", [(34, 4096, 320), (2, 69632, 320), (2, 1088, 1280), (34, 64, 2560)])
+def test_groupnorm_benchmarked_shapes_and_repeat(samples, rows, c):
+    """The extents of a config-2 UNet forward (2-D per frame, 3-D per clip, more chunks than resident CTAs): the fused
+    kernel's flags / tickets must come back to zero, so a SECOND call through the same workspace gives the same bits."""
+    from animate_anything_b200 import ops
+    dtype = torch.bfloat16
+    x = _rand((samples * rows, c), dtype, 1.5, 1, shift=0.3)
+    gamma = _rand((c,), torch.float32, 0.2, 2, shift=1.0)
+    beta = _rand((c,), torch.float32, 0.2, 3)
+    y1 = ops.groupnorm(x, samples, rows, gamma, beta, 1e-5, True)
+    y2 = ops.groupnorm(x, samples, rows, gamma, beta, 1e-5, True)
+    assert torch.equal(y1, y2)
+    xr = x.float().reshape(samples, rows, c).permute(0, 2, 1)
+    ref = F.silu(F.group_norm(xr, 32, gamma, beta, 1e-5)).permute(0, 2, 1).reshape(samples * rows, c)
+    check(f"groupnorm s{samples} r{rows} c{c}", y1, ref, *TOL[dtype])
+
+
+def test_groupnorm_large_mean_no_cancellation():
+    """Statistics are E[x^2] - E[x]^2 from fp32 per-thread partials combined in fp64: a mean 50x the standard deviation
+    must not lose the variance."""
+    from animate_anything_b200 import ops
+    dtype = torch.float16
+    samples, rows, c = 2, 4096, 320
+    x = _rand((samples * rows, c), dtype, 1.0, 7, shift=50.0)
+    gamma = torch.ones(c, device="cuda")
+    beta = torch.zeros(c, device="cuda")
+    y = ops.groupnorm(x, samples, rows, gamma, beta, 1e-5, False)
+    xr = x.double().reshape(samples, rows, c).permute(0, 2, 1)
+    ref = F.group_norm(xr, 32, gamma.double(), beta.double(), 1e-5).permute(0, 2, 1).reshape(samples * rows, c)
+    check("groupnorm mean=50 std=1", y, ref.float(), 2e-3, 2e-3)
+
+
 def test_groupnorm_batch_invariant():
     """A sample's output does not depend on the batch it is normalised in (fixed (rows, C) row partition)."""
     from animate_anything_b200 import ops

@@ -36,15 +36,17 @@ def _no_tf32():
     torch.backends.cudnn.allow_tf32 = False
 
 
-@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-def test_vae_encode_decode(dtype):
+@pytest.mark.parametrize("dtype,hw", [(torch.float16, (64, 96)), (torch.bfloat16, (64, 96)), (torch.float16, (120, 136))])
+def test_vae_encode_decode(dtype, hw):
+    """(120, 136): latent 15 x 17 -- what train.py:738-742 produces for a 170x150 prompt image; H*W of the mid-block
+    attention is then not a multiple of 8 (zero-padded K of the P.V product)."""
     from oracle.composition import AutoencoderKL as OVAE, oracle_decode_latents, oracle_encode_image
     from animate_anything_b200.autoencoder_kl import AutoencoderKL
     _no_tf32()
     ovae, vae = _pair(OVAE, AutoencoderKL, VAE, dtype, seed=1)
     g = torch.Generator().manual_seed(3)
-    img = torch.randn(2, 3, 64, 96, generator=g).to(dtype).cuda()
-    lat = torch.randn(1, 4, 3, 8, 12, generator=g).to(dtype).cuda()
+    img = torch.randn(2, 3, hw[0], hw[1], generator=g).to(dtype).cuda()
+    lat = torch.randn(1, 4, 3, hw[0] // 8, hw[1] // 8, generator=g).to(dtype).cuda()
     with torch.no_grad():
         ref_mean = ovae.encode(img.float()).latent_dist.mode()
         ref_vid = oracle_decode_latents(ovae, lat.float())
@@ -63,7 +65,7 @@ def test_vae_encode_decode(dtype):
         assert e.max().item() <= 2.5 * es.max().item() + 2e-3 * sc
     # diffusers-surface decode(): [N,4,h,w] -> .sample [N,3,H,W] in model dtype
     img2 = vae.decode(lat[0].permute(1, 0, 2, 3)).sample
-    assert img2.shape == (3, 3, 64, 96) and img2.dtype == dtype
+    assert img2.shape == (3, 3, hw[0], hw[1]) and img2.dtype == dtype
 
 
 @pytest.mark.parametrize("sched_name,steps", [("ddim", 3), ("dpm", 4)])

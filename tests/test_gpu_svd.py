@@ -1,0 +1,96 @@
+"""GPU parity of the SVD leg (BASELINE config 4): UNetSpatioTemporalConditionModel on the sm_100a
+kernels against the oracle restatement (oracle/shim/diffusers/_svd.py: leaf semantics recalled from diffusers 0.24,
+PARITY UNPINNED at that level; the composition is pinned to the verbatim reference pipeline by
+tests/test_oracle_golden.py::test_svd_loop_matches_reference_pipeline).  Input layout as the reference builds it at
+models/pipeline.py:422: cat([mask, latents, image_latents], dim=2) -> 9 channels; CFG batch 2 with a zeroed negative
+image embedding (:343)."""
+import os
+import sys
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from util import assert_vs_stock, record_parity  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+SVD_SMALL = dict(in_channels=9, block_out_channels=(64, 128, 128, 128), num_attention_heads=(1, 2, 2, 2),
+                 cross_attention_dim=96, addition_time_embed_dim=32, projection_class_embeddings_input_dim=96,
+                 num_frames=6, sample_size=16)
+STAGES = (["conv_in"] + [f"down_blocks.{i}" for i in range(4)] + ["mid_block"] + [f"up_blocks.{i}" for i in range(4)])
+
+
+def _pair(dtype):
+    from oracle.composition import UNetSpatioTemporalConditionModel as OUNet, fill_deterministic
+    from animate_anything_b200.unet_spatio_temporal_condition import UNetSpatioTemporalConditionModel
+    oracle = fill_deterministic(OUNet(**SVD_SMALL).eval(), seed=0)
+    sd16 = {k: v.to(dtype) for k, v in oracle.state_dict().items()}
+    oracle.load_state_dict({k: v.float() for k, v in sd16.items()})
+    ours = UNetSpatioTemporalConditionModel(**SVD_SMALL).eval()
+    ours.load_state_dict(sd16, strict=True)            # identical state_dict keys
+    return oracle.cuda(), ours.to(dtype).cuda()
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_svd_unet_forward(dtype):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    oracle, ours = _pair(dtype)
+    g = torch.Generator().manual_seed(3)
+    b, nf, h, w = 2, 6, 16, 24
+    lat = torch.randn(1, nf, 4, h, w, generator=g)
+    il = torch.randn(1, nf, 4, h, w, generator=g)
+    mask = (torch.rand(1, 1, 1, h, w, generator=g) > 0.5).float().expand(2, nf, 1, h, w)
+    x = torch.cat([mask, torch.cat([lat, lat]), torch.cat([torch.zeros_like(il), il])], dim=2).to(dtype).cuda()   # [2, F, 9, h, w]
+    emb = torch.randn(1, 1, 96, generator=g)
+    ehs = torch.cat([torch.zeros_like(emb), emb]).to(dtype).cuda()
+    ids = torch.tensor([[6.0, 127.0, 0.02]] * 2).cuda()
+    t = torch.tensor(1.6378)
+    st32, st16 = {}, {}
+
+    def hook_into(store):
+        hs = []
+        for name in STAGES:
+            def mk(n):
+                def f(mod, args, out):
+                    o = out[0] if isinstance(out, tuple) else out
+                    store[n] = o.detach().float()
+                return f
+            hs.append(oracle.get_submodule(name).register_forward_hook(mk(name)))
+        return hs
+    hooks = hook_into(st32)
+    with torch.no_grad():
+        ref = oracle(x.float(), t, ehs.float(), ids, return_dict=False)[0]
+    for hk in hooks:
+        hk.remove()
+    ours.__dict__["_trace"] = []
+    out = ours(x, t, ehs, ids).sample
+    torch.cuda.synchronize()
+    trace = ours.__dict__["_trace"]
+    ours.__dict__["_trace"] = None
+    hooks = hook_into(st16)
+    with torch.no_grad():
+        stock = oracle.to(dtype)(x, t, ehs, ids.to(dtype), return_dict=False)[0].float()
+    for hk in hooks:
+        hk.remove()
+    assert out.shape == ref.shape == (b, nf, 4, h, w) and torch.isfinite(out).all()
+    case = f"SVD UNet small {str(dtype).split('.')[-1]} [2,6,9,16,24]"
+    for name, xx, gg in trace:
+        got = xx.float().reshape(gg.n, gg.h, gg.w, -1).permute(0, 3, 1, 2)
+        row = record_parity(case, name, got, st32[name], st16[name])
+        assert_vs_stock(row, mean_factor=2.0, max_factor=3.0, mean_floor=1e-3, max_floor=1e-2)
+    assert_vs_stock(record_parity(case, "output", out, ref, stock))
+
+
+def test_svd_unet_rejects_bad_inputs():
+    _, ours = _pair(torch.float16)
+    x = torch.zeros(1, 6, 9, 16, 24, dtype=torch.float16, device="cuda")
+    e = torch.zeros(1, 1, 96, dtype=torch.float16, device="cuda")
+    with pytest.raises(ValueError):
+        ours(x, 1.0, e, torch.zeros(1, 2, device="cuda"))              # added_time_ids of the wrong length
+    with pytest.raises(ValueError):
+        ours(x[:, :, :8], 1.0, e, torch.zeros(1, 3, device="cuda"))     # 8 instead of 9 input channels
+    with pytest.raises(ValueError):
+        ours(x[..., :20], 1.0, e, torch.zeros(1, 3, device="cuda"))     # width 20: not a multiple of 8
