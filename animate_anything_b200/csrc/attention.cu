@@ -733,6 +733,197 @@ temporal_attn_d64_kernel(const void* __restrict__ qkv, long ld, int q_col0, int 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ temporal v2
+// Same math as temporal_attn_d64_kernel (bit-identical results), restructured for HBM throughput (round 2: the v1 kernel
+// reached 0.30 of the HBM roofline, profiles/r02_kernels_by_shape.md).  Persistent warps walk the (b, pixel, head) items;
+// the Q/K/V rows of the NEXT item are fetched with 16-byte cp.async copies straight into the second shared-memory buffer
+// (408 copies in flight per warp, no registers involved) while the current item is computed; the normalised output is
+// staged in shared memory and written with 16-byte stores (one 128-byte row per 8 lanes).
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(128)
+temporal_attn_d64_v2_kernel(const void* __restrict__ qkv, long ld, int q_col0, int k_col0, int v_col0,
+                            void* __restrict__ out, long ld_out, int B, int T, int HW, int heads, float scale) {
+  extern __shared__ uint16_t sm16[];
+  const int w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long total = static_cast<long>(B) * HW * heads;
+  const long stride = static_cast<long>(gridDim.x) * 4;
+  long item = static_cast<long>(blockIdx.x) * 4 + w;
+  uint16_t* wbase = sm16 + static_cast<size_t>(w) * 2 * TA_WARP_HALVES;      // two buffers of (Q, K, V)[32][72]
+  // rows T..31 of every buffer stay zero for the whole kernel (cp.async only ever writes rows < T)
+  for (int i = lane; i < 2 * TA_WARP_HALVES / 8; i += 32) reinterpret_cast<uint4*>(wbase)[i] = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  const int col_off[3] = {q_col0, k_col0, v_col0};
+  auto prefetch = [&](long it, int buf) {
+    const int head = static_cast<int>(it % heads);
+    const long bp = it / heads;
+    const int pos = static_cast<int>(bp % HW);
+    const int b = static_cast<int>(bp / HW);
+    uint16_t* dst = wbase + buf * TA_WARP_HALVES;
+    const int nchunks = T * 24;                 // T rows x 3 tensors x 8 pieces of 16 bytes
+    for (int c = lane; c < nchunks; c += 32) {
+      const int t = c / 24;
+      const int rem = c - t * 24;
+      const int seg = rem >> 3;
+      const int part = rem & 7;
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(qkv) +
+                           (((static_cast<long>(b) * T + t) * HW + pos) * ld + col_off[seg] + head * 64 + part * 8) * 2;
+      cp_async_16(dst + seg * 32 * TA_ROW + t * TA_ROW + part * 8, src);
+    }
+  };
+  int buf = 0;
+  if (item < total) prefetch(item, 0);
+  cp_async_commit();
+  const int g = lane >> 2;
+  const int t4 = lane & 3;
+  const float sl2 = scale * 1.4426950408889634f;
+  for (; item < total; item += stride, buf ^= 1) {
+    const long nxt = item + stride;
+    if (nxt < total) prefetch(nxt, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+    uint16_t* sQ = wbase + buf * TA_WARP_HALVES;
+    uint16_t* sK = sQ + 32 * TA_ROW;
+    uint16_t* sV = sK + 32 * TA_ROW;
+    // ---------------- S = Q K^T
+    float S[2][4][4];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) S[mi][nj][e] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t afr[2][4];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const uint16_t* base = sQ + (16 * mi + g) * TA_ROW + 16 * kk + 2 * t4;
+        afr[mi][0] = *reinterpret_cast<const uint32_t*>(base);
+        afr[mi][1] = *reinterpret_cast<const uint32_t*>(base + 8 * TA_ROW);
+        afr[mi][2] = *reinterpret_cast<const uint32_t*>(base + 8);
+        afr[mi][3] = *reinterpret_cast<const uint32_t*>(base + 8 * TA_ROW + 8);
+      }
+#pragma unroll
+      for (int nj = 0; nj < 4; ++nj) {
+        uint32_t bfr[2];
+        const uint16_t* kb = sK + (8 * nj + g) * TA_ROW + 16 * kk + 2 * t4;
+        bfr[0] = *reinterpret_cast<const uint32_t*>(kb);
+        bfr[1] = *reinterpret_cast<const uint32_t*>(kb + 8);
+        mma_16816<BF16>(S[0][nj], afr[0], bfr);
+        mma_16816<BF16>(S[1][nj], afr[1], bfr);
+      }
+    }
+    // ---------------- softmax over the keys
+    float inv_l[2][2];
+    uint32_t pfr[2][2][4];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = 8 * nj + 2 * t4 + e;
+            float v = S[mi][nj][2 * h + e] * sl2;
+            v = (col < T) ? v : -INFINITY;
+            S[mi][nj][2 * h + e] = v;
+            mx = fmaxf(mx, v);
+          }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        float l = 0.f;
+#pragma unroll
+        for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float pv = fast_exp2(S[mi][nj][2 * h + e] - mx);
+            S[mi][nj][2 * h + e] = pv;
+            l += pv;
+          }
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        inv_l[mi][h] = 1.0f / l;
+      }
+#pragma unroll
+      for (int k2 = 0; k2 < 2; ++k2) {
+        pfr[mi][k2][0] = pack2(S[mi][2 * k2][0], S[mi][2 * k2][1], BF16);
+        pfr[mi][k2][1] = pack2(S[mi][2 * k2][2], S[mi][2 * k2][3], BF16);
+        pfr[mi][k2][2] = pack2(S[mi][2 * k2 + 1][0], S[mi][2 * k2 + 1][1], BF16);
+        pfr[mi][k2][3] = pack2(S[mi][2 * k2 + 1][2], S[mi][2 * k2 + 1][3], BF16);
+      }
+    }
+    // ---------------- O = P V
+    float O[2][8][4];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int dj = 0; dj < 8; ++dj)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) O[mi][dj][e] = 0.f;
+#pragma unroll
+    for (int k2 = 0; k2 < 2; ++k2) {
+#pragma unroll
+      for (int dj = 0; dj < 8; ++dj) {
+        const uint16_t* vb = sV + (16 * k2 + 2 * t4) * TA_ROW + 8 * dj + g;
+        uint32_t bfr[2];
+        bfr[0] = static_cast<uint32_t>(vb[0]) | (static_cast<uint32_t>(vb[TA_ROW]) << 16);
+        bfr[1] = static_cast<uint32_t>(vb[8 * TA_ROW]) | (static_cast<uint32_t>(vb[9 * TA_ROW]) << 16);
+        mma_16816<BF16>(O[0][dj], pfr[0][k2], bfr);
+        mma_16816<BF16>(O[1][dj], pfr[1][k2], bfr);
+      }
+    }
+    // ---------------- normalise -> stage in the Q buffer (all Q reads of this warp are done) -> 16-byte row stores
+    __syncwarp();
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int row = 16 * mi + g + 8 * h;
+        const float il = inv_l[mi][h];
+        uint16_t* orow = sQ + row * TA_ROW + 2 * t4;
+#pragma unroll
+        for (int dj = 0; dj < 8; ++dj)
+          *reinterpret_cast<uint32_t*>(orow + dj * 8) = pack2(O[mi][dj][2 * h] * il, O[mi][dj][2 * h + 1] * il, BF16);
+      }
+    __syncwarp();
+    {
+      const int head = static_cast<int>(item % heads);
+      const long bp = item / heads;
+      const int pos = static_cast<int>(bp % HW);
+      const int b = static_cast<int>(bp / HW);
+      for (int c = lane; c < T * 8; c += 32) {
+        const int t = c >> 3;
+        const int part = c & 7;
+        const uint4 v = *reinterpret_cast<const uint4*>(sQ + t * TA_ROW + part * 8);
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out) +
+                                  (((static_cast<long>(b) * T + t) * HW + pos) * ld_out + head * 64 + part * 8) * 2) = v;
+      }
+    }
+    __syncwarp();
+    // rows >= T of the Q buffer were overwritten by the staging (rows 16 mi + g + 8 h cover all 32): zero them again
+    for (int c = lane; c < (32 - T) * 9; c += 32) {
+      const int r = T + c / 9;
+      reinterpret_cast<uint4*>(sQ + r * TA_ROW)[c % 9] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+  }
+  cp_async_wait<0>();
+}
+
 }  // namespace aab
 
 using namespace aab;
@@ -807,6 +998,28 @@ extern "C" int aab_temporal_attn_d64(const void* qkv, long ld, int q_col0, int k
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!qkv || !out || t < 1 || t > 32 || (ld % 8) || (ld_out % 8)) return AAB_ERR_ARG;
   const long total = static_cast<long>(b) * hw * heads;
+  static int use_v1 = -1;                 // AAB_TATTN_V1=1: the round-1 kernel (A/B measurements)
+  if (use_v1 < 0) {
+    const char* e = getenv("AAB_TATTN_V1");
+    use_v1 = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (!use_v1) {
+    if ((q_col0 | k_col0 | v_col0) % 8) return AAB_ERR_ARG;     // 16-byte cp.async pieces
+    const size_t smem2 = static_cast<size_t>(4) * 2 * TA_WARP_HALVES * sizeof(uint16_t);   // 108 KiB: double-buffered Q, K, V
+    static std::atomic<unsigned long long> a2t{0}, a2f{0};
+    if (int r = ensure_dyn_smem(temporal_attn_d64_v2_kernel<true>, static_cast<int>(smem2), a2t)) return r;
+    if (int r = ensure_dyn_smem(temporal_attn_d64_v2_kernel<false>, static_cast<int>(smem2), a2f)) return r;
+    long ctas = (total + 3) / 4;
+    const long cap = 2L * num_sms();                              // two 108 KiB CTAs per SM, persistent
+    const int grid2 = static_cast<int>(ctas < cap ? ctas : cap);
+    if (is_bf16)
+      temporal_attn_d64_v2_kernel<true><<<grid2, 128, smem2, stream>>>(qkv, ld, q_col0, k_col0, v_col0, out, ld_out, b, t, hw,
+                                                                       heads, scale);
+    else
+      temporal_attn_d64_v2_kernel<false><<<grid2, 128, smem2, stream>>>(qkv, ld, q_col0, k_col0, v_col0, out, ld_out, b, t, hw,
+                                                                        heads, scale);
+    return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
+  }
   const int grid = static_cast<int>((total + 3) / 4);
   const size_t smem = static_cast<size_t>(4) * TA_WARP_HALVES * sizeof(uint16_t);   // 54 KiB: Q, K, V padded to 32 rows
   static std::atomic<unsigned long long> attr_t{0}, attr_f{0};

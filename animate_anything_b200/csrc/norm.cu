@@ -9,6 +9,7 @@
 //   * LayerNorm over C (one warp per token row, exact two-pass variance in registers).
 // Algorithmic bytes: stats = 1 read of the activation; apply = 1 read + 1 write; layernorm = 1 read + 1 write.
 #include "common.cuh"
+#include "igemm.h"
 #include <stdlib.h>
 
 namespace aab {
@@ -529,6 +530,93 @@ layernorm_kernel(const void* __restrict__ x, long ldx, void* __restrict__ y, lon
   }
 }
 
+// LayerNorm v2 (round 2; v1 reached 0.48 of the HBM roofline): LPR lanes share one row (LPR = 8 / 16 / 32 chosen so that
+// ceil(C/8 / LPR) octets per lane waste no lanes: C=320 -> 8 lanes x 5 octets, 640 -> 16 x 5, 1280 -> 32 x 5), a warp
+// normalises 32/LPR rows at once, persistent warps walk the row groups and the NEXT group's loads are issued before the
+// current group is reduced (register double buffering), so every warp always has loads in flight.  Exact two-pass
+// variance in registers as before; results are per-row (batch-invariant).
+template <int OPL, int LPR>
+__global__ void __launch_bounds__(256)
+layernorm_v2_kernel(const void* __restrict__ x, long ldx, void* __restrict__ y, long ldy, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, long rows, int C, float eps, int bf16) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;
+  const int slot = lane / LPR;
+  const long nwarps = static_cast<long>(gridDim.x) * (blockDim.x >> 5);
+  long grp = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long ngroups = (rows + RPW - 1) / RPW;
+  if (grp >= ngroups) return;
+  const bool bf = bf16 != 0;
+  const int V = C >> 3;
+  const float invc = 1.0f / C;
+  auto load = [&](uint4 (&buf)[OPL], long g) {
+    const long row = g * RPW + slot;
+#pragma unroll
+    for (int i = 0; i < OPL; ++i) {
+      const int o = sub + i * LPR;
+      buf[i] = make_uint4(0, 0, 0, 0);
+      if (o < V && row < rows) buf[i] = ldg16(reinterpret_cast<const uint8_t*>(x) + (row * ldx + o * 8) * 2);
+    }
+  };
+  uint4 cur[OPL], nxt[OPL];
+  load(cur, grp);
+  for (; grp < ngroups; grp += nwarps) {
+    const long ng = grp + nwarps;
+    if (ng < ngroups) load(nxt, ng);
+    const long row = grp * RPW + slot;
+    float v[OPL][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < OPL; ++i) {
+      const uint32_t w[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack2(w[e], bf);
+        v[i][2 * e] = f.x; v[i][2 * e + 1] = f.y;
+        sum += f.x + f.y;                   // octets beyond V hold zeros
+      }
+    }
+#pragma unroll
+    for (int off = LPR / 2; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const float mean = sum * invc;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < OPL; ++i) {
+      if (sub + i * LPR < V) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; sq += d * d; }
+      }
+    }
+#pragma unroll
+    for (int off = LPR / 2; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    const float rstd = rsqrtf(sq * invc + eps);
+    if (row < rows) {
+#pragma unroll
+      for (int i = 0; i < OPL; ++i) {
+        const int o = sub + i * LPR;
+        if (o < V) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + o * 8));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + o * 8) + 1);
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + o * 8));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + o * 8) + 1);
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          uint32_t ow[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            ow[e] = pack2((v[i][2 * e] - mean) * rstd * gg[2 * e] + bb[2 * e],
+                          (v[i][2 * e + 1] - mean) * rstd * gg[2 * e + 1] + bb[2 * e + 1], bf);
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y) + (row * ldy + o * 8) * 2) =
+              make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < OPL; ++i) cur[i] = nxt[i];
+  }
+}
+
 // row softmax: fp32 scores [rows][L] -> 16-bit probabilities (VAE mid-block attention, upcast_softmax semantics)
 __global__ void softmax_rows_kernel(const float* __restrict__ s, long lds, void* __restrict__ p, long ldp, int L, int Lpad,
                                     int bf16) {
@@ -588,12 +676,17 @@ static int gn_launch_cfg(int C, long samples, long rows, int* threads, int* rows
   return AAB_OK;
 }
 
-// Workspace layout (bytes): [0, 12*samples) tickets | flags | done counters (must be zero before the first use; self-
-// resetting afterwards), then mean/rstd floats [samples*groups*2], then double partials [samples*chunks*groups*2].
+// Workspace layout (bytes): a FIXED 48 KiB header of counters -- tickets [0, 16K), flags [16K, 32K), done [32K, 48K), one
+// u32 per sample each -- that must be zero before the first use and is self-resetting afterwards (fixed offsets: calls
+// with different sample counts share one workspace, and a counter must never alias another call's statistics);
+// then mean/rstd floats [samples*groups*2], then double partials [samples*chunks*groups*2].
+static const long GN_MAX_SAMPLES = 4096;
+static const long GN_HEADER_BYTES = 3 * GN_MAX_SAMPLES * 4;
 extern "C" long aab_groupnorm_workspace_bytes(long samples, long rows, int c, int groups) {
   int threads, rpc, chunks;
   if (gn_launch_cfg(c, samples, rows, &threads, &rpc, &chunks)) return -1;
-  long off = ((samples * 12 + 255) / 256) * 256;
+  if (samples > GN_MAX_SAMPLES) return -1;
+  long off = GN_HEADER_BYTES;
   off += ((samples * groups * 2 * 4 + 255) / 256) * 256;
   off += samples * chunks * groups * 2 * 8;
   return off;
@@ -615,10 +708,11 @@ extern "C" int aab_groupnorm(const void* x1, long ld1, int c1, const void* x2, l
   a.x1 = x1; a.x2 = x2; a.C1 = c1; a.C2 = c2; a.ld1 = ld1; a.ld2 = ld2; a.rows = rows; a.groups = groups;
   a.rows_per_cta = rpc; a.bf16 = is_bf16;
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  if (samples > GN_MAX_SAMPLES) return AAB_ERR_ARG;
   unsigned int* ticket = reinterpret_cast<unsigned int*>(ws);
-  unsigned int* flag = ticket + samples;
-  unsigned int* done = flag + samples;
-  long off = ((samples * 12 + 255) / 256) * 256;
+  unsigned int* flag = ticket + GN_MAX_SAMPLES;
+  unsigned int* done = flag + GN_MAX_SAMPLES;
+  long off = GN_HEADER_BYTES;
   float* mean_rstd = reinterpret_cast<float*>(ws + off);
   off += ((samples * groups * 2 * 4 + 255) / 256) * 256;
   double* partial = reinterpret_cast<double*>(ws + off);
@@ -668,11 +762,43 @@ static void launch_ln(const void* x, long ldx, void* y, long ldy, const float* g
       x, ldx, y, ldy, gamma, beta, rows, c, eps, is_bf16);
 }
 
+template <int OPL, int LPR>
+static void launch_ln2(const void* x, long ldx, void* y, long ldy, const float* gamma, const float* beta, long rows, int c,
+                       float eps, int is_bf16, cudaStream_t stream) {
+  constexpr int RPW = 32 / LPR;
+  const int wpb = 8;
+  const long groups = (rows + RPW - 1) / RPW;
+  long ctas = (groups + wpb - 1) / wpb;
+  const long cap = 6L * aab::num_sms();                 // persistent: ~6 CTAs of 8 warps per SM
+  if (ctas > cap) ctas = cap;
+  layernorm_v2_kernel<OPL, LPR><<<static_cast<unsigned>(ctas), wpb * 32, 0, stream>>>(x, ldx, y, ldy, gamma, beta, rows, c,
+                                                                                     eps, is_bf16);
+}
+
 extern "C" int aab_layernorm(const void* x, long ldx, void* y, long ldy, const float* gamma, const float* beta,
                              long rows, int c, float eps, int is_bf16, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!x || !y || (c % 8) || c > 2048 || (ldx % 8) || (ldy % 8)) return AAB_ERR_ARG;
   const int V = c / 8;
+  static int use_v1 = -1;                 // AAB_LN_V1=1: the round-1 kernel (A/B measurements)
+  if (use_v1 < 0) {
+    const char* e = getenv("AAB_LN_V1");
+    use_v1 = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (!use_v1) {
+    // lanes per row: the smallest of 8 / 16 / 32 that keeps <= 8 octets per lane, preferring exact fits
+    if (V <= 8) launch_ln2<1, 8>(x, ldx, y, ldy, gamma, beta, rows, c, eps, is_bf16, stream);
+    else if (V <= 16) launch_ln2<2, 8>(x, ldx, y, ldy, gamma, beta, rows, c, eps, is_bf16, stream);
+    else if (V <= 24) launch_ln2<3, 8>(x, ldx, y, ldy, gamma, beta, rows, c, eps, is_bf16, stream);
+    else if (V <= 32) launch_ln2<4, 8>(x, ldx, y, ldy, gamma, beta, rows, c, eps, is_bf16, stream);
+    else if (V <= 40) launch_ln2<5, 8>(x, ldx, y, ldy, gamma, beta, rows, c, eps, is_bf16, stream);
+    else if (V <= 64) launch_ln2<4, 16>(x, ldx, y, ldy, gamma, beta, rows, c, eps, is_bf16, stream);
+    else if (V <= 80) launch_ln2<5, 16>(x, ldx, y, ldy, gamma, beta, rows, c, eps, is_bf16, stream);
+    else if (V <= 128) launch_ln2<4, 32>(x, ldx, y, ldy, gamma, beta, rows, c, eps, is_bf16, stream);
+    else if (V <= 160) launch_ln2<5, 32>(x, ldx, y, ldy, gamma, beta, rows, c, eps, is_bf16, stream);
+    else launch_ln2<8, 32>(x, ldx, y, ldy, gamma, beta, rows, c, eps, is_bf16, stream);
+    return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
+  }
   if (V <= 64) launch_ln<2, 4>(x, ldx, y, ldy, gamma, beta, rows, c, eps, is_bf16, stream);
   else if (V <= 96) launch_ln<3, 4>(x, ldx, y, ldy, gamma, beta, rows, c, eps, is_bf16, stream);
   else if (V <= 160) launch_ln<5, 2>(x, ldx, y, ldy, gamma, beta, rows, c, eps, is_bf16, stream);
