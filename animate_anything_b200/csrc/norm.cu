@@ -56,15 +56,21 @@ __global__ void gn_stats_kernel(GnArgs a, double* __restrict__ partial /* [S][ch
   int cc;
   if (c0 < a.C1) { base = reinterpret_cast<const uint8_t*>(a.x1); ld = a.ld1; cc = c0; }
   else { base = reinterpret_cast<const uint8_t*>(a.x2); ld = a.ld2; cc = c0 - a.C1; }
-  // 8 independent 16-byte loads in flight per thread (the kernel is latency-bound otherwise)
-  for (long r = r0 + rsub; r < r1; r += 8 * rpi) {
-    uint4 u[8];
+  // 8 independent 16-byte loads in flight per thread, and the NEXT batch of 8 is requested before the current one is
+  // accumulated (register double buffering): the kernel is latency-bound otherwise
+  auto load8 = [&](uint4 (&u)[8], long r) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const long rk = r + static_cast<long>(k) * rpi;
       u[k] = make_uint4(0, 0, 0, 0);
       if (rk < r1) u[k] = ldg16(base + ((static_cast<long>(s) * a.rows + rk) * ld + cc) * 2);
     }
+  };
+  uint4 u[8], un[8];
+  load8(u, r0 + rsub);
+  for (long r = r0 + rsub; r < r1; r += 8 * rpi) {
+    const bool more = r + 8 * rpi < r1;
+    if (more) load8(un, r + 8 * rpi);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
@@ -74,6 +80,10 @@ __global__ void gn_stats_kernel(GnArgs a, double* __restrict__ partial /* [S][ch
         sum[2 * e] += f.x; sq[2 * e] += f.x * f.x;
         sum[2 * e + 1] += f.y; sq[2 * e + 1] += f.y * f.y;
       }
+    }
+    if (more) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) u[k] = un[k];
     }
   }
   float* shs = sh;
@@ -193,14 +203,19 @@ __global__ void gn_apply_kernel(GnArgs a, const float* __restrict__ mean_rstd, c
   int cc;
   if (c0 < a.C1) { base = reinterpret_cast<const uint8_t*>(a.x1); ld = a.ld1; cc = c0; }
   else { base = reinterpret_cast<const uint8_t*>(a.x2); ld = a.ld2; cc = c0 - a.C1; }
-  for (long r = r0 + rsub; r < r1; r += 4 * rpi) {
-    uint4 u[4];
+  auto load4 = [&](uint4 (&u)[4], long r) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const long rk = r + static_cast<long>(k) * rpi;
       u[k] = make_uint4(0, 0, 0, 0);
       if (rk < r1) u[k] = ldg16(base + ((static_cast<long>(s) * a.rows + rk) * ld + cc) * 2);
     }
+  };
+  uint4 u[4], un[4];
+  load4(u, r0 + rsub);
+  for (long r = r0 + rsub; r < r1; r += 4 * rpi) {
+    const bool more = r + 4 * rpi < r1;
+    if (more) load4(un, r + 4 * rpi);       // next batch in flight while this one is normalised and stored
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const long rk = r + static_cast<long>(k) * rpi;
@@ -218,239 +233,9 @@ __global__ void gn_apply_kernel(GnArgs a, const float* __restrict__ mean_rstd, c
       *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y) + ((static_cast<long>(s) * a.rows + rk) * ldy + c0) * 2) =
           make_uint4(o[0], o[1], o[2], o[3]);
     }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ fused GroupNorm
-// ONE launch instead of two (statistics + apply).  Measured in round 2 (profiles/r02_kernels_by_shape.md): a GroupNorm call
-// on an 11 MB tensor took 21 us against 1.7 us of HBM time -- two launches, two tails, and the serial "last CTA reduces the
-// partials" step in between; 166 calls per UNet forward made that fixed cost ~3 ms.  Here a co-resident (cooperatively
-// launched) grid walks the same fixed row partition twice:
-//   phase 1: per-chunk (sum, sumsq) partials -> workspace; the last CTA of a SAMPLE (ticket) reduces that sample's partials in
-//            index order, publishes mean / rstd and raises the sample's flag (release);
-//   phase 2: every CTA waits for the flag of its chunk's sample (acquire; other samples keep streaming meanwhile) and
-//            normalises its chunk -- the re-read hits the 126 MB L2, only the write goes to HBM.
-// Bitwise reproducibility and batch invariance are unchanged: the partition depends on (rows, C) only, partials are
-// combined in fixed order, which CTA computed a partial does not matter.
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-__global__ void gn_fused_kernel(GnArgs a, double* __restrict__ partial /* [S][chunks][G][2] */,
-                                float* __restrict__ mean_rstd /* [S][G][2] */, unsigned int* __restrict__ ticket /* [S] */,
-                                unsigned int* __restrict__ flag /* [S] */, unsigned int* __restrict__ done /* [S] */,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
-                                void* __restrict__ y, long ldy, float eps, int chunks, int total_chunks) {
-  extern __shared__ float sh[];   // [rpi][C] sums, [rpi][C] squares (phase 1) / fp64 reduction scratch (finalize)
-  __shared__ bool is_last;
-  const int C = a.C1 + a.C2;
-  const int V = C >> 3;
-  const int oct = threadIdx.x % V;
-  const int rsub = threadIdx.x / V;
-  const int rpi = blockDim.x / V;
-  const bool bf = a.bf16 != 0;
-  const int c0 = oct * 8;
-  const int cpg = C / a.groups;
-  const uint8_t* base;
-  long ld;
-  int cc;
-  if (c0 < a.C1) { base = reinterpret_cast<const uint8_t*>(a.x1); ld = a.ld1; cc = c0; }
-  else { base = reinterpret_cast<const uint8_t*>(a.x2); ld = a.ld2; cc = c0 - a.C1; }
-  float* shs = sh;
-  float* shq = sh + rpi * C;
-
-  // ------------------------------------------------------------------ phase 1: statistics
-  for (int ch = blockIdx.x; ch < total_chunks; ch += gridDim.x) {
-    const int s = ch / chunks;
-    const int cix = ch - s * chunks;
-    const long r0 = static_cast<long>(cix) * a.rows_per_cta;
-    long r1 = r0 + a.rows_per_cta;
-    if (r1 > a.rows) r1 = a.rows;
-    float sum[8], sq[8];
+    if (more) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
-    for (long r = r0 + rsub; r < r1; r += 8 * rpi) {
-      uint4 u[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const long rk = r + static_cast<long>(k) * rpi;
-        u[k] = make_uint4(0, 0, 0, 0);
-        if (rk < r1) u[k] = ldg16(base + ((static_cast<long>(s) * a.rows + rk) * ld + cc) * 2);
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = unpack2(w[e], bf);
-          sum[2 * e] += f.x; sq[2 * e] += f.x * f.x;
-          sum[2 * e + 1] += f.y; sq[2 * e + 1] += f.y * f.y;
-        }
-      }
-    }
-    __syncthreads();                      // previous iteration's readers of sh are done
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      shs[rsub * C + c0 + j] = sum[j];
-      shq[rsub * C + c0 + j] = sq[j];
-    }
-    __syncthreads();
-    if (threadIdx.x < a.groups) {
-      const int g = threadIdx.x;
-      float fs0 = 0.f, fs1 = 0.f, fq0 = 0.f, fq1 = 0.f;
-      for (int r = 0; r < rpi; ++r) {
-        int c = g * cpg;
-        for (; c + 1 < (g + 1) * cpg; c += 2) {
-          fs0 += shs[r * C + c];
-          fs1 += shs[r * C + c + 1];
-          fq0 += shq[r * C + c];
-          fq1 += shq[r * C + c + 1];
-        }
-        if (c < (g + 1) * cpg) {
-          fs0 += shs[r * C + c];
-          fq0 += shq[r * C + c];
-        }
-      }
-      double* pp = partial + ((static_cast<long>(s) * chunks + cix) * a.groups + g) * 2;
-      pp[0] = static_cast<double>(fs0) + static_cast<double>(fs1);
-      pp[1] = static_cast<double>(fq0) + static_cast<double>(fq1);
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const unsigned int t = atomicAdd(&ticket[s], 1u);
-      is_last = (t == static_cast<unsigned int>(chunks - 1));
-      if (is_last) ticket[s] = 0;          // self-reset for the next launch
-    }
-    __syncthreads();
-    if (is_last) {
-      __threadfence();
-      const int P = blockDim.x / a.groups;                 // >= 1 (host guarantees blockDim >= groups)
-      double* red = reinterpret_cast<double*>(sh);
-      const int g = threadIdx.x % a.groups;
-      const int part = threadIdx.x / a.groups;
-      if (part < P) {
-        double ds[8], dq[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) ds[k] = dq[k] = 0.0;
-        const double* pp = partial + (static_cast<long>(s) * chunks * a.groups + g) * 2;
-        for (int c1 = part; c1 < chunks; c1 += 8 * P) {
-          double2 v[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int c2 = c1 + k * P;
-            v[k] = make_double2(0.0, 0.0);
-            if (c2 < chunks) v[k] = __ldcg(reinterpret_cast<const double2*>(pp + static_cast<long>(c2) * a.groups * 2));
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            ds[k] += v[k].x;
-            dq[k] += v[k].y;
-          }
-        }
-        red[(part * a.groups + g) * 2] = ((ds[0] + ds[1]) + (ds[2] + ds[3])) + ((ds[4] + ds[5]) + (ds[6] + ds[7]));
-        red[(part * a.groups + g) * 2 + 1] = ((dq[0] + dq[1]) + (dq[2] + dq[3])) + ((dq[4] + dq[5]) + (dq[6] + dq[7]));
-      }
-      __syncthreads();
-      if (threadIdx.x < a.groups) {
-        double ds = 0.0, dq = 0.0;
-        for (int q = 0; q < P; ++q) {
-          ds += red[(q * a.groups + g) * 2];
-          dq += red[(q * a.groups + g) * 2 + 1];
-        }
-        const double n = static_cast<double>(a.rows) * cpg;
-        const double m = ds / n;
-        double var = dq / n - m * m;
-        if (var < 0) var = 0;
-        mean_rstd[(static_cast<long>(s) * a.groups + g) * 2] = static_cast<float>(m);
-        mean_rstd[(static_cast<long>(s) * a.groups + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-      }
-      __threadfence();
-      __syncthreads();
-      if (threadIdx.x == 0) st_release_u32(&flag[s], 1u);
-    }
-  }
-
-  // ------------------------------------------------------------------ phase 2: apply (+ SiLU)
-  float* sc_sh = sh;            // [C] scale, [C] shift of the current sample (recomputed when the sample changes)
-  float* sf_sh = sh + C;
-  int cur_s = -1;
-  for (int ch = blockIdx.x; ch < total_chunks; ch += gridDim.x) {
-    const int s = ch / chunks;
-    const int cix = ch - s * chunks;
-    if (s != cur_s) {
-      __syncthreads();                    // everyone is done with the previous sample's scale / shift (and with `red`)
-      if (threadIdx.x == 0) {
-        unsigned int spins = 0;
-        while (ld_acquire_u32(&flag[s]) == 0u) {
-          __nanosleep(32);
-          if (++spins > (1u << 26)) {
-            printf("aab: groupnorm flag timeout sample %d block %d\n", s, blockIdx.x);
-            __trap();
-          }
-        }
-      }
-      __syncthreads();
-      for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int g = c / cpg;
-        const float m = __ldcg(&mean_rstd[(static_cast<long>(s) * a.groups + g) * 2]);
-        const float rstd = __ldcg(&mean_rstd[(static_cast<long>(s) * a.groups + g) * 2 + 1]);
-        const float gm = gamma[c];
-        sc_sh[c] = rstd * gm;
-        sf_sh[c] = beta[c] - m * rstd * gm;
-      }
-      __syncthreads();
-      cur_s = s;
-    }
-    float sc[8], sf[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sc[j] = sc_sh[c0 + j];
-      sf[j] = sf_sh[c0 + j];
-    }
-    const long r0 = static_cast<long>(cix) * a.rows_per_cta;
-    long r1 = r0 + a.rows_per_cta;
-    if (r1 > a.rows) r1 = a.rows;
-    for (long r = r0 + rsub; r < r1; r += 4 * rpi) {
-      uint4 u[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const long rk = r + static_cast<long>(k) * rpi;
-        u[k] = make_uint4(0, 0, 0, 0);
-        if (rk < r1) u[k] = ldg16(base + ((static_cast<long>(s) * a.rows + rk) * ld + cc) * 2);
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const long rk = r + static_cast<long>(k) * rpi;
-        if (rk >= r1) break;
-        const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
-        uint32_t o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = unpack2(w[e], bf);
-          float v0 = fmaf(f.x, sc[2 * e], sf[2 * e]);
-          float v1 = fmaf(f.y, sc[2 * e + 1], sf[2 * e + 1]);
-          if (silu) { v0 = silu_fast_f(v0); v1 = silu_fast_f(v1); }
-          o[e] = pack2(v0, v1, bf);
-        }
-        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y) + ((static_cast<long>(s) * a.rows + rk) * ldy + c0) * 2) =
-            make_uint4(o[0], o[1], o[2], o[3]);
-      }
-    }
-    // the last chunk of a sample to be applied lowers the flag again for the next launch (nobody can still wait on it:
-    // every chunk of the sample has passed its wait)
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const unsigned int d = atomicAdd(&done[s], 1u);
-      if (d == static_cast<unsigned int>(chunks - 1)) {
-        done[s] = 0;
-        flag[s] = 0;
-      }
+      for (int k = 0; k < 4; ++k) u[k] = un[k];
     }
   }
 }
@@ -676,12 +461,12 @@ static int gn_launch_cfg(int C, long samples, long rows, int* threads, int* rows
   return AAB_OK;
 }
 
-// Workspace layout (bytes): a FIXED 48 KiB header of counters -- tickets [0, 16K), flags [16K, 32K), done [32K, 48K), one
-// u32 per sample each -- that must be zero before the first use and is self-resetting afterwards (fixed offsets: calls
-// with different sample counts share one workspace, and a counter must never alias another call's statistics);
-// then mean/rstd floats [samples*groups*2], then double partials [samples*chunks*groups*2].
+// Workspace layout (bytes): a FIXED 16 KiB header of tickets (one u32 per sample) that must be zero before the first use
+// and is self-resetting afterwards (fixed offset: calls with different sample counts share one workspace, and a ticket must
+// never alias another call's statistics); then mean/rstd floats [samples*groups*2], then double partials
+// [samples*chunks*groups*2].
 static const long GN_MAX_SAMPLES = 4096;
-static const long GN_HEADER_BYTES = 3 * GN_MAX_SAMPLES * 4;
+static const long GN_HEADER_BYTES = GN_MAX_SAMPLES * 4;
 extern "C" long aab_groupnorm_workspace_bytes(long samples, long rows, int c, int groups) {
   int threads, rpc, chunks;
   if (gn_launch_cfg(c, samples, rows, &threads, &rpc, &chunks)) return -1;
@@ -710,8 +495,6 @@ extern "C" int aab_groupnorm(const void* x1, long ld1, int c1, const void* x2, l
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   if (samples > GN_MAX_SAMPLES) return AAB_ERR_ARG;
   unsigned int* ticket = reinterpret_cast<unsigned int*>(ws);
-  unsigned int* flag = ticket + GN_MAX_SAMPLES;
-  unsigned int* done = flag + GN_MAX_SAMPLES;
   long off = GN_HEADER_BYTES;
   float* mean_rstd = reinterpret_cast<float*>(ws + off);
   off += ((samples * groups * 2 * 4 + 255) / 256) * 256;
@@ -721,36 +504,14 @@ extern "C" int aab_groupnorm(const void* x1, long ld1, int c1, const void* x2, l
   const size_t smem_red = static_cast<size_t>(threads / groups) * groups * 2 * sizeof(double);
   if (smem_red > smem) smem = smem_red;
   if (smem > 48 * 1024 || threads < groups) return AAB_ERR_ARG;
-  static int two_pass = -1;               // AAB_GN_TWO_PASS=1: the round-1 pair of kernels (A/B measurements)
-  if (two_pass < 0) {
-    const char* e = getenv("AAB_GN_TWO_PASS");
-    two_pass = (e && e[0] == '1') ? 1 : 0;
-  }
-  if (two_pass) {
-    dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(samples));
-    gn_stats_kernel<<<grid, threads, smem, stream>>>(a, partial, mean_rstd, ticket, eps);
-    gn_apply_kernel<<<grid, threads, 0, stream>>>(a, mean_rstd, gamma, beta, silu, y, ldy);
-    return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
-  }
-  // fused kernel: the grid must be co-resident (CTAs of phase 2 wait for flags raised by other CTAs) -> cooperative launch,
-  // sized from the occupancy of this (threads, smem) configuration on the current device
-  size_t smem2 = static_cast<size_t>(2) * C * sizeof(float);      // phase-2 scale / shift
-  if (smem2 > smem) smem = smem2;
-  int dev = 0, sms = 0, per_sm = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return AAB_ERR_CUDA;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel, threads, smem) != cudaSuccess || per_sm < 1)
-    return AAB_ERR_CUDA;
-  if (per_sm > 8) per_sm = 8;
-  const long total_chunks = static_cast<long>(chunks) * samples;
-  long grid_l = static_cast<long>(per_sm) * sms;
-  if (grid_l > total_chunks) grid_l = total_chunks;
-  int chunks_i = chunks, total_i = static_cast<int>(total_chunks);
-  void* args[] = {&a, &partial, &mean_rstd, &ticket, &flag, &done, const_cast<float**>(&gamma), const_cast<float**>(&beta),
-                  &silu, &y, &ldy, &eps, &chunks_i, &total_i};
-  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(gn_fused_kernel),
-                                              dim3(static_cast<unsigned>(grid_l)), dim3(threads), args, smem, stream);
-  return e == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
+  // A fused single-launch variant (cooperative grid: statistics -> per-sample flag -> apply) was built and measured in
+  // round 2 and LOST to this pair in every shape (profiles/r02_kernel_ab_fusedGN_LNv2_TAv2.md vs ..._round1_kernels.md:
+  // 84 vs 72 us at [34, 4096, 320], 38 vs 24 us at [34, 256, 1280]): the flag wait serialises the two phases inside every
+  // CTA, while two plain launches let the hardware overlap the tail of one with the head of the next.  Not kept.
+  dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(samples));
+  gn_stats_kernel<<<grid, threads, smem, stream>>>(a, partial, mean_rstd, ticket, eps);
+  gn_apply_kernel<<<grid, threads, 0, stream>>>(a, mean_rstd, gamma, beta, silu, y, ldy);
+  return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }
 
 template <int OPL, int R>

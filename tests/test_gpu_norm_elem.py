@@ -36,8 +36,8 @@ def test_groupnorm(dtype, samples, rows, c, silu):
 
 @pytest.mark.parametrize("samples,rows,c", [(34, 4096, 320), (2, 69632, 320), (2, 1088, 1280), (34, 64, 2560)])
 def test_groupnorm_benchmarked_shapes_and_repeat(samples, rows, c):
-    """The extents of a config-2 UNet forward (2-D per frame, 3-D per clip, more chunks than resident CTAs): the fused
-    kernel's flags / tickets must come back to zero, so a SECOND call through the same workspace gives the same bits."""
+    """The extents of a config-2 UNet forward (2-D per frame, 3-D per clip) through ONE shared workspace: the tickets must
+    come back to zero and must not alias another call's statistics (fixed header), so a SECOND call gives the same bits."""
     from animate_anything_b200 import ops
     dtype = torch.bfloat16
     x = _rand((samples * rows, c), dtype, 1.5, 1, shift=0.3)
