@@ -389,6 +389,84 @@ __global__ void svd_out_finalize_kernel(const float* __restrict__ y, int ldc, vo
   store_elem(out, i, y[((n * H + yy) * W + x) * ldc + c], BF16);
 }
 
+// SVD loop, input side (models/pipeline.py:418-422): latent_model_input = cat([latents] * 2) / sqrt(sigma^2 + 1)
+// (EulerDiscreteScheduler.scale_model_input), then cat([mask, latent_model_input, image_latents], dim=2) with the
+// unconditional half seeing ZERO image latents (_encode_vae_image) -> channels-last [2B*F, h, w, 16] (9 used).
+// x [B, F, 4, h, w]; img_lat [B, 4, h, w] (positive half); mask [h, w]; `cfg` = 1: two halves, 0: one.
+template <bool BF16>
+__global__ void svd_in_assemble_kernel(const void* __restrict__ x, const void* __restrict__ img_lat, const void* __restrict__ mask,
+                                       float inv_scale, void* __restrict__ out, int B, int F, int H, int W, int cfg) {
+  const long per_half = static_cast<long>(B) * F * H * W;
+  const long total = per_half * (cfg ? 2 : 1) * 2;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int half8 = i & 1;                       // which 8-channel octet of the 16
+  long r = i >> 1;
+  const int cond = (cfg && r >= per_half) ? 1 : (cfg ? 0 : 1);
+  if (r >= per_half) r -= per_half;
+  const int xx = r % W;
+  long q = r / W;
+  const int yy = q % H;
+  q /= H;
+  const int f = q % F;
+  const int b = q / F;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = half8 * 8 + j;
+    float val = 0.f;
+    if (c == 0) {
+      val = load_elem(mask, static_cast<long>(yy) * W + xx, BF16);
+    } else if (c <= 4) {
+      // torch: 16-bit tensor / 0-d fp32 tensor -> computed in fp32, rounded once to the 16-bit dtype
+      val = load_elem(x, (((static_cast<long>(b) * F + f) * 4 + (c - 1)) * H + yy) * W + xx, BF16) * inv_scale;
+    } else if (c <= 8) {
+      val = cond ? load_elem(img_lat, ((static_cast<long>(b) * 4 + (c - 5)) * H + yy) * W + xx, BF16) : 0.f;
+    }
+    v[j] = val;
+  }
+  reinterpret_cast<uint4*>(out)[i] =
+      make_uint4(pack2(v[0], v[1], BF16), pack2(v[2], v[3], BF16), pack2(v[4], v[5], BF16), pack2(v[6], v[7], BF16));
+}
+
+// SVD loop, output side (models/pipeline.py:433-439): per-frame classifier-free guidance
+//   v = v_u + g_f (v_c - v_u), g_f = linspace(min, max, F)[f]      (16-bit roundings of every op, as torch does on fp16)
+// then EulerDiscreteScheduler.step with v-prediction in fp32:
+//   x0 = v * (-sigma / sqrt(sigma^2 + 1)) + x / (sigma^2 + 1);  x' = x + (x - x0) / sigma * (sigma_next - sigma)
+// pred: fp32 [2B*F*h*w, ldc] channels-last straight from conv_out (rows: uncond half then cond half); x, x_out [B, F, 4, h, w].
+template <bool BF16>
+__global__ void svd_cfg_euler_step_kernel(const float* __restrict__ pred, int ldc, int cfg, const float* __restrict__ gs,
+                                          const void* __restrict__ x, void* __restrict__ x_out, float sigma, float sigma_next,
+                                          int B, int F, int H, int W) {
+  const long total = static_cast<long>(B) * F * 4 * H * W;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int xx = i % W;
+  long r = i / W;
+  const int yy = r % H;
+  r /= H;
+  const int c = r % 4;
+  r /= 4;
+  const int f = r % F;
+  const int b = r / F;
+  const long row = ((static_cast<long>(b) * F + f) * H + yy) * W + xx;
+  const long per_half = static_cast<long>(B) * F * H * W;
+  float v;
+  if (cfg) {
+    const float vu = round16(pred[row * ldc + c], BF16);                  // the UNet's 16-bit output
+    const float vc = round16(pred[(per_half + row) * ldc + c], BF16);
+    const float g = round16(gs[f], BF16);                                 // guidance_scale.to(latents.dtype)
+    v = round16(vu + round16(g * round16(vc - vu, BF16), BF16), BF16);
+  } else {
+    v = round16(pred[row * ldc + c], BF16);
+  }
+  const float xs = load_elem(x, i, BF16);                                 // sample.to(float32)
+  const float s2 = sigma * sigma + 1.0f;
+  const float x0 = v * (-sigma / sqrtf(s2)) + xs / s2;
+  const float d = (xs - x0) / sigma;
+  store_elem(x_out, i, xs + d * (sigma_next - sigma), BF16);
+}
+
 // encoder tail: conv_out result [N, h, w, ldm] (8 ch) -> quant_conv (1x1, 8->8) -> moments [N, 8, h, w] (NCHW, 16-bit)
 // (AutoencoderKL.encode: `moments = self.quant_conv(h)`; DiagonalGaussianDistribution.mode() is channels 0..3)
 template <bool BF16>
@@ -722,6 +800,30 @@ extern "C" int aab_svd_out_finalize(const float* y, int ldc, void* out, long bf,
   const long total = bf * 4 * h * w;
   if (is_bf16) svd_out_finalize_kernel<true><<<AAB_GRID(total, 256), 256, 0, stream>>>(y, ldc, out, bf, h, w);
   else svd_out_finalize_kernel<false><<<AAB_GRID(total, 256), 256, 0, stream>>>(y, ldc, out, bf, h, w);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_svd_in_assemble(const void* x, const void* img_lat, const void* mask, float inv_scale, void* out, int b, int f,
+                                   int h, int w, int cfg, int is_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !img_lat || !mask || !out) return AAB_ERR_ARG;
+  const long total = static_cast<long>(b) * f * h * w * (cfg ? 2 : 1) * 2;
+  if (is_bf16) svd_in_assemble_kernel<true><<<AAB_GRID(total, 256), 256, 0, stream>>>(x, img_lat, mask, inv_scale, out, b, f, h, w, cfg);
+  else svd_in_assemble_kernel<false><<<AAB_GRID(total, 256), 256, 0, stream>>>(x, img_lat, mask, inv_scale, out, b, f, h, w, cfg);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_svd_cfg_euler_step(const float* pred, int ldc, int cfg, const float* gs, const void* x, void* x_out,
+                                      float sigma, float sigma_next, int b, int f, int h, int w, int is_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!pred || !x || !x_out || (cfg && !gs) || ldc < 4 || sigma <= 0.f) return AAB_ERR_ARG;
+  const long total = static_cast<long>(b) * f * 4 * h * w;
+  if (is_bf16)
+    svd_cfg_euler_step_kernel<true><<<AAB_GRID(total, 256), 256, 0, stream>>>(pred, ldc, cfg, gs, x, x_out, sigma, sigma_next, b,
+                                                                             f, h, w);
+  else
+    svd_cfg_euler_step_kernel<false><<<AAB_GRID(total, 256), 256, 0, stream>>>(pred, ldc, cfg, gs, x, x_out, sigma, sigma_next, b,
+                                                                              f, h, w);
   AAB_LAUNCH_RET();
 }
 

@@ -482,6 +482,25 @@ def svd_out_finalize(y: torch.Tensor, b: int, f: int, h: int, w: int, dtype) -> 
     return out
 
 
+def svd_in_assemble(x: torch.Tensor, img_lat: torch.Tensor, mask: torch.Tensor, sigma: float, cfg: bool) -> torch.Tensor:
+    """x [B, F, 4, h, w], img_lat [B, 4, h, w], mask [h, w] (same 16-bit dtype) -> UNet input [(2)B*F, h, w, 16]."""
+    b, f, _, h, w = x.shape
+    assert x.is_contiguous() and img_lat.is_contiguous() and mask.is_contiguous() and mask.numel() == h * w
+    out = torch.empty(((2 if cfg else 1) * b * f, h, w, 16), device=x.device, dtype=x.dtype)
+    _lib.call("aab_svd_in_assemble", _ptr(x), _ptr(img_lat), _ptr(mask), 1.0 / math.sqrt(sigma * sigma + 1.0), _ptr(out), b, f,
+              h, w, int(cfg), _is_bf16(x), _stream())
+    return out
+
+
+def svd_cfg_euler_step(pred: torch.Tensor, cfg: bool, gs: Optional[torch.Tensor], x: torch.Tensor, sigma: float,
+                       sigma_next: float) -> torch.Tensor:
+    b, f, _, h, w = x.shape
+    out = torch.empty_like(x)
+    _lib.call("aab_svd_cfg_euler_step", _ptr(pred), pred.stride(0), int(cfg), _ptr(gs), _ptr(x), _ptr(out), float(sigma),
+              float(sigma_next), b, f, h, w, _is_bf16(x), _stream())
+    return out
+
+
 def vae_enc_finalize(mom: torch.Tensor, wq, bq, scale, b, f, h, w) -> torch.Tensor:
     """conv_out output [b*f*h*w, >=8] -> quant_conv -> moments [b, 8, f, h, w]."""
     out = torch.empty((b, 8, f, h, w), device=mom.device, dtype=mom.dtype)

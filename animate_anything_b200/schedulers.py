@@ -242,3 +242,76 @@ class DPMSolverMultistepScheduler(_Base):
                 lower_order_nums += 1
             step_index += 1
         return np.asarray(rows, dtype=np.float32), True
+
+
+class EulerDiscreteScheduler(_Base):
+    """Host side of diffusers' EulerDiscreteScheduler as Stable Video Diffusion configures it (v-prediction, Karras sigmas,
+    continuous timesteps 0.25 * log(sigma), "leading" spacing; called at models/pipeline.py:412,418,439).  The arithmetic of
+    `scale_model_input` / `step` runs in `aab_svd_in_assemble` / `aab_svd_cfg_euler_step`; this class owns the sigma and
+    timestep tables (float32, same construction order as diffusers so that the values agree bit for bit with the oracle)."""
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
+                 prediction_type="epsilon", interpolation_type="linear", use_karras_sigmas=False, sigma_min=None,
+                 sigma_max=None, timestep_spacing="linspace", timestep_type="discrete", steps_offset=0):
+        self._capture(locals())
+        self._init_tables()
+        import numpy as np
+        sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sigmas = torch.from_numpy(sig[::-1].copy()).to(dtype=torch.float32)
+        self.sigmas = torch.cat([sigmas, torch.zeros(1)])
+        self.timesteps = (torch.Tensor([0.25 * s.log() for s in sigmas]) if self._continuous_v() else
+                          torch.from_numpy(np.linspace(0, num_train_timesteps - 1, num_train_timesteps, dtype=float)[::-1].copy()
+                                           ).to(torch.float32))
+        self.num_inference_steps = None
+
+    def _continuous_v(self):
+        return self.config.timestep_type == "continuous" and self.config.prediction_type == "v_prediction"
+
+    @property
+    def init_noise_sigma(self):
+        m = self.sigmas.max()
+        if self.config.timestep_spacing in ("linspace", "trailing"):
+            return m
+        return (m ** 2 + 1) ** 0.5
+
+    def set_timesteps(self, num_inference_steps, device=None):
+        import numpy as np
+        c = self.config
+        n = c.num_train_timesteps
+        self.num_inference_steps = num_inference_steps
+        if c.timestep_spacing == "linspace":
+            ts = np.linspace(0, n - 1, num_inference_steps, dtype=np.float32)[::-1].copy()
+        elif c.timestep_spacing == "leading":
+            ts = (np.arange(0, num_inference_steps) * (n // num_inference_steps)).round()[::-1].copy().astype(np.float32)
+            ts += c.steps_offset
+        else:
+            ts = (np.arange(n, 0, -n / num_inference_steps)).round().copy().astype(np.float32) - 1
+        sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        log_sig = np.log(sig)
+        sig = np.interp(ts, np.arange(0, len(sig)), sig)
+        if c.use_karras_sigmas:
+            smin = c.sigma_min if c.sigma_min is not None else sig[-1].item()
+            smax = c.sigma_max if c.sigma_max is not None else sig[0].item()
+            ramp = np.linspace(0, 1, num_inference_steps)
+            sig = (smax ** (1 / 7.0) + ramp * (smin ** (1 / 7.0) - smax ** (1 / 7.0))) ** 7.0
+            ts = np.array([self._sigma_to_t(s_, log_sig) for s_ in sig])
+        sigmas = torch.from_numpy(sig).to(dtype=torch.float32)
+        if self._continuous_v():
+            self.timesteps = torch.Tensor([0.25 * s_.log() for s_ in sigmas]).to(device=device)
+        else:
+            self.timesteps = torch.from_numpy(np.asarray(ts, dtype=np.float32)).to(device=device)
+        self.sigmas = torch.cat([sigmas, torch.zeros(1)])
+
+    @staticmethod
+    def _sigma_to_t(sigma, log_sigmas):
+        import numpy as np
+        log_sigma = np.log(np.maximum(sigma, 1e-10))
+        dists = log_sigma - log_sigmas[:, np.newaxis]
+        low_idx = np.cumsum((dists >= 0), axis=0).argmax(axis=0).clip(max=log_sigmas.shape[0] - 2)
+        high_idx = low_idx + 1
+        low, high = log_sigmas[low_idx], log_sigmas[high_idx]
+        w = np.clip((low - log_sigma) / (low - high), 0, 1)
+        return ((1 - w) * low_idx + w * high_idx).reshape(sigma.shape)
+
+    def step_coefficients(self, *a, **k):
+        raise NotImplementedError("Euler steps are fused in aab_svd_cfg_euler_step (pipeline_svd.py)")

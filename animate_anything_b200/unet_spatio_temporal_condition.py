@@ -508,14 +508,19 @@ class UNetSpatioTemporalConditionModel(ModelBase):
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, sample: torch.Tensor, timestep, encoder_hidden_states: torch.Tensor, added_time_ids: torch.Tensor,
-                return_dict: bool = True, _raw: bool = False):
+                return_dict: bool = True, _raw: bool = False, _x16: Optional[torch.Tensor] = None, _shape=None):
+        """`_x16` / `_shape` (used by the fused SVD loop, pipeline_svd.py): the channels-last, 16-channel-padded input
+        [B*F, h, w, 16] already assembled by `aab_svd_in_assemble`, with `_shape` = (B, F, C, h, w); `sample` is ignored."""
         prep = self._prepared()
         own = prep.get(self)
         dt, dev = prep.dtype, prep.device
         cfg = self.config
-        if sample.dim() != 5 or sample.shape[2] != cfg.in_channels:
-            raise ValueError(f"sample must be [batch, frames, {cfg.in_channels}, height, width], got {tuple(sample.shape)}")
-        b, nf, c, h, w = sample.shape
+        if _x16 is not None:
+            b, nf, c, h, w = _shape
+        else:
+            if sample.dim() != 5 or sample.shape[2] != cfg.in_channels:
+                raise ValueError(f"sample must be [batch, frames, {cfg.in_channels}, height, width], got {tuple(sample.shape)}")
+            b, nf, c, h, w = sample.shape
         if any(s % (2 ** self.num_upsamplers) for s in (h, w)):
             raise ValueError("latent height/width must be multiples of 2**num_upsamplers (diffusers' SVD UNet has no "
                              "upsample_size path either)")
@@ -525,7 +530,6 @@ class UNetSpatioTemporalConditionModel(ModelBase):
             raise ValueError(
                 f"Model expects an added time embedding vector of length {cfg.projection_class_embeddings_input_dim}, but a "
                 f"vector of {added_time_ids.shape[-1] * cfg.addition_time_embed_dim} was created.")
-        sample = sample.to(dt)
         g = E.Geo(b, nf, h, w)
         ctx = E.Ctx(prep, g)
         ctx.fuse_geglu = self.fuse_geglu
@@ -549,7 +553,7 @@ class UNetSpatioTemporalConditionModel(ModelBase):
         semb = ops.linear(h2, ae["l2"][0], ae["l2"][1], residual=e1, act=ops.ACT_SILU)     # silu(emb + aug_emb)
         ctx.temb_all = ops.linear(semb, own["temb_w"], own["temb_b"], out_f32=True)
 
-        x16 = ops.image_to_nhwc16(sample.reshape(b * nf, c, h, w))
+        x16 = _x16 if _x16 is not None else ops.image_to_nhwc16(sample.to(dt).reshape(b * nf, c, h, w))
         x = ops.conv3x3(x16, own["conv_in"][0], own["conv_in"][1])
         trace = self.__dict__.get("_trace")
         if trace is not None:

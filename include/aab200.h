@@ -87,6 +87,12 @@ int aab_add_rowvec(const void* x, long ldx, void* out, long ldo, const float* ve
                    long rows_per_vec, int mod, int mode, int mod2, int is_bf16, void* stream);
 int aab_axpby(const void* x, const void* y, void* out, long n_elems, float a, float b, int is_bf16, void* stream);
 int aab_svd_out_finalize(const float* y, int ldc, void* out, long bf, int h, int w, int is_bf16, void* stream);
+/* SVD loop boundary kernels (models/pipeline.py:416-439): scale_model_input + CFG duplication + 9-channel cat in one pass;
+ * per-frame guidance + Euler step (v-prediction) in one pass.  gs: fp32 [f] = linspace(min, max, f) (:405-408). */
+int aab_svd_in_assemble(const void* x, const void* img_lat, const void* mask, float inv_scale, void* out, int b, int f, int h,
+                        int w, int cfg, int is_bf16, void* stream);
+int aab_svd_cfg_euler_step(const float* pred, int ldc, int cfg, const float* gs, const void* x, void* x_out, float sigma,
+                           float sigma_next, int b, int f, int h, int w, int is_bf16, void* stream);
 
 /* Unfused fallbacks / helpers: GEGLU gate (diffusers GEGLU.forward), nearest 2x upsample (Upsample2D), copies. */
 int aab_geglu(const void* x, long ldx, void* out, long ldo, long rows, int nh, int is_bf16, void* stream);

@@ -94,3 +94,86 @@ def test_svd_unet_rejects_bad_inputs():
         ours(x[:, :, :8], 1.0, e, torch.zeros(1, 3, device="cuda"))     # 8 instead of 9 input channels
     with pytest.raises(ValueError):
         ours(x[..., :20], 1.0, e, torch.zeros(1, 3, device="cuda"))     # width 20: not a multiple of 8
+
+
+SVD_VAE = dict(block_out_channels=(64, 64, 128, 128), layers_per_block=1)
+
+
+def _vae_pair(dtype):
+    from oracle.composition import AutoencoderKLTemporalDecoder as OVAE, fill_deterministic
+    from animate_anything_b200.autoencoder_kl_temporal_decoder import AutoencoderKLTemporalDecoder
+    ovae = fill_deterministic(OVAE(**SVD_VAE).eval(), seed=1)
+    sd16 = {k: v.to(dtype) for k, v in ovae.state_dict().items()}
+    ovae.load_state_dict({k: v.float() for k, v in sd16.items()})
+    vae = AutoencoderKLTemporalDecoder(**SVD_VAE).eval()
+    vae.load_state_dict(sd16, strict=True)
+    return ovae.cuda(), vae.to(dtype).cuda()
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_svd_temporal_vae(dtype):
+    """AutoencoderKLTemporalDecoder: encode (mode) and chunked temporal decode against the oracle restatement."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    ovae, vae = _vae_pair(dtype)
+    g = torch.Generator().manual_seed(4)
+    img = torch.randn(1, 3, 64, 96, generator=g).clamp(-1, 1).to(dtype).cuda()
+    z = torch.randn(5, 4, 8, 12, generator=g).to(dtype).cuda()
+    with torch.no_grad():
+        r_enc = ovae.encode(img.float()).latent_dist.mode()
+        r_dec = ovae.decode(z.float(), num_frames=5).sample
+        o16 = ovae.to(dtype)
+        s_enc = o16.encode(img).latent_dist.mode().float()
+        s_dec = o16.decode(z, num_frames=5).sample.float()
+    enc = vae.encode(img).latent_dist.mode()
+    dec = vae.decode(z, num_frames=5).sample
+    vid = vae.decode_chunk_video(z, 5)
+    assert dec.shape == r_dec.shape == (5, 3, 64, 96) and dec.dtype == dtype
+    assert torch.equal(vid[0].permute(1, 0, 2, 3).to(dtype), dec)
+    case = f"SVD temporal VAE {str(dtype).split('.')[-1]}"
+    assert_vs_stock(record_parity(case, "encode", enc, r_enc, s_enc), max_factor=2.5)
+    assert_vs_stock(record_parity(case, "decode 5 frames", dec, r_dec, s_dec), max_factor=2.5)
+
+
+def test_svd_pipeline_loop_matches_oracle():
+    """MaskStableVideoDiffusionPipeline.__call__ mirror (fused input assembly, UNet, fused per-frame CFG + Euler step,
+    chunked temporal decode) against `oracle_svd_sampling_loop` (pinned to the verbatim reference pipeline on CPU)."""
+    from oracle.composition import EulerDiscreteScheduler as OEuler, SVD_SCHED, oracle_svd_sampling_loop
+    from animate_anything_b200.pipeline_svd import MaskStableVideoDiffusionPipeline
+    from animate_anything_b200.schedulers import EulerDiscreteScheduler
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dtype = torch.float16
+    ounet, unet = _pair(dtype)
+    ovae, vae = _vae_pair(dtype)
+    g = torch.Generator().manual_seed(6)
+    img = torch.randn(1, 3, 128, 192, generator=g).clamp(-1, 1)
+    mask = (torch.rand(1, 16, 24, generator=g) > 0.5).float()
+    lat0 = torch.randn(1, 6, 4, 16, 24, generator=g)
+    emb = torch.randn(1, 1, 96, generator=g)
+    pipe = MaskStableVideoDiffusionPipeline(vae=vae, image_encoder=None, unet=unet, scheduler=EulerDiscreteScheduler(**SVD_SCHED))
+    kw = dict(height=128, width=192, num_frames=6, num_inference_steps=3, decode_chunk_size=3, noise_aug_strength=0.0,
+              latents=lat0, mask=mask, image_embeddings=emb, return_dict=False)
+    frames = pipe(img, output_type="pt", **kw)
+    lat = pipe(img, output_type="latent", **kw)
+    torch.cuda.synchronize()
+    assert pipe.last_gpu_launches > 500
+    with torch.no_grad():
+        il32 = ovae.encode(img.to(dtype).float().cuda()).latent_dist.mode()
+        rf, rl = oracle_svd_sampling_loop(ounet, OEuler(**SVD_SCHED), ovae, emb.to(dtype).float().cuda(), il32, mask.cuda(),
+                                          lat0.to(dtype).float().cuda(), num_inference_steps=3, noise_aug_strength=0.0,
+                                          decode_chunk_size=3)
+        o16u, o16v = ounet.to(dtype), ovae.to(dtype)
+        il16 = o16v.encode(img.to(dtype).cuda()).latent_dist.mode()
+        sf, sl = oracle_svd_sampling_loop(o16u, OEuler(**SVD_SCHED), o16v, emb.to(dtype).cuda(), il16, mask.to(dtype).cuda(),
+                                          lat0.to(dtype).cuda(), num_inference_steps=3, noise_aug_strength=0.0,
+                                          decode_chunk_size=3)
+    assert lat.shape == rl.shape == (1, 6, 4, 16, 24)
+    case = "SVD pipeline fp16 3 Euler steps"
+    assert_vs_stock(record_parity(case, "latents", lat, rl, sl), mean_factor=3.0, max_factor=4.0, mean_floor=5e-4,
+                    max_floor=5e-3)
+    got = frames[0]                                         # [F, 3, H, W] in [0, 1]
+    want = (rf[0].permute(1, 0, 2, 3) / 2 + 0.5).clamp(0, 1)
+    stock = (sf[0].permute(1, 0, 2, 3) / 2 + 0.5).clamp(0, 1)
+    assert_vs_stock(record_parity(case, "frames", got, want, stock), mean_factor=3.0, max_factor=4.0, mean_floor=2e-3,
+                    max_floor=2e-2)
