@@ -342,23 +342,31 @@ flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 // warpgroup (4 warps, one per SM sub-partition) works on S(j), so the exp2 (MUFU) pipe — the real bound of d=64
 // attention on Blackwell — never waits for an MMA.  The O_j = P_j.V_j read-back is deferred by one block.
 //   TMEM columns: S0 [0,128)  S1 [128,256)  O_j [256,320)
+// SHORT = true (round 2): the key/value sequence fits ONE 128-key block (text cross-attention: 77 tokens).  One K/V stage,
+// 256 TMEM columns (S at 0, O at 128) and 80 KiB of shared memory let two or three CTAs share an SM, so the prologue /
+// load / softmax latencies of one CTA overlap the others' -- v1 (one 192 KiB CTA per SM) spent 160 us on 54 us of work.
 constexpr int FA2_THREADS = 192;      // warp0 TMA, warp1 MMA, warps 2-5 softmax
 constexpr int FA2_SMEM_BYTES = FA_TILE_BYTES + FA_KV_STAGES * 2 * FA_TILE_BYTES + 2 * FA_TILE_BYTES + 1024 + 256;
+constexpr int FA2S_SMEM_BYTES = FA_TILE_BYTES + 1 * 2 * FA_TILE_BYTES + 2 * FA_TILE_BYTES + 1024 + 256;
 
-__global__ void __launch_bounds__(FA2_THREADS, 1)
+template <bool SHORT>
+__global__ void __launch_bounds__(FA2_THREADS, SHORT ? 2 : 1)
 flash_attn_d64_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, const FaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int KVS = SHORT ? 1 : FA_KV_STAGES;
+  constexpr uint32_t TCOLS = SHORT ? 256 : 512;
+  constexpr uint32_t O_COL = SHORT ? 128 : 256;
   uint8_t* smQ = smem;
   uint8_t* smK = smQ + FA_TILE_BYTES;
-  uint8_t* smV = smK + FA_KV_STAGES * FA_TILE_BYTES;
-  uint8_t* smP = smV + FA_KV_STAGES * FA_TILE_BYTES;      // two 64-key halves
+  uint8_t* smV = smK + KVS * FA_TILE_BYTES;
+  uint8_t* smP = smV + KVS * FA_TILE_BYTES;      // two 64-key halves
   uint64_t* bars = reinterpret_cast<uint64_t*>(smP + 2 * FA_TILE_BYTES);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = kv_full + FA_KV_STAGES;
-  uint64_t* s_full = kv_empty + FA_KV_STAGES;   // 2
+  uint64_t* kv_empty = kv_full + KVS;
+  uint64_t* s_full = kv_empty + KVS;   // 2
   uint64_t* s_free = s_full + 2;                // 2 (128 arrivals)
   uint64_t* p_ready = s_free + 2;               // 1 (128 arrivals)
   uint64_t* p_free = p_ready + 1;               // 1
@@ -382,7 +390,7 @@ flash_attn_d64_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   if (warp == 1) {
     if (elect_one()) {
       mbar_init(q_full, 1);
-      for (int i = 0; i < FA_KV_STAGES; ++i) {
+      for (int i = 0; i < KVS; ++i) {
         mbar_init(&kv_full[i], 1);
         mbar_init(&kv_empty[i], 1);
       }
@@ -397,7 +405,7 @@ flash_attn_d64_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, TCOLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -410,8 +418,8 @@ flash_attn_d64_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       mbar_arrive_expect_tx(q_full, FA_TILE_BYTES);
       tma_load_3d(smQ, &tmQ, q_full, p.q_col0 + head * 64, q0, b);
       for (int j = 0; j < nkv; ++j) {
-        const int s = j % FA_KV_STAGES;
-        const uint32_t ph = (j / FA_KV_STAGES) & 1;
+        const int s = j % KVS;
+        const uint32_t ph = (j / KVS) & 1;
         mbar_wait(&kv_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&kv_full[s], 2 * FA_TILE_BYTES);
         tma_load_3d(smK + s * FA_TILE_BYTES, &tmK, &kv_full[s], p.k_col0 + head * 64, j * 128, bkv);
@@ -424,7 +432,7 @@ flash_attn_d64_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     auto issue_s = [&](int jj) {
       if (elect_one()) {
         const uint32_t qa = smem_u32(smQ);
-        const uint32_t ka = smem_u32(smK + (jj % FA_KV_STAGES) * FA_TILE_BYTES);
+        const uint32_t ka = smem_u32(smK + (jj % KVS) * FA_TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16_ss(tmem_base + (jj & 1) * 128, make_desc_kmajor_sw128(qa + k * 32),
@@ -439,7 +447,7 @@ flash_attn_d64_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     issue_s(0);
     for (int j = 0; j < nkv; ++j) {
       if (j + 1 < nkv) {                      // S(j+1) into the other buffer while the softmax works on S(j)
-        mbar_wait(&kv_full[(j + 1) % FA_KV_STAGES], ((j + 1) / FA_KV_STAGES) & 1);
+        mbar_wait(&kv_full[(j + 1) % KVS], ((j + 1) / KVS) & 1);
         if (j >= 1) mbar_wait(&s_free[(j + 1) & 1], ((j - 1) >> 1) & 1);   // softmax(j-1) has read that buffer
         tc_fence_after();
         issue_s(j + 1);
@@ -449,14 +457,14 @@ flash_attn_d64_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tc_fence_after();
       if (elect_one()) {
         const uint32_t pa = smem_u32(smP);
-        const uint32_t va = smem_u32(smV + (j % FA_KV_STAGES) * FA_TILE_BYTES);
+        const uint32_t va = smem_u32(smV + (j % KVS) * FA_TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_f16_ss(tmem_base + 256, make_desc_kmajor_sw128(pa + (k >> 2) * FA_TILE_BYTES + (k & 3) * 32),
+          umma_f16_ss(tmem_base + O_COL, make_desc_kmajor_sw128(pa + (k >> 2) * FA_TILE_BYTES + (k & 3) * 32),
                       make_desc_mnmajor_sw128(va + k * 2048, 8192), idesc_o, k > 0 ? 1u : 0u);
         umma_commit(o_full);
         umma_commit(p_free);
-        umma_commit(&kv_empty[j % FA_KV_STAGES]);
+        umma_commit(&kv_empty[j % KVS]);
       }
       __syncwarp();
     }
@@ -464,7 +472,7 @@ flash_attn_d64_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     const int qd = warp & 3;
     const int row = qd * 32 + lane_id();
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
-    const uint32_t t_o = tmem_base + 256 + lane_off;
+    const uint32_t t_o = tmem_base + O_COL + lane_off;
     uint8_t* prow = smP + row * 128;
     float o_acc[64];
 #pragma unroll
@@ -565,7 +573,7 @@ flash_attn_d64_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, TCOLS);
   }
 }
 
@@ -980,14 +988,26 @@ extern "C" int aab_flash_attn_d64(const void* q, long ldq, long q_batch_stride, 
     const char* e = getenv("AAB_FLASH_V2");
     use_v1 = (e && e[0] == '1') ? 0 : 1;
   }
+  static int no_short = -1;               // AAB_FLASH_NO_SHORT=1: round-1 behaviour (A/B measurements)
+  if (no_short < 0) {
+    const char* e = getenv("AAB_FLASH_NO_SHORT");
+    no_short = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (lk <= 128 && !causal && !no_short) {      // one K/V block: the multi-CTA-per-SM variant
+    static std::atomic<unsigned long long> attr_s{0};
+    if (int r = ensure_dyn_smem(flash_attn_d64_v2_kernel<true>, FA2S_SMEM_BYTES, attr_s)) return r;
+    dim3 grid((lq + 127) / 128, heads, nb);
+    flash_attn_d64_v2_kernel<true><<<grid, FA2_THREADS, FA2S_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+    return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
+  }
   if (use_v1 || causal) {       // two query tiles per CTA (two softmax warpgroups), S single-buffered
     dim3 grid((lq + 255) / 256, heads, nb);
     flash_attn_d64_kernel<<<grid, FA_THREADS, FA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   } else {
     static std::atomic<unsigned long long> attr2_done{0};
-    if (int r = ensure_dyn_smem(flash_attn_d64_v2_kernel, FA2_SMEM_BYTES, attr2_done)) return r;
+    if (int r = ensure_dyn_smem(flash_attn_d64_v2_kernel<false>, FA2_SMEM_BYTES, attr2_done)) return r;
     dim3 grid((lq + 127) / 128, heads, nb);
-    flash_attn_d64_v2_kernel<<<grid, FA2_THREADS, FA2_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+    flash_attn_d64_v2_kernel<false><<<grid, FA2_THREADS, FA2_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   }
   return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }

@@ -593,6 +593,80 @@ def latency_breakdown(pipe, runner, devin, dev, rank, world, lat_split, frames_s
     return info
 
 
+def run_svd(args):
+    """BASELINE config 4 (opt-in: `--workload svd`; the driver's default line stays config 2): the SVD path of
+    train_svd.py:756-777 -- MaskStableVideoDiffusionPipeline.__call__, 25 frames x 576 x 1024, 25 Euler steps, per-frame
+    CFG 1 -> 3, full-size random-init UNetSpatioTemporalConditionModel (9 input channels) + AutoencoderKLTemporalDecoder,
+    bf16, 1 GPU.  The CLIP vision tower is outside the hot path: a synthetic image embedding is passed in."""
+    import torch
+    from animate_anything_b200 import _lib
+    from animate_anything_b200.autoencoder_kl_temporal_decoder import AutoencoderKLTemporalDecoder
+    from animate_anything_b200.pipeline_svd import MaskStableVideoDiffusionPipeline
+    from animate_anything_b200.schedulers import EulerDiscreteScheduler
+    from animate_anything_b200.unet_spatio_temporal_condition import UNetSpatioTemporalConditionModel
+    from oracle.composition import SVD_SCHED
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    dtype = torch.bfloat16
+    nf, hh, ww, steps = 25, 576, 1024, 25
+    torch.manual_seed(0)
+    with torch.device(dev):
+        unet = UNetSpatioTemporalConditionModel(in_channels=9, sample_size=96)
+        vae = AutoencoderKLTemporalDecoder()
+    with torch.no_grad():
+        for n, p in unet.named_parameters():
+            if p.abs().max() == 0:
+                p.normal_(0.0, 0.02)
+    pipe = MaskStableVideoDiffusionPipeline(vae=vae.to(dtype).eval(), image_encoder=None, unet=unet.to(dtype).eval(),
+                                            scheduler=EulerDiscreteScheduler(**SVD_SCHED))
+    g = torch.Generator().manual_seed(7)
+    host = {"image": torch.randn(1, 3, hh, ww, generator=g).clamp(-1, 1).pin_memory(),
+            "mask": (torch.rand(1, hh // 8, ww // 8, generator=g) > 0.5).float().pin_memory(),
+            "latents": torch.randn(1, nf, 4, hh // 8, ww // 8, generator=g).to(dtype).pin_memory(),
+            "emb": torch.randn(1, 1, 1024, generator=g).to(dtype).pin_memory()}
+
+    def clip(inp, output_type="pt"):
+        return pipe(inp["image"], height=hh, width=ww, num_frames=nf, num_inference_steps=steps, decode_chunk_size=8,
+                    latents=inp["latents"], mask=inp["mask"], image_embeddings=inp["emb"], output_type=output_type,
+                    return_dict=False)
+    devin = {k: v.to(dev) for k, v in host.items()}
+    for _ in range(args.warmup):
+        clip(devin)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = _lib.launch_count()
+    t_dev = _ev_ms(lambda: clip(devin), reps=args.steps, warm=0) / 1e3
+    launches = _lib.launch_count() - l0
+
+    def e2e():
+        inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        fr = clip(inp)                                   # list of [F, 3, H, W] in [0, 1] on the device
+        return (fr[0] * 255).to(torch.uint8).cpu()       # the frames leave the device as uint8
+    t_e2e = _ev_ms(e2e, reps=args.steps, warm=0) / 1e3
+    sampler.stop_flag = True
+    # UNet forward alone (B = 2 CFG halves, 25 frames, 72 x 128 latents)
+    from animate_anything_b200 import ops
+    x16 = ops.svd_in_assemble(devin["latents"], torch.zeros(1, 4, hh // 8, ww // 8, device=dev, dtype=dtype),
+                              devin["mask"].to(dtype).reshape(hh // 8, ww // 8).contiguous(), 1.0, True)
+    emb2 = torch.cat([torch.zeros_like(devin["emb"]), devin["emb"]])
+    ids = torch.tensor([[6.0, 127.0, 0.02]] * 2, device=dev)
+    unet_ms = _ev_ms(lambda: pipe.unet(None, 1.0, emb2, ids, _raw=True, _x16=x16, _shape=(2, nf, 9, hh // 8, ww // 8)),
+                     reps=3, warm=1)
+    line = {"metric": "denoised_frames_per_sec_25f_576x1024_25euler_svd", "value": nf / t_dev, "unit": UNIT, "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "config4: MaskStableVideoDiffusionPipeline.__call__ 25x576x1024, 25 Euler steps, per-frame CFG "
+                                   "1->3, random-init UNetSpatioTemporalConditionModel (9-ch) + AutoencoderKLTemporalDecoder, "
+                                   "decode_chunk_size 8; image embedding synthetic (CLIP vision tower outside the hot path)",
+                       "l2_policy": "working set per UNet forward >> 126 MB L2", "cuda_graph": False},
+            "unet_fwd_ms_per_step": unet_ms, "clocks": sampler.summary(),
+            "e2e": {"value": nf / t_e2e, "unit": UNIT, "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()),
+                    "d2h_bytes_per_step": nf * 3 * hh * ww},
+            "gpu_launches": launches}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -606,9 +680,13 @@ def main():
                     help="N>1 only. throughput (default, what the driver's scaling run uses): one clip per GPU. latency: "
                          "BASELINE config 3 -- N=2 one clip with its CFG halves on two GPUs; N=4 four prompts, pairs "
                          "co-located; N=8 four prompts, one batch element per GPU")
+    ap.add_argument("--workload", default="config2", choices=["config2", "svd"],
+                    help="config2 (default, BASELINE's headline) or svd (BASELINE config 4, 1 GPU, this repo's arm only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "svd":
+        run_svd(args)
     else:
         run_product(args)
 

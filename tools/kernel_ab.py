@@ -1,7 +1,7 @@
 """A/B timing of the HBM-bound kernels at the shapes of a config-2 UNet forward (one CUDA graph of 24 calls over rotating input buffers, replay timed with events: GPU-bound like
 the pipeline's graph replay; a call never finds its own input of the previous iteration in L2).  Variants are selected per PROCESS by the env
 switches read in csrc (AAB_GN_TWO_PASS=1, AAB_LN_V1=1, AAB_TATTN_V1=1); run it twice to compare.
-    python tools/kernel_ab.py [gn|ln|ta|all]
+    python tools/kernel_ab.py [gn|ln|ta|fa|all]      (fa: text cross-attention; AAB_FLASH_NO_SHORT=1 = round-1 kernel)
 """
 import os
 import sys
@@ -45,7 +45,7 @@ def timeit(fn, nbuf, iters=24):
     return e0.elapsed_time(e1) / (3 * iters) * 1e3      # us
 
 
-tag = ",".join(k for k in ("AAB_GN_TWO_PASS", "AAB_LN_V1", "AAB_TATTN_V1") if os.environ.get(k) == "1") or "round-2 kernels"
+tag = ",".join(k for k in ("AAB_LN_V1", "AAB_TATTN_V1", "AAB_FLASH_NO_SHORT") if os.environ.get(k) == "1") or "round-2 kernels"
 print(f"variant: {tag}")
 print("| kernel | shape | us / call | algorithmic GB/s | frac of 6485.5 |")
 print("|---|---|---|---|---|")
@@ -81,3 +81,15 @@ if what in ("ta", "all"):
         by = 2.0 * rows * c * 4
         print(f"| temporal_attn_d64 | ({b_}, {t}, {hw}, {heads}) | {us:.1f} | {by / us / 1e3:.0f} | {by / us / 1e3 / HBM:.2f} |")
         del xs
+if what in ("fa", "all"):
+    for nb, heads, lq, lk in [(34, 5, 4096, 77), (34, 10, 1024, 77), (34, 20, 256, 77), (34, 20, 64, 77)]:
+        c = heads * 64
+        nbuf = min(8, max(2, int(300e6 // (nb * lq * c * 2)) + 1))
+        qs = [torch.randn(nb * lq, c, device=dev).to(dt) for _ in range(nbuf)]
+        kv = torch.randn(2 * lk, 2 * c, device=dev).to(dt)
+        us = timeit(lambda i: ops.flash_attn_d64(qs[i], 0, kv, 0, c, nb, lq, lk, heads, kv_batch_div=17), nbuf)
+        by = 2.0 * 2 * nb * lq * c
+        fl = 4.0 * nb * heads * lq * lk * 64
+        print(f"| flash cross-attn | ({nb}, {heads}, {lq}, {lk}) | {us:.1f} | {by / us / 1e3:.0f} | {by / us / 1e3 / HBM:.2f} | "
+              f"{fl / us / 1e6:.0f} TFLOP/s |")
+        del qs
