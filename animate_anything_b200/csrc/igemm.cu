@@ -31,10 +31,14 @@ constexpr int NUM_EPI_GROUPS = 4;                // epilogue warpgroups (4 warps
 constexpr int NUM_THREADS = 32 * (2 + 4 * NUM_EPI_GROUPS);  // warp0 TMA, warp1 MMA, warps 2..17 epilogue
 
 // smem ring depth per tile width: 192 KiB of operands in flight whatever BN
-template <int BN>
+// PAIR (cta_group::2): a cluster of two CTAs computes a 256 x BN tile with ONE tcgen05.mma per K=16 step; each CTA stages its
+// own 128 activation rows and HALF of the weight tile (BN/2 rows), so a stage is 32 KiB instead of 48 and the MMA reads a third
+// less shared memory per FLOP (measured, profiles/r02_umma_rate.log: single-CTA SS-mode N=256 runs at 171 clk per K=16
+// instruction = 75 % of the tensor peak whatever the pipeline does).
+template <int BN, bool PAIR = false>
 struct Cfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGES = PAIR ? 6 : (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
+  static constexpr int B_STAGE_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator stages
   static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 4 /*epilogue groups*/ * OUT_CHUNK_BYTES +
                                     1024 /*align*/ + 512 /*barriers*/;
@@ -73,12 +77,13 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 //      3 = + bias + residual       4 = + bias + per-sample bias (time embedding)       5 = + bias, SiLU
 // The epilogue is written as compact loops (no full unrolling): its instruction footprint is executed once per tile by
 // four warps, and a bloated epilogue thrashes the instruction cache when K is small.
-template <int BN, int EPI>
+template <int BN, int EPI, bool PAIR = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
              const __grid_constant__ CUtensorMap tmR, const IgemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, PAIR>;
+  static_assert(!PAIR || BN == 256, "the CTA-pair variant is built for 256-column tiles");
   constexpr int STAGES = C::STAGES;
   constexpr bool GEGLU = (EPI == 1);
   constexpr int OUT_BN = GEGLU ? BN / 2 : BN;
@@ -100,7 +105,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5;
   const bool bf16 = (p.flags & AAB_F_BF16) != 0;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  // PAIR: the two CTAs of a cluster walk the same list of PAIR tiles (two consecutive m-tiles x one n-tile); CTA rank r owns
+  // m-tile 2 * pm + r.  With an odd number of m-tiles the last pair's second m-tile does not exist: rank 1 then recomputes
+  // m-tile 0 (coordinates wrap) and its epilogue stores nothing.
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  const int tile_first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int num_tiles = (PAIR ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * p.num_n_tiles;
   const int kb_per_tap = p.kb_per_tap;
   const int k_iters = p.num_taps * kb_per_tap;
 
@@ -119,16 +130,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull_bar[i], 1);
-        mbar_init(&tempty_bar[i], 128 * NUM_EPI_GROUPS);
+        // PAIR: the leader's MMA thread waits for the epilogue threads of BOTH CTAs
+        mbar_init(&tempty_bar[i], (PAIR ? 2 : 1) * 128 * NUM_EPI_GROUPS);
       }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, C::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();     // the peer's barriers must be initialised before anything is signalled across the pair
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -138,9 +156,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       WaitTimer w_empty(p.dbg);
       const long long t_start = clock64();
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         const int nt = tile % p.num_n_tiles;
         int mt = tile / p.num_n_tiles;
+        if (PAIR) mt = 2 * mt + static_cast<int>(crank);
         int cb[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -149,6 +168,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         const int bbatch = (p.b_batch_dim >= 0) ? cb[p.b_batch_dim] : 0;
         const int n0 = nt * OUT_BN;
+        // PAIR: this CTA stages rows [crank * n_mma / 2, (crank + 1) * n_mma / 2) of the weight tile (n_mma = valid columns
+        // rounded up to 32); for GEGLU rank 0 holds the value rows and rank 1 the gate rows
+        int nb0 = n0;
+        if (PAIR && !GEGLU) {
+          int nv = p.N - n0;
+          nv = nv < BN ? ((nv + 31) & ~31) : BN;
+          nb0 = n0 + static_cast<int>(crank) * (nv / 2);
+        }
         for (int tap = 0; tap < p.num_taps; ++tap) {
           const int o0 = p.tap_off[tap][0], o1 = p.tap_off[tap][1], o2 = p.tap_off[tap][2], o3 = p.tap_off[tap][3],
                     o4 = p.tap_off[tap][4];
@@ -163,15 +190,30 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               if (!(p.flags & AAB_F_DBG_NO_SYNC)) mbar_arrive(&full_bar[s]);
               continue;
             }
-            mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + C::B_STAGE_BYTES);
             const int kc = kb * BK;
+            const int kg = tap * p.Kc + kc;
+            if (PAIR) {
+              // one expect_tx for the bytes of BOTH CTAs on the leader's barrier; every load of the pair is credited there
+              if (crank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * (A_STAGE_BYTES + C::B_STAGE_BYTES));
+              if (kc < p.Kc1)
+                tma_load_5d_pair(smA + s * A_STAGE_BYTES, &tmA, &full_bar[s], kc + o0, cb[0] + o1, cb[1] + o2, cb[2] + o3,
+                                 cb[3] + o4);
+              else
+                tma_load_5d_pair(smA + s * A_STAGE_BYTES, &tmA2, &full_bar[s], kc - p.Kc1 + o0, cb[0] + o1, cb[1] + o2,
+                                 cb[2] + o3, cb[3] + o4);
+              if (GEGLU)
+                tma_load_3d_pair(smB + s * C::B_STAGE_BYTES, &tmB, &full_bar[s], kg, (crank ? p.N / 2 : 0) + n0, bbatch);
+              else
+                tma_load_3d_pair(smB + s * C::B_STAGE_BYTES, &tmB, &full_bar[s], kg, nb0, bbatch);
+              continue;
+            }
+            mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + C::B_STAGE_BYTES);
             if (kc < p.Kc1)
               tma_load_5d(smA + s * A_STAGE_BYTES, &tmA, &full_bar[s], kc + o0, cb[0] + o1, cb[1] + o2, cb[2] + o3,
                           cb[3] + o4);
             else
               tma_load_5d(smA + s * A_STAGE_BYTES, &tmA2, &full_bar[s], kc - p.Kc1 + o0, cb[0] + o1, cb[1] + o2,
                           cb[2] + o3, cb[3] + o4);
-            const int kg = tap * p.Kc + kc;
             tma_load_3d(smB + s * C::B_STAGE_BYTES, &tmB, &full_bar[s], kg, n0, bbatch);
             if (GEGLU)
               tma_load_3d(smB + s * C::B_STAGE_BYTES + (BN / 2) * 128, &tmB, &full_bar[s], kg, p.N / 2 + n0, bbatch);
@@ -188,7 +230,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // mbarrier wait sat between two k-blocks' MMAs and let the pipe's short queue run dry.  So the NEXT stage's full
     // barrier is peeked (non-blocking test_wait) in the middle of the current k-block's MMAs; when it is already
     // complete -- the common case -- the next k-block's MMAs follow back to back.
-    if (elect_one()) {
+    if ((!PAIR || crank == 0) && elect_one()) {      // PAIR: only the leader CTA issues (for both)
       WaitTimer w_full(p.dbg), w_tempty(p.dbg);
       const bool nosync = (p.flags & AAB_F_DBG_NO_SYNC) != 0;
       const bool nomma = (p.flags & AAB_F_DBG_NO_MMA) != 0;
@@ -198,17 +240,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint32_t it = 0;
       uint32_t tl = 0;
       bool ready = false;   // full barrier of k-block `it` already observed complete
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++tl) {
         const uint32_t as = tl & 1;
         const uint32_t aph = (tl >> 1) & 1;
-        // ragged last N tile: issue the MMA only over the valid columns (multiple of 16); the TMA box of B is
-        // zero-filled beyond N, so no extra traffic either.
+        // ragged last N tile: issue the MMA only over the valid columns (multiple of 16; 32 for a CTA pair, which splits
+        // them between its two CTAs); the TMA box of B is zero-filled beyond N, so no extra traffic either.
         int n_mma = BN;
         if (!GEGLU) {
           const int nvalid = p.N - (tile % p.num_n_tiles) * BN;
-          if (nvalid < BN) n_mma = (nvalid + 15) & ~15;
+          if (nvalid < BN) n_mma = PAIR ? ((nvalid + 31) & ~31) : ((nvalid + 15) & ~15);
         }
-        const uint32_t idesc = make_idesc_f16(bf16 ? 1 : 0, BM, n_mma, 0, 0);
+        const uint32_t idesc = make_idesc_f16(bf16 ? 1 : 0, PAIR ? 2 * BM : BM, n_mma, 0, 0);
         w_tempty.wait(&tempty_bar[as], aph ^ 1);
         const uint32_t tmem_d = tmem_base + as * BN;
         for (int ki = 0; ki < k_iters; ++ki, ++it) {
@@ -233,11 +275,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = make_desc_kmajor_sw128(a_addr + k * 32);
             const uint64_t db = make_desc_kmajor_sw128(b_addr + k * 32);
-            umma_f16_ss(tmem_d, da, db, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+            if (PAIR) umma_f16_ss_pair(tmem_d, da, db, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+            else umma_f16_ss(tmem_d, da, db, idesc, (ki > 0 || k > 0) ? 1u : 0u);
             if (k == BK / 32 - 1) ready = !nosync && !(p.flags & AAB_F_DBG_NO_PEEK) && mbar_test_wait(&full_bar[s1], ph1);
           }
-          if (!nosync) umma_commit(&empty_bar[s]);
-          if (ki == k_iters - 1) umma_commit(&tfull_bar[as]);
+          if (PAIR) {                       // release the stage / publish the accumulator in BOTH CTAs
+            umma_commit_pair(&empty_bar[s]);
+            if (ki == k_iters - 1) umma_commit_pair(&tfull_bar[as]);
+          } else {
+            if (!nosync) umma_commit(&empty_bar[s]);
+            if (ki == k_iters - 1) umma_commit(&tfull_bar[as]);
+          }
 #ifdef AAB_IGEMM_TRACE
           if (trace && it < 96) p.dbg[16 + 192 + it] = static_cast<unsigned long long>(clock64());
 #endif
@@ -281,14 +329,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (col2 < p.n_out) tma_prefetch_l2_5d(&tmR, col2, c2[0], c2[1], c2[2], c2[3]);
       }
     };
-    const bool do_prefetch = HAS_RES && p.residual != nullptr && leader && eg == 0;
+    const bool do_prefetch = !PAIR && HAS_RES && p.residual != nullptr && leader && eg == 0;
     if (do_prefetch) prefetch_res_tile(blockIdx.x);
 
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++tl) {
       const uint32_t as = tl & 1;
       const uint32_t aph = (tl >> 1) & 1;
       const int nt = tile % p.num_n_tiles;
       int mt = tile / p.num_n_tiles;
+      if (PAIR) mt = 2 * mt + static_cast<int>(crank);
+      const bool tile_ok = !PAIR || mt < p.num_m_tiles;      // PAIR, odd m-tile count: rank 1 of the last pair stores nothing
       int cb[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -306,6 +356,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           rr /= p.box[i];
           rvalid = rvalid && (g[i] < p.dimD[i]);
         }
+        rvalid = rvalid && tile_ok;
         grow = ((static_cast<long>(g[3]) * p.dimD[2] + g[2]) * p.dimD[1] + g[1]) * p.dimD[0] + g[0];
       }
       const int n0 = nt * OUT_BN;
@@ -359,7 +410,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             tmem_ld_wait();
             if (hf == 1 && last_read) {
               tc_fence_before();
-              mbar_arrive(&tempty_bar[as]);
+              if (PAIR) mbar_arrive_leader(&tempty_bar[as]);
+              else mbar_arrive(&tempty_bar[as]);
               released = true;
             }
             float vv[16], gg[16];
@@ -398,7 +450,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (last_read) {
             // last TMEM read of this group for this tile: give the accumulator stage back before the (slower) store path
             tc_fence_before();
-            mbar_arrive(&tempty_bar[as]);
+            if (PAIR) mbar_arrive_leader(&tempty_bar[as]);
+            else mbar_arrive(&tempty_bar[as]);
             released = true;
           }
         }
@@ -452,7 +505,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int j4 = 0; j4 < 4; ++j4) *reinterpret_cast<uint4*>(rowp + ((j4 ^ sw) << 4)) = o[j4];
           fence_proxy_async_smem();
           named_bar_sync(bar_id, 128);
-          if (leader) {
+          if (leader && tile_ok) {
             tma_store_5d(&tmD, stage_buf, col, cb[0], cb[1], cb[2], cb[3]);
             tma_store_commit();
           }
@@ -487,7 +540,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       if (!released) {                            // this group had no chunk in range for this tile
         tc_fence_before();
-        mbar_arrive(&tempty_bar[as]);
+        if (PAIR) mbar_arrive_leader(&tempty_bar[as]);
+        else mbar_arrive(&tempty_bar[as]);
       }
 #ifdef AAB_IGEMM_TRACE
       if (p.dbg && blockIdx.x == 0 && leader && tl < 32) p.dbg[16 + 288 + eg * 64 + 2 * tl + 1] = static_cast<unsigned long long>(clock64());
@@ -504,10 +558,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();     // neither CTA may exit (or free TMEM) while the peer can still signal into it
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -573,6 +629,34 @@ static int launch_bn(const CUtensorMap& a, const CUtensorMap& a2, const CUtensor
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   igemm_kernel<BN, EPI><<<grid, NUM_THREADS, CF::SMEM_BYTES, stream>>>(a, a2, b, d, r, p);
   return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
+}
+
+// CTA-pair launch: clusters of 2, persistent over pair tiles (two m-tiles x one n-tile)
+template <int EPI>
+static int launch_pair(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& d,
+                       const CUtensorMap& r, const IgemmParams& p, int max_ctas, cudaStream_t stream) {
+  using CF = Cfg<256, true>;
+  static std::atomic<unsigned long long> attr_done{0};
+  if (int rc = ensure_dyn_smem(igemm_kernel<256, EPI, true>, CF::SMEM_BYTES, attr_done)) return rc;
+  const int pair_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+  int clusters = num_sms() / 2;
+  if (pair_tiles < clusters) clusters = pair_tiles;
+  if (max_ctas > 0 && clusters > max_ctas / 2) clusters = max_ctas / 2 > 0 ? max_ctas / 2 : 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(2 * clusters));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = CF::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_kernel<256, EPI, true>, a, a2, b, d, r, p);
+  return e == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }
 
 template <int EPI>
@@ -690,6 +774,20 @@ extern "C" int aab_igemm(const AabIgemmDesc* d, void* stream_) {
   } else {
     tmD = tmB;
     tmR = tmB;
+  }
+  // CTA pairs (cta_group::2): 256-column tiles of the staged epilogues; the tile box of B is half a tile per CTA
+  const bool pair = (d->flags & AAB_F_PAIR) != 0 && bn == 256 && !direct && d->b_batch_dim < 0 && p.num_m_tiles >= 2;
+  if (pair) {
+    long dimsb[3] = {static_cast<long>(d->num_taps) * d->kc, d->n, 1};
+    long stridesb[3] = {1, d->ld_b, static_cast<long>(d->n) * d->ld_b};
+    int boxb[3] = {BK, 128, 1};
+    int rb = make_tmap_16(&tmB, d->b, 3, dimsb, stridesb, boxb, is_bf16, 128);
+    if (rb) return rb;
+    if (geglu) return launch_pair<1>(tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
+    if (d->residual) return launch_pair<3>(tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
+    if (d->bias2) return launch_pair<4>(tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
+    if (d->act == AAB_ACT_SILU) return launch_pair<5>(tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
+    return launch_pair<0>(tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);
   }
   if (direct) {
     switch (bn) {

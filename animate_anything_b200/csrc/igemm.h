@@ -17,6 +17,7 @@
 #define AAB_F_DBG_NO_SYNC 256 /* diagnostics only: with NO_LOAD, the MMA warp neither waits for stages nor commits them -> raw tcgen05.mma issue rate */
 #define AAB_F_DBG_NO_LOAD 128 /* diagnostics only (wrong results): no TMA loads, stages are always full -> pure MMA + epilogue rate */
 #define AAB_F_SCALE_ACC 16 /* out = act(acc + bias + bias2) * out_scale + residual (scale BEFORE the residual; direct store only) */
+#define AAB_F_PAIR 32     /* 256-column tiles on CTA pairs (cta_group::2): two m-tiles per tcgen05.mma, half a weight tile per CTA */
 #define AAB_F_GEGLU 8     /* B rows [0,N/2) are values, [N/2,N) gates: out = value * gelu(gate), N/2 columns */
 
 #ifdef __cplusplus

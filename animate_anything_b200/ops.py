@@ -12,13 +12,15 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_NONE, ACT_QUICK_GELU, ACT_SILU, F_BF16, F_DIRECT, F_GEGLU, F_OUT_F32, F_SCALE_ACC,
+from ._lib import (ACT_GELU, ACT_NONE, ACT_QUICK_GELU, ACT_SILU, F_BF16, F_DIRECT, F_GEGLU, F_OUT_F32, F_PAIR, F_SCALE_ACC,
                    IgemmDesc)
 
 NUM_SMS = 148
 IGEMM_DEBUG = None       # optional uint64[16] device tensor: per-role wait-cycle counters (tools/igemm_roles.py)
 IGEMM_DBG_FLAGS = 4096 if os.environ.get("AAB_IGEMM_NOPEEK") else 0     # tools/igemm_roles.py only: AAB_F_DBG_NO_MMA (64) / AAB_F_DBG_NO_LOAD (128); results are wrong by design
 IGEMM_PROFILE = None     # bench.py sets this to a list to time every implicit-GEMM launch with CUDA events
+# 256-column tiles on CTA pairs (cta_group::2).  AAB_IGEMM_PAIR=0 restores the single-CTA kernel everywhere (A/B runs).
+IGEMM_PAIR = os.environ.get("AAB_IGEMM_PAIR", "0") != "0"
 KERNEL_PROFILE = None    # same for the other kernels: list of {"name", "bytes" (algorithmic HBM bytes), "flops", "ev"}
 
 
@@ -167,7 +169,7 @@ def igemm(a: torch.Tensor, a_dims, a_strides, w: torch.Tensor, n: int, kc: int, 
     d.out_scale = out_scale
     d.act = act
     flags = ((F_BF16 if bf else 0) | (F_GEGLU if geglu else 0) | (F_OUT_F32 if out_f32 else 0) | (F_DIRECT if direct else 0) |
-             (F_SCALE_ACC if scale_acc else 0))
+             (F_SCALE_ACC if scale_acc else 0) | (F_PAIR if IGEMM_PAIR else 0))
     d.flags = flags | IGEMM_DBG_FLAGS
     if block_n is None:
         if n_out < 64 and not geglu:

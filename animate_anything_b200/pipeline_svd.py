@@ -69,9 +69,8 @@ class MaskStableVideoDiffusionPipeline:
         """diffusers StableVideoDiffusionPipeline.decode_latents: [B, F, 4, h, w] -> fp32 [B, 3, F, H, W], decoded in
         chunks of `decode_chunk_size` frames (the temporal layers of the decoder see one chunk at a time)."""
         lat = latents.flatten(0, 1)
-        b = latents.shape[0]
-        if b != 1 and decode_chunk_size % num_frames and num_frames % decode_chunk_size:
-            raise NotImplementedError("chunks that straddle videos")
+        if latents.shape[0] != 1:
+            raise NotImplementedError("one video per call (as the reference's mask handling implies, models/pipeline.py:372)")
         outs = []
         inv = 1.0 / self.vae.config.scaling_factor
         for i in range(0, lat.shape[0], decode_chunk_size):
@@ -80,9 +79,7 @@ class MaskStableVideoDiffusionPipeline:
             # scale of a [n, 4, h, w] latent, once per clip)
             z = (z * inv).contiguous()
             outs.append(self.vae.decode_chunk_video(z, z.shape[0]))           # [1, 3, n, H, W] fp32
-        frames = torch.cat(outs, dim=2)                                       # chunks are consecutive frames
-        return frames.reshape(-1, 3, num_frames, frames.shape[-2], frames.shape[-1]) if b == 1 else \\
-            frames.permute(0, 2, 1, 3, 4).reshape(b, num_frames, 3, *frames.shape[-2:]).permute(0, 2, 1, 3, 4)
+        return torch.cat(outs, dim=2)                                         # [1, 3, F, H, W]: chunks are consecutive frames
 
     @torch.no_grad()
     def __call__(self, image, height: int = 576, width: int = 1024, num_frames: Optional[int] = None,
