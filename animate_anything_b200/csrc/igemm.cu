@@ -130,8 +130,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull_bar[i], 1);
-        // PAIR: the leader's MMA thread waits for the epilogue threads of BOTH CTAs
-        mbar_init(&tempty_bar[i], (PAIR ? 2 : 1) * 128 * NUM_EPI_GROUPS);
+        // PAIR: the leader's MMA thread waits for the epilogue WARPS of both CTAs (one remote arrival per warp: 32 per
+        // accumulator stage instead of 1024 per-thread arrivals crossing the pair link)
+        mbar_init(&tempty_bar[i], PAIR ? 2 * 4 * NUM_EPI_GROUPS : 128 * NUM_EPI_GROUPS);
       }
       fence_barrier_init();
     }
@@ -410,8 +411,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             tmem_ld_wait();
             if (hf == 1 && last_read) {
               tc_fence_before();
-              if (PAIR) mbar_arrive_leader(&tempty_bar[as]);
-              else mbar_arrive(&tempty_bar[as]);
+              if (PAIR) {
+                __syncwarp();
+                if (lane_id() == 0) mbar_arrive_leader(&tempty_bar[as]);
+              } else {
+                mbar_arrive(&tempty_bar[as]);
+              }
               released = true;
             }
             float vv[16], gg[16];
@@ -450,8 +455,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (last_read) {
             // last TMEM read of this group for this tile: give the accumulator stage back before the (slower) store path
             tc_fence_before();
-            if (PAIR) mbar_arrive_leader(&tempty_bar[as]);
-            else mbar_arrive(&tempty_bar[as]);
+            if (PAIR) {
+              __syncwarp();
+              if (lane_id() == 0) mbar_arrive_leader(&tempty_bar[as]);
+            } else {
+              mbar_arrive(&tempty_bar[as]);
+            }
             released = true;
           }
         }
@@ -540,8 +549,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       if (!released) {                            // this group had no chunk in range for this tile
         tc_fence_before();
-        if (PAIR) mbar_arrive_leader(&tempty_bar[as]);
-        else mbar_arrive(&tempty_bar[as]);
+        if (PAIR) {
+          __syncwarp();
+          if (lane_id() == 0) mbar_arrive_leader(&tempty_bar[as]);
+        } else {
+          mbar_arrive(&tempty_bar[as]);
+        }
       }
 #ifdef AAB_IGEMM_TRACE
       if (p.dbg && blockIdx.x == 0 && leader && tl < 32) p.dbg[16 + 288 + eg * 64 + 2 * tl + 1] = static_cast<unsigned long long>(clock64());

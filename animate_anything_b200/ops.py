@@ -19,8 +19,17 @@ NUM_SMS = 148
 IGEMM_DEBUG = None       # optional uint64[16] device tensor: per-role wait-cycle counters (tools/igemm_roles.py)
 IGEMM_DBG_FLAGS = 4096 if os.environ.get("AAB_IGEMM_NOPEEK") else 0     # tools/igemm_roles.py only: AAB_F_DBG_NO_MMA (64) / AAB_F_DBG_NO_LOAD (128); results are wrong by design
 IGEMM_PROFILE = None     # bench.py sets this to a list to time every implicit-GEMM launch with CUDA events
-# 256-column tiles on CTA pairs (cta_group::2).  AAB_IGEMM_PAIR=0 restores the single-CTA kernel everywhere (A/B runs).
-IGEMM_PAIR = os.environ.get("AAB_IGEMM_PAIR", "0") != "0"
+# 256-column tiles on CTA pairs (cta_group::2).  AAB_IGEMM_PAIR=0 restores the single-CTA kernel everywhere, =2 forces pairs
+# wherever the kernel supports them (A/B runs); default: pairs where they won in profiles/r02_igemm_pair_vs_single.md.
+IGEMM_PAIR = {"0": False, "2": "all"}.get(os.environ.get("AAB_IGEMM_PAIR", "1"), True)
+
+
+def use_pair(k_total: int, n: int) -> bool:
+    """Pairs pay where the main loop dominates (measured on every launch shape of a config-2 forward: +10-24 % for K >= 960,
+    and for K >= 512 with wide outputs); short K loops (K <= 640 with N <= 1280) are epilogue / latency bound and lose."""
+    if IGEMM_PAIR == "all":
+        return True
+    return bool(IGEMM_PAIR) and (k_total >= 960 or (k_total >= 512 and n >= 1536))
 KERNEL_PROFILE = None    # same for the other kernels: list of {"name", "bytes" (algorithmic HBM bytes), "flops", "ev"}
 
 
@@ -169,13 +178,16 @@ def igemm(a: torch.Tensor, a_dims, a_strides, w: torch.Tensor, n: int, kc: int, 
     d.out_scale = out_scale
     d.act = act
     flags = ((F_BF16 if bf else 0) | (F_GEGLU if geglu else 0) | (F_OUT_F32 if out_f32 else 0) | (F_DIRECT if direct else 0) |
-             (F_SCALE_ACC if scale_acc else 0) | (F_PAIR if IGEMM_PAIR else 0))
+             (F_SCALE_ACC if scale_acc else 0))
     d.flags = flags | IGEMM_DBG_FLAGS
     if block_n is None:
         if n_out < 64 and not geglu:
             block_n = 32 if n_out <= 32 else 64
         else:
             block_n = pick_block_n(n_out, m_tiles, geglu, kc * len(taps))
+    if block_n == 256 and use_pair(kc * len(taps), n):
+        flags |= F_PAIR
+    d.flags = flags | IGEMM_DBG_FLAGS
     d.block_n = block_n
     d.max_ctas = max_ctas
     d.debug_cycles = None if IGEMM_DEBUG is None else IGEMM_DEBUG.data_ptr()
@@ -186,6 +198,7 @@ def igemm(a: torch.Tensor, a_dims, a_strides, w: torch.Tensor, n: int, kc: int, 
         _lib.call("aab_igemm", C.byref(d), _stream())
         ev1.record()
         IGEMM_PROFILE.append({"rows": rows, "n": n, "k": kc * len(taps), "taps": len(taps), "block_n": block_n,
+                              "pair": bool(flags & F_PAIR),
                               "flops": 2.0 * rows * n * kc * len(taps), "ev": (ev0, ev1)})
     else:
         _lib.call("aab_igemm", C.byref(d), _stream())

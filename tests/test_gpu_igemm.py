@@ -181,7 +181,7 @@ def test_batched_gemm_qk():
 def pair_mode():
     ops = _ops()
     old = ops.IGEMM_PAIR
-    ops.IGEMM_PAIR = True
+    ops.IGEMM_PAIR = "all"
     yield ops
     ops.IGEMM_PAIR = old
 
@@ -206,7 +206,7 @@ def test_pair_linear(pair_mode, dtype, m, k, n):
     ops.IGEMM_PAIR = False
     single = ops.linear(x, w, b, block_n=256)
     single_r = ops.linear(x, w, b, residual=res, block_n=256)
-    ops.IGEMM_PAIR = True
+    ops.IGEMM_PAIR = "all"
     assert torch.equal(out, single) and torch.equal(out_r, single_r)
 
 

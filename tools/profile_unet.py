@@ -100,17 +100,17 @@ else:
     ops.IGEMM_PROFILE = None
     agg = {}
     for r in rows:
-        key = (r["rows"], r["n"], r["k"], r["taps"], r["block_n"])
+        key = (r["rows"], r["n"], r["k"], r["taps"], r["block_n"], r.get("pair", False))
         a = agg.setdefault(key, {"count": 0, "ms": 0.0, "flops": 0.0})
         a["count"] += 1
         a["ms"] += r["ms"]
         a["flops"] += r["flops"]
-    table = sorted(({"rows": k[0], "n": k[1], "k": k[2], "taps": k[3], "block_n": k[4], **v,
+    table = sorted(({"rows": k[0], "n": k[1], "k": k[2], "taps": k[3], "block_n": k[4], "pair": k[5], **v,
                      "tflops": v["flops"] / v["ms"] / 1e9} for k, v in agg.items()), key=lambda d: -d["ms"])
     tot = sum(t["ms"] for t in table)
     print(f"igemm total {tot:.2f} ms over {len(rows)} launches")
     for t in table[:40]:
-        print(f"rows={t['rows']:7d} n={t['n']:5d} k={t['k']:6d} taps={t['taps']} bn={t['block_n']:3d} x{t['count']:3d} "
+        print(f"rows={t['rows']:7d} n={t['n']:5d} k={t['k']:6d} taps={t['taps']} bn={t['block_n']:3d}{'p' if t['pair'] else ' '} x{t['count']:3d} "
               f"{t['ms']:8.3f} ms  {t['tflops']:7.1f} TFLOP/s")
     json.dump(table, open(os.path.join(ROOT, "gpurun_out", "igemm_shapes.json"), "w"), indent=1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
