@@ -49,6 +49,7 @@ struct FaParams {
 __global__ void __launch_bounds__(FA_THREADS, 1)
 flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const FaParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smQ = smem;                                    // [2][16K]
@@ -103,6 +104,7 @@ flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
   // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384)
 
   if (warp == 0) {
@@ -353,6 +355,7 @@ template <bool SHORT>
 __global__ void __launch_bounds__(FA2_THREADS, SHORT ? 2 : 1)
 flash_attn_d64_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, const FaParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int KVS = SHORT ? 1 : FA_KV_STAGES;
@@ -412,6 +415,7 @@ flash_attn_d64_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -602,6 +606,8 @@ template <bool BF16>
 __global__ void __launch_bounds__(128)
 temporal_attn_d64_kernel(const void* __restrict__ qkv, long ld, int q_col0, int k_col0, int v_col0, void* __restrict__ out,
                          long ld_out, int B, int T, int HW, int heads, float scale) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ uint16_t sm16[];
   const int w = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -761,6 +767,8 @@ template <bool BF16>
 __global__ void __launch_bounds__(128)
 temporal_attn_d64_v2_kernel(const void* __restrict__ qkv, long ld, int q_col0, int k_col0, int v_col0,
                             void* __restrict__ out, long ld_out, int B, int T, int HW, int heads, float scale) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ uint16_t sm16[];
   const int w = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -997,17 +1005,17 @@ extern "C" int aab_flash_attn_d64(const void* q, long ldq, long q_batch_stride, 
     static std::atomic<unsigned long long> attr_s{0};
     if (int r = ensure_dyn_smem(flash_attn_d64_v2_kernel<true>, FA2S_SMEM_BYTES, attr_s)) return r;
     dim3 grid((lq + 127) / 128, heads, nb);
-    flash_attn_d64_v2_kernel<true><<<grid, FA2_THREADS, FA2S_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+    launch_k(flash_attn_d64_v2_kernel<true>, dim3(grid), dim3(FA2_THREADS), FA2S_SMEM_BYTES, stream, tmQ, tmK, tmV, p);
     return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
   }
   if (use_v1 || causal) {       // two query tiles per CTA (two softmax warpgroups), S single-buffered
     dim3 grid((lq + 255) / 256, heads, nb);
-    flash_attn_d64_kernel<<<grid, FA_THREADS, FA_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+    launch_k(flash_attn_d64_kernel, dim3(grid), dim3(FA_THREADS), FA_SMEM_BYTES, stream, tmQ, tmK, tmV, p);
   } else {
     static std::atomic<unsigned long long> attr2_done{0};
     if (int r = ensure_dyn_smem(flash_attn_d64_v2_kernel<false>, FA2_SMEM_BYTES, attr2_done)) return r;
     dim3 grid((lq + 127) / 128, heads, nb);
-    flash_attn_d64_v2_kernel<false><<<grid, FA2_THREADS, FA2_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+    launch_k(flash_attn_d64_v2_kernel<false>, dim3(grid), dim3(FA2_THREADS), FA2_SMEM_BYTES, stream, tmQ, tmK, tmV, p);
   }
   return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }
@@ -1033,10 +1041,10 @@ extern "C" int aab_temporal_attn_d64(const void* qkv, long ld, int q_col0, int k
     const long cap = 2L * num_sms();                              // two 108 KiB CTAs per SM, persistent
     const int grid2 = static_cast<int>(ctas < cap ? ctas : cap);
     if (is_bf16)
-      temporal_attn_d64_v2_kernel<true><<<grid2, 128, smem2, stream>>>(qkv, ld, q_col0, k_col0, v_col0, out, ld_out, b, t, hw,
+      launch_k(temporal_attn_d64_v2_kernel<true>, dim3(grid2), dim3(128), smem2, stream, qkv, ld, q_col0, k_col0, v_col0, out, ld_out, b, t, hw,
                                                                        heads, scale);
     else
-      temporal_attn_d64_v2_kernel<false><<<grid2, 128, smem2, stream>>>(qkv, ld, q_col0, k_col0, v_col0, out, ld_out, b, t, hw,
+      launch_k(temporal_attn_d64_v2_kernel<false>, dim3(grid2), dim3(128), smem2, stream, qkv, ld, q_col0, k_col0, v_col0, out, ld_out, b, t, hw,
                                                                         heads, scale);
     return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
   }
@@ -1046,10 +1054,10 @@ extern "C" int aab_temporal_attn_d64(const void* qkv, long ld, int q_col0, int k
   if (int r = ensure_dyn_smem(temporal_attn_d64_kernel<true>, 65536, attr_t)) return r;
   if (int r = ensure_dyn_smem(temporal_attn_d64_kernel<false>, 65536, attr_f)) return r;
   if (is_bf16)
-    temporal_attn_d64_kernel<true><<<grid, 128, smem, stream>>>(qkv, ld, q_col0, k_col0, v_col0, out, ld_out, b, t, hw,
+    launch_k(temporal_attn_d64_kernel<true>, dim3(grid), dim3(128), smem, stream, qkv, ld, q_col0, k_col0, v_col0, out, ld_out, b, t, hw,
                                                                 heads, scale);
   else
-    temporal_attn_d64_kernel<false><<<grid, 128, smem, stream>>>(qkv, ld, q_col0, k_col0, v_col0, out, ld_out, b, t, hw,
+    launch_k(temporal_attn_d64_kernel<false>, dim3(grid), dim3(128), smem, stream, qkv, ld, q_col0, k_col0, v_col0, out, ld_out, b, t, hw,
                                                                  heads, scale);
   return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }

@@ -9,6 +9,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <atomic>
 
 #define AAB_OK 0
@@ -314,6 +315,43 @@ inline int ensure_dyn_smem(Kernel kernel, int bytes, std::atomic<unsigned long l
   if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return AAB_ERR_CUDA;
   done.fetch_or(bit, std::memory_order_release);
   return AAB_OK;
+}
+
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel of the path is launched with cudaLaunchAttributeProgrammaticStreamSerialization and follows one rule:
+//   pdl_trigger()  at the very top   -- the NEXT kernel of the stream may be scheduled as soon as every CTA of this grid
+//                                       has started (its CTAs take the SM resources this grid frees while draining);
+//   pdl_wait()     before the first global-memory access (read OR write) -- blocks until the PREVIOUS grid has completed
+//                                       and its memory is visible.
+// So only set-up work (barrier init, TMEM allocation, descriptor prefetch, index math) overlaps the predecessor's tail;
+// data hazards are impossible by construction.  AAB_PDL=0 launches without the attribute (then both calls are no-ops).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("AAB_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+
+// kernel<<<grid, block, smem, stream>>>(args...) with the PDL attribute (and an optional cluster dimension)
+template <typename... P, typename... A>
+inline cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
 }
 
 // ---------------------------------------------------------------- numeric helpers

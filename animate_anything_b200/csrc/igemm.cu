@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
              const __grid_constant__ CUtensorMap tmR, const IgemmParams p) {
+  pdl_trigger();
   using C = Cfg<BN, PAIR>;
   static_assert(!PAIR || BN == 256, "the CTA-pair variant is built for 256-column tiles");
   constexpr int STAGES = C::STAGES;
@@ -150,6 +151,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();       // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -640,7 +642,7 @@ static int launch_bn(const CUtensorMap& a, const CUtensorMap& a2, const CUtensor
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  igemm_kernel<BN, EPI><<<grid, NUM_THREADS, CF::SMEM_BYTES, stream>>>(a, a2, b, d, r, p);
+  launch_k(igemm_kernel<BN, EPI>, dim3(grid), dim3(NUM_THREADS), CF::SMEM_BYTES, stream, a, a2, b, d, r, p);
   return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }
 
@@ -661,13 +663,15 @@ static int launch_pair(const CUtensorMap& a, const CUtensorMap& a2, const CUtens
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = CF::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_kernel<256, EPI, true>, a, a2, b, d, r, p);
   return e == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }

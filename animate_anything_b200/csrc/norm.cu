@@ -34,6 +34,8 @@ struct GnArgs {
 __global__ void gn_stats_kernel(GnArgs a, double* __restrict__ partial /* [S][chunks][G][2] */,
                                 float* __restrict__ mean_rstd /* [S][G][2] */, unsigned int* __restrict__ ticket /* [S] */,
                                 float eps) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sh[];   // [rpi][C] sums, [rpi][C] squares
   __shared__ bool is_last;
   const int C = a.C1 + a.C2;
@@ -176,6 +178,8 @@ __global__ void gn_stats_kernel(GnArgs a, double* __restrict__ partial /* [S][ch
 
 __global__ void gn_apply_kernel(GnArgs a, const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, int silu, void* __restrict__ y, long ldy) {
+  pdl_trigger();
+  pdl_wait();
   const int C = a.C1 + a.C2;
   const int V = C >> 3;
   const int oct = threadIdx.x % V;
@@ -246,6 +250,8 @@ template <int OPL, int R>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const void* __restrict__ x, long ldx, void* __restrict__ y, long ldy, const float* __restrict__ gamma,
                  const float* __restrict__ beta, long rows, int C, float eps, int bf16) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long warp_global = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long row0 = warp_global * R;
@@ -324,6 +330,8 @@ template <int OPL, int LPR>
 __global__ void __launch_bounds__(256)
 layernorm_v2_kernel(const void* __restrict__ x, long ldx, void* __restrict__ y, long ldy, const float* __restrict__ gamma,
                     const float* __restrict__ beta, long rows, int C, float eps, int bf16) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPR;
@@ -405,6 +413,8 @@ layernorm_v2_kernel(const void* __restrict__ x, long ldx, void* __restrict__ y, 
 // row softmax: fp32 scores [rows][L] -> 16-bit probabilities (VAE mid-block attention, upcast_softmax semantics)
 __global__ void softmax_rows_kernel(const float* __restrict__ s, long lds, void* __restrict__ p, long ldp, int L, int Lpad,
                                     int bf16) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[32];
   const long row = blockIdx.x;
   const float* sr = s + row * lds;
@@ -509,8 +519,8 @@ extern "C" int aab_groupnorm(const void* x1, long ld1, int c1, const void* x2, l
   // 84 vs 72 us at [34, 4096, 320], 38 vs 24 us at [34, 256, 1280]): the flag wait serialises the two phases inside every
   // CTA, while two plain launches let the hardware overlap the tail of one with the head of the next.  Not kept.
   dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(samples));
-  gn_stats_kernel<<<grid, threads, smem, stream>>>(a, partial, mean_rstd, ticket, eps);
-  gn_apply_kernel<<<grid, threads, 0, stream>>>(a, mean_rstd, gamma, beta, silu, y, ldy);
+  launch_k(gn_stats_kernel, dim3(grid), dim3(threads), smem, stream, a, partial, mean_rstd, ticket, eps);
+  launch_k(gn_apply_kernel, dim3(grid), dim3(threads), 0, stream, a, mean_rstd, gamma, beta, silu, y, ldy);
   return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }
 
@@ -519,7 +529,7 @@ static void launch_ln(const void* x, long ldx, void* y, long ldy, const float* g
                       float eps, int is_bf16, cudaStream_t stream) {
   const int wpb = 8;
   const long warps = (rows + R - 1) / R;
-  layernorm_kernel<OPL, R><<<static_cast<unsigned>((warps + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+  launch_k(layernorm_kernel<OPL, R>, dim3(static_cast<unsigned>((warps + wpb - 1) / wpb)), dim3(wpb * 32), 0, stream, 
       x, ldx, y, ldy, gamma, beta, rows, c, eps, is_bf16);
 }
 
@@ -532,7 +542,7 @@ static void launch_ln2(const void* x, long ldx, void* y, long ldy, const float* 
   long ctas = (groups + wpb - 1) / wpb;
   const long cap = 6L * aab::num_sms();                 // persistent: ~6 CTAs of 8 warps per SM
   if (ctas > cap) ctas = cap;
-  layernorm_v2_kernel<OPL, LPR><<<static_cast<unsigned>(ctas), wpb * 32, 0, stream>>>(x, ldx, y, ldy, gamma, beta, rows, c,
+  launch_k(layernorm_v2_kernel<OPL, LPR>, dim3(static_cast<unsigned>(ctas)), dim3(wpb * 32), 0, stream, x, ldx, y, ldy, gamma, beta, rows, c,
                                                                                      eps, is_bf16);
 }
 
@@ -572,6 +582,6 @@ extern "C" int aab_softmax_rows(const float* s, long lds, void* p, long ldp, lon
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!s || !p || ldp < l) return AAB_ERR_ARG;
   // the probability rows are `ldp` wide: columns l..ldp-1 are written as zeros
-  softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(s, lds, p, ldp, l, static_cast<int>(ldp), is_bf16);
+  launch_k(softmax_rows_kernel, dim3(static_cast<unsigned>(rows)), dim3(256), 0, stream, s, lds, p, ldp, l, static_cast<int>(ldp), is_bf16);
   return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }
