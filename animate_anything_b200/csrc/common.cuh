@@ -324,7 +324,9 @@ inline int ensure_dyn_smem(Kernel kernel, int bytes, std::atomic<unsigned long l
 //   pdl_wait()     before the first global-memory access (read OR write) -- blocks until the PREVIOUS grid has completed
 //                                       and its memory is visible.
 // So only set-up work (barrier init, TMEM allocation, descriptor prefetch, index math) overlaps the predecessor's tail;
-// data hazards are impossible by construction.  AAB_PDL=0 launches without the attribute (then both calls are no-ops).
+// data hazards are impossible by construction.  Measured in round 2 (profiles/r02_pdl_ab.md, same box, all 135 GPU tests green
+// with it on): 5.214 frames/s with, 5.229 without -- the persistent kernels leave no gap worth hiding, so it is OFF by
+// default (launches carry no attribute and both calls are no-ops); AAB_PDL=1 enables it.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -332,7 +334,7 @@ inline bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {
     const char* e = getenv("AAB_PDL");
-    on = (e && e[0] == '0') ? 0 : 1;
+    on = (e && e[0] == '1') ? 1 : 0;
   }
   return on != 0;
 }
