@@ -667,6 +667,80 @@ def run_svd(args):
     print(json.dumps(line), flush=True)
 
 
+def run_vae(args):
+    """BASELINE config 5 (opt-in: `--workload vae`): VAE-only throughput sweep.  N frames (64 ... 1024) are split evenly over
+    the ranks; every rank decodes its latent frames to uint8 (fused tail) and encodes as many 512x512 images; the decoded
+    frames are all-gathered (the path's one collective).  Per N: frames/s (max over ranks) and achieved tensor TFLOP/s
+    against the measured peak (2.515 TFLOP per decoded frame, 1.117 per encoded frame: BASELINE.md section 4)."""
+    import torch
+    import torch.distributed as dist
+    from animate_anything_b200.autoencoder_kl import AutoencoderKL
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dtype = torch.bfloat16
+    torch.manual_seed(0)
+    with torch.device(dev):
+        vae = AutoencoderKL()
+    vae = vae.to(dtype).eval()
+    peak_tf, _, peak_src = _peaks()
+    rows = []
+    g = torch.Generator().manual_seed(3 + rank)
+    for n_total in (64, 128, 256, 512, 1024):
+        n = n_total // world
+        lat = torch.randn(1, 4, n, LAT, LAT, generator=g).to(dtype).to(dev)
+        img = torch.randn(min(n, 64), 3, HW, HW, generator=g).clamp(-1, 1).to(dtype).to(dev)      # encoded in rounds of <= 64
+        gather = torch.empty((world, n, HW, HW, 3), dtype=torch.uint8, device=dev) if world > 1 else None
+
+        def decode():
+            fr = vae.decode_frames_uint8(lat)
+            if world > 1:
+                dist.all_gather_into_tensor(gather, fr.unsqueeze(0))
+            return fr
+
+        def encode():
+            done = 0
+            while done < n:
+                k = min(img.shape[0], n - done)
+                vae.encode(img[:k])
+                done += k
+        t_dec = torch.tensor([_ev_ms(decode, reps=1 if n_total >= 512 else 2, warm=1)], device=dev, dtype=torch.float64)
+        t_enc = torch.tensor([_ev_ms(encode, reps=1 if n_total >= 512 else 2, warm=1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_dec, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t_enc, op=dist.ReduceOp.MAX)
+        d_fps = n_total / (t_dec.item() / 1e3)
+        e_fps = n_total / (t_enc.item() / 1e3)
+        rows.append({"frames": n_total, "decode_frames_per_s": d_fps, "encode_frames_per_s": e_fps,
+                     "decode_tflops_per_gpu": d_fps * 2.515 / world, "encode_tflops_per_gpu": e_fps * 1.117 / world,
+                     "decode_frac_of_peak": d_fps * 2.515 / world / peak_tf, "encode_frac_of_peak": e_fps * 1.117 / world / peak_tf})
+        del lat, img, gather
+        torch.cuda.empty_cache()
+    if rank == 0:
+        last = rows[-1]
+        line = {"metric": "vae_decode_frames_per_sec_512x512", "value": last["decode_frames_per_s"], "unit": UNIT,
+                "n_gpus": world, "steps": 1, "warmup": 1, "ms_per_step": 1024 / last["decode_frames_per_s"] * 1e3,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "config5: AutoencoderKL (SD VAE, random init) decode [N,4,64,64] -> uint8 512x512 frames and "
+                                       "encode [N,3,512,512], N = 64..1024 split evenly over the GPUs, one all-gather of decoded frames",
+                           "peak_source": peak_src},
+                "sweep": rows}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        wd = threading.Timer(20.0, lambda: os._exit(0))
+        wd.daemon = True
+        wd.start()
+        dist.destroy_process_group()
+        wd.cancel()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -680,13 +754,16 @@ def main():
                     help="N>1 only. throughput (default, what the driver's scaling run uses): one clip per GPU. latency: "
                          "BASELINE config 3 -- N=2 one clip with its CFG halves on two GPUs; N=4 four prompts, pairs "
                          "co-located; N=8 four prompts, one batch element per GPU")
-    ap.add_argument("--workload", default="config2", choices=["config2", "svd"],
-                    help="config2 (default, BASELINE's headline) or svd (BASELINE config 4, 1 GPU, this repo's arm only)")
+    ap.add_argument("--workload", default="config2", choices=["config2", "svd", "vae"],
+                    help="config2 (default, BASELINE's headline), svd (BASELINE config 4, 1 GPU) or vae (config 5: VAE-only "
+                         "sweep, frames split over the GPUs); svd / vae exist for this repo's arm only")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "svd":
         run_svd(args)
+    elif args.workload == "vae":
+        run_vae(args)
     else:
         run_product(args)
 
