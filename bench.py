@@ -611,7 +611,8 @@ def run_svd(args):
     nf, hh, ww, steps = 25, 576, 1024, 25
     torch.manual_seed(0)
     with torch.device(dev):
-        unet = UNetSpatioTemporalConditionModel(in_channels=9, sample_size=96)
+        # the released SVD checkpoints' config (heads 5/10/20/20 = head dim 64 everywhere; the class default has a 10 at level 2)
+        unet = UNetSpatioTemporalConditionModel(in_channels=9, sample_size=96, num_attention_heads=(5, 10, 20, 20))
         vae = AutoencoderKLTemporalDecoder()
     with torch.no_grad():
         for n, p in unet.named_parameters():
