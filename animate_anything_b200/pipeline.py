@@ -104,6 +104,8 @@ class LatentToVideoPipeline:
         te = self.text_encoder
         if te is None or isinstance(te, CLIPTextModel):
             return te
+        if not (hasattr(te, "text_model") and hasattr(te, "config") and hasattr(te, "parameters")):
+            return te                    # not a CLIP text model (a caller-supplied embedding callable): used as it is
         p0 = next(te.parameters())
         key = (id(te), p0.data_ptr(), p0.dtype, p0.device)
         cached = self.__dict__.get("_te_mirror")
