@@ -31,7 +31,7 @@ class IgemmDesc(C.Structure):
         ("bias", C.c_void_p), ("bias2", C.c_void_p), ("rows_per_bias2", C.c_int), ("ld_bias2", C.c_long),
         ("residual", C.c_void_p), ("ld_res", C.c_long),
         ("out_scale", C.c_float), ("act", C.c_int), ("flags", C.c_int), ("block_n", C.c_int), ("max_ctas", C.c_int),
-        ("debug_cycles", C.c_void_p),
+        ("debug_cycles", C.c_void_p), ("colstats", C.c_void_p),
     ]
 
 
@@ -52,6 +52,9 @@ _SIGS = {
                               C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p],
     "aab_groupnorm": [C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_long, C.c_int, C.c_long, C.c_long, C.c_int,
                       C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_int, C.c_void_p],
+    "aab_groupnorm_colstats": [C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_long,
+                               C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_long, C.c_void_p,
+                               C.c_int, C.c_void_p],
     "aab_layernorm": [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_float,
                       C.c_int, C.c_void_p],
     "aab_softmax_rows": [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_long, C.c_int, C.c_int, C.c_void_p],
@@ -97,7 +100,7 @@ _SIGS = {
 EXPORTS = tuple(_SIGS.keys())
 
 _launch_count = 0
-_KERNELS_PER_CALL = {"aab_groupnorm": 2}     # statistics + apply
+_KERNELS_PER_CALL = {"aab_groupnorm": 2, "aab_groupnorm_colstats": 2}     # statistics + apply
 
 
 def load():
@@ -115,6 +118,8 @@ def load():
         fn.restype = C.c_int
     lib.aab_groupnorm_workspace_bytes.argtypes = [C.c_long, C.c_long, C.c_int, C.c_int]
     lib.aab_groupnorm_workspace_bytes.restype = C.c_long
+    lib.aab_igemm_emits_colstats.argtypes = [C.POINTER(IgemmDesc)]
+    lib.aab_igemm_emits_colstats.restype = C.c_int
     _lib = lib
     return lib
 

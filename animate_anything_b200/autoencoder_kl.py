@@ -201,7 +201,7 @@ class AutoencoderKL(ModelBase):
         vt = ops.transpose_batched(qkv, 2 * c, n, l, c, ld=lp)            # [n, c, lp]
         o = ops.igemm(pr, (lp, l, n, 1, 1), (1, lp, l * lp, 0, 0), vt, c, lp, (l, n, 1, 1), (128, 1, 1, 1),
                       [[0, 0, 0, 0, 0]], ld_b=lp, b_batch=n, b_batch_stride=c * lp, b_batch_dim=1)
-        return ops.linear(o, p["o"][0], p["o"][1], residual=x, out_scale=1.0 / attn.rescale_output_factor)
+        return ops.linear(o, p["o"][0], p["o"][1], residual=x, out_scale=1.0 / attn.rescale_output_factor, stats=True)
 
     def _mid(self, ctx, mid: UNetMidBlock2D, x, g):
         x = E.resnet_forward(ctx, mid.resnets[0], x, g)
@@ -216,7 +216,7 @@ class AutoencoderKL(ModelBase):
             raise ValueError("image height/width must be multiples of 8")
         g = E.Geo(n, 1, hh, ww)
         ctx = E.Ctx(prep, g)
-        h = ops.conv3x3(ops.image_to_nhwc8(x), own["enc_in"][0], own["enc_in"][1])
+        h = ops.conv3x3(ops.image_to_nhwc8(x), own["enc_in"][0], own["enc_in"][1], stats=True)
         for blk in self.encoder.down_blocks:
             for r in blk.resnets:
                 h = E.resnet_forward(ctx, r, h, g)
@@ -239,7 +239,7 @@ class AutoencoderKL(ModelBase):
         g = E.Geo(b * f, 1, hh, ww)
         ctx = E.Ctx(prep, g)
         z = ops.vae_dec_in(lat5, inv_scale, own["post_quant"][0], own["post_quant"][1])
-        h = ops.conv3x3(z, own["dec_in"][0], own["dec_in"][1])
+        h = ops.conv3x3(z, own["dec_in"][0], own["dec_in"][1], stats=True)
         h = self._mid(ctx, self.decoder.mid_block, h, g)
         for blk in self.decoder.up_blocks:
             for r in blk.resnets:

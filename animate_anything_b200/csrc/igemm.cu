@@ -253,6 +253,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int nvalid = p.N - (tile % p.num_n_tiles) * BN;
           if (nvalid < BN) n_mma = PAIR ? ((nvalid + 31) & ~31) : ((nvalid + 15) & ~15);
         }
+        // (Splitting the tile into two column halves issued alternately -- so that consecutive tcgen05.mma never accumulate into
+        // the same TMEM columns, which a bare issue loop rewards with N/2 instead of N/2 + 43 clk per instruction,
+        // profiles/r02_umma_rate_v3.log -- was built and measured for single CTAs and for pairs: 2-5 % SLOWER on every large
+        // shape (profiles/r02_igemm_split_issue.md).  The tensor pipe is not what paces this kernel; the operand feed is.)
         const uint32_t idesc = make_idesc_f16(bf16 ? 1 : 0, PAIR ? 2 * BM : BM, n_mma, 0, 0);
         w_tempty.wait(&tempty_bar[as], aph ^ 1);
         const uint32_t tmem_d = tmem_base + as * BN;
@@ -342,6 +346,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int mt = tile / p.num_n_tiles;
       if (PAIR) mt = 2 * mt + static_cast<int>(crank);
       const bool tile_ok = !PAIR || mt < p.num_m_tiles;      // PAIR, odd m-tile count: rank 1 of the last pair stores nothing
+      const int mt_lin = mt;                                  // linear m-tile index (row of the column-statistics table)
       int cb[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -510,6 +515,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
           const long long tm1 = p.dbg ? clock64() : 0;
+          if (!GEGLU && p.colstats != nullptr && !rvalid) {
+            // rows outside the output (partial tiles) are clipped by the TMA store; zeroed here they add nothing to the
+            // column statistics below
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) o[j4] = make_uint4(0, 0, 0, 0);
+          }
           if (leader) tma_store_wait_read<0>();    // the group's previous store has drained the staging buffer
           named_bar_sync(bar_id, 128);
 #pragma unroll
@@ -519,6 +530,46 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (leader && tile_ok) {
             tma_store_5d(&tmD, stage_buf, col, cb[0], cb[1], cb[2], cb[3]);
             tma_store_commit();
+          }
+          if (!GEGLU && p.colstats != nullptr) {
+            // GroupNorm statistics of the tensor being written, from the staged (rounded) tile: warp q of the group owns the
+            // 8 columns of 16-byte piece q, lane l the rows l, l+32, l+64, l+96 (conflict-free through the 64B swizzle);
+            // fixed-order butterfly over the lanes -> one (sum, sumsq) pair per column and m-tile, bitwise reproducible.
+            float v[16];                                     // v[j]: sum of column j, v[8 + j]: its sum of squares
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = static_cast<int>(lane_id()) + 32 * i;
+              const uint4 u = *reinterpret_cast<const uint4*>(stage_buf + r * 64 + ((q ^ ((r >> 1) & 3)) << 4));
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack2(w[e], bf16);
+                v[2 * e] += f.x; v[8 + 2 * e] = fmaf(f.x, f.x, v[8 + 2 * e]);
+                v[2 * e + 1] += f.y; v[9 + 2 * e] = fmaf(f.y, f.y, v[9 + 2 * e]);
+              }
+            }
+            // reduce-scatter over the lanes (16 shuffles instead of 80): at distance `off` a lane keeps one half of its
+            // values and hands the other half to its partner; afterwards lane l holds the warp total of value
+            // idx = (l>>4 & 1) << 3 | (l>>3 & 1) << 2 | (l>>2 & 1) << 1 | (l>>1 & 1)
+#pragma unroll
+            for (int half = 8; half >= 1; half >>= 1) {
+              const int off = half * 2;
+              const bool up = (lane_id() & off) != 0;
+#pragma unroll
+              for (int jj = 0; jj < half; ++jj) {
+                const float send = up ? v[jj] : v[jj + half];
+                const float keep = up ? v[jj + half] : v[jj];
+                v[jj] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+              }
+            }
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+            if (!(lane_id() & 1) && tile_ok) {
+              const uint32_t l = lane_id();
+              const uint32_t idx = ((l >> 4) & 1) << 3 | ((l >> 3) & 1) << 2 | ((l >> 2) & 1) << 1 | ((l >> 1) & 1);
+              p.colstats[(static_cast<long>(mt_lin) * p.n_out + col + q * 8 + (idx & 7)) * 2 + (idx >> 3)] = v[0];
+            }
           }
           if (p.dbg) {
             t_math += static_cast<unsigned long long>(tm1 - tm0);
@@ -690,6 +741,23 @@ static int launch_epi(int bn, const CUtensorMap& a, const CUtensorMap& a2, const
 
 using namespace aab;
 
+// 1 when this launch takes a staged (smem + TMA store) epilogue -- the only ones that can emit `colstats` -- else 0
+static int igemm_is_staged(const AabIgemmDesc* d) {
+  const bool geglu = (d->flags & AAB_F_GEGLU) != 0;
+  const int bn = d->block_n;
+  const int n_out = geglu ? d->n / 2 : d->n;
+  if ((d->flags & (AAB_F_DIRECT | AAB_F_OUT_F32 | AAB_F_SCALE_ACC)) || bn == 32 || (d->ld_out % 8) || (n_out % 32)) return 0;
+  if (d->residual && (d->ld_res % 8)) return 0;
+  if ((d->act == AAB_ACT_GELU || d->act == AAB_ACT_QUICK_GELU) && !geglu) return 0;
+  const int extras = (d->residual ? 1 : 0) + (d->bias2 ? 1 : 0) + (d->act == AAB_ACT_SILU ? 1 : 0);
+  if (!geglu && (extras > 1 || d->out_scale != 1.0f)) return 0;
+  return 1;
+}
+
+extern "C" int aab_igemm_emits_colstats(const AabIgemmDesc* d) {
+  return (d && d->colstats && !(d->flags & AAB_F_GEGLU) && igemm_is_staged(d)) ? 1 : 0;
+}
+
 extern "C" int aab_igemm(const AabIgemmDesc* d, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!d || !d->a || !d->b || !d->out) return AAB_ERR_ARG;
@@ -749,6 +817,7 @@ extern "C" int aab_igemm(const AabIgemmDesc* d, void* stream_) {
   p.act = d->act;
   p.flags = d->flags | (direct ? AAB_F_DIRECT : 0);
   p.dbg = d->debug_cycles;
+  p.colstats = direct ? nullptr : d->colstats;   // staged epilogues only (the caller checks the result of aab_igemm_emits_colstats)
 
   CUtensorMap tmA, tmA2, tmB, tmD, tmR;
   {

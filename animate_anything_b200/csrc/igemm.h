@@ -58,6 +58,9 @@ typedef struct AabIgemmDesc {
   int block_n;              // 32 / 64 / 128 / 256
   int max_ctas;             // 0 = one CTA per SM
   unsigned long long* debug_cycles;   // optional [16] device counters: per-role wait cycles (profiling aid), or NULL
+  float* colstats;          // optional [num_m_tiles][n_out][2] fp32: per m-tile column sums (sum, sum of squares) of the ROUNDED
+                            // 16-bit outputs over the tile's valid rows -- the statistics of the GroupNorm that follows, taken
+                            // where the data already is in registers / shared memory (staged epilogues only), or NULL
 } AabIgemmDesc;
 
 #ifdef __cplusplus
@@ -86,6 +89,7 @@ struct IgemmParams {
   int act;
   int flags;
   unsigned long long* dbg;
+  float* colstats;
 };
 int make_tmap_16(CUtensorMap* out, const void* base, int rank, const long* dims, const long* strides, const int* box,
                  int is_bf16, int swizzle_bytes = 128);

@@ -244,6 +244,50 @@ __global__ void gn_apply_kernel(GnArgs a, const float* __restrict__ mean_rstd, c
   }
 }
 
+// GroupNorm statistics from the column sums the producing GEMM left behind (igemm `colstats`: [m-tiles][C][2] fp32, one
+// (sum, sumsq) per 128-row tile and column).  CTA (sample s, group g) adds the tps tiles of the sample x the cpg columns of the
+// group in a fixed order (fp64) and publishes mean / rstd -- the 89 MB statistics read of a level-0 GroupNorm becomes a 2.8 MB
+// one.  Two sources = virtual channel concat (channels [0, C1) from cs1, [C1, C1+C2) from cs2).
+__global__ void gn_finalize_kernel(const float* __restrict__ cs1, int C1, const float* __restrict__ cs2, int C2, int tps, long rows,
+                                   int groups, float eps, float* __restrict__ mean_rstd) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ double red[2][256];
+  const int s = blockIdx.y;
+  const int g = blockIdx.x;
+  const int C = C1 + C2;
+  const int cpg = C / groups;
+  const int n = tps * cpg;                       // (tile, column) pairs of this (sample, group)
+  double ds = 0.0, dq = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int t = i / cpg;
+    const int c = g * cpg + (i - t * cpg);
+    const long tile = static_cast<long>(s) * tps + t;
+    const float2 v = (c < C1) ? __ldg(reinterpret_cast<const float2*>(cs1 + (tile * C1 + c) * 2))
+                              : __ldg(reinterpret_cast<const float2*>(cs2 + (tile * C2 + (c - C1)) * 2));
+    ds += static_cast<double>(v.x);
+    dq += static_cast<double>(v.y);
+  }
+  red[0][threadIdx.x] = ds;
+  red[1][threadIdx.x] = dq;
+  __syncthreads();
+  for (int off = blockDim.x >> 1; off > 0; off >>= 1) {      // fixed-order tree
+    if (threadIdx.x < off) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + off];
+      red[1][threadIdx.x] += red[1][threadIdx.x + off];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double cnt = static_cast<double>(rows) * cpg;
+    const double m = red[0][0] / cnt;
+    double var = red[1][0] / cnt - m * m;
+    if (var < 0) var = 0;
+    mean_rstd[(static_cast<long>(s) * groups + g) * 2] = static_cast<float>(m);
+    mean_rstd[(static_cast<long>(s) * groups + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+}
+
 // One warp handles R consecutive rows at a time (all loads of the R rows are issued before any reduction, so that
 // enough bytes are in flight per SM); OPL = 16-byte octets per lane = ceil(C/8/32).  C % 8 == 0, C <= 2048.
 template <int OPL, int R>
@@ -520,6 +564,36 @@ extern "C" int aab_groupnorm(const void* x1, long ld1, int c1, const void* x2, l
   // CTA, while two plain launches let the hardware overlap the tail of one with the head of the next.  Not kept.
   dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(samples));
   launch_k(gn_stats_kernel, dim3(grid), dim3(threads), smem, stream, a, partial, mean_rstd, ticket, eps);
+  launch_k(gn_apply_kernel, dim3(grid), dim3(threads), 0, stream, a, mean_rstd, gamma, beta, silu, y, ldy);
+  return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
+}
+
+// GroupNorm with the statistics pass replaced by the producer's column sums (see gn_finalize_kernel).  colstats1 / colstats2:
+// [samples * rows / 128][c1 | c2][2] fp32 as written by aab_igemm (each 128-row tile must lie inside one sample: rows % 128 == 0).
+extern "C" int aab_groupnorm_colstats(const void* x1, long ld1, int c1, const float* colstats1, const void* x2, long ld2, int c2,
+                                      const float* colstats2, long samples, long rows, int groups, const float* gamma,
+                                      const float* beta, float eps, int silu, void* y, long ldy, void* workspace, int is_bf16,
+                                      void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int C = c1 + c2;
+  if (!x1 || !y || !workspace || !colstats1 || groups < 1 || groups > 256 || C % groups || (c1 % 8) || (c2 % 8) || (ld1 % 8) ||
+      (ldy % 8) || (rows % 128) || samples > GN_MAX_SAMPLES)
+    return AAB_ERR_ARG;
+  if (c2 > 0 && (!x2 || !colstats2 || (ld2 % 8))) return AAB_ERR_ARG;
+  int threads, rpc, chunks;
+  int r = gn_launch_cfg(C, samples, rows, &threads, &rpc, &chunks);
+  if (r) return r;
+  GnArgs a;
+  a.x1 = x1; a.x2 = x2; a.C1 = c1; a.C2 = c2; a.ld1 = ld1; a.ld2 = ld2; a.rows = rows; a.groups = groups;
+  a.rows_per_cta = rpc; a.bf16 = is_bf16;
+  float* mean_rstd = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + GN_HEADER_BYTES);
+  const int tps = static_cast<int>(rows / 128);
+  const int n = tps * (C / groups);
+  int fthreads = 32;
+  while (fthreads < n && fthreads < 256) fthreads <<= 1;
+  launch_k(gn_finalize_kernel, dim3(static_cast<unsigned>(groups), static_cast<unsigned>(samples)), dim3(fthreads), 0, stream,
+           colstats1, c1, colstats2, c2, tps, rows, groups, eps, mean_rstd);
+  dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(samples));
   launch_k(gn_apply_kernel, dim3(grid), dim3(threads), 0, stream, a, mean_rstd, gamma, beta, silu, y, ldy);
   return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }

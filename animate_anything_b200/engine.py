@@ -193,7 +193,8 @@ def resnet_forward(ctx: Ctx, m: L.ResnetBlock2D, x: torch.Tensor, g: Geo, skip: 
     if p["temb"] is not None and ctx.temb_all is not None:
         off = ctx.temb_off[id(m)]
         bias2 = ctx.temb_all[:, off: off + m.out_channels]
-    h = ops.conv3x3(h.view(g.n, g.h, g.w, cin), p["c1"][0], p["c1"][1], bias2=bias2, rows_per_bias2=g.t * g.hw)
+    # stats=True: the producing GEMM leaves per-tile column sums for the GroupNorm that reads this tensor next
+    h = ops.conv3x3(h.view(g.n, g.h, g.w, cin), p["c1"][0], p["c1"][1], bias2=bias2, rows_per_bias2=g.t * g.hw, stats=True)
     h = ops.groupnorm(h, g.n, g.hw, p["n2"][0], p["n2"][1], m.eps, True, m.groups)
     if p["sc"] is not None:
         sc = ops.conv1x1_cat(x, skip, p["sc"][0], p["sc"][1])
@@ -201,7 +202,7 @@ def resnet_forward(ctx: Ctx, m: L.ResnetBlock2D, x: torch.Tensor, g: Geo, skip: 
         assert skip is None
         sc = x
     return ops.conv3x3(h.view(g.n, g.h, g.w, m.out_channels), p["c2"][0], p["c2"][1], residual=sc,
-                       out_scale=1.0 / m.output_scale_factor)
+                       out_scale=1.0 / m.output_scale_factor, stats=True)
 
 
 def temporal_conv_forward(ctx: Ctx, m: L.TemporalConvLayer, x: torch.Tensor, g: Geo):
@@ -210,7 +211,7 @@ def temporal_conv_forward(ctx: Ctx, m: L.TemporalConvLayer, x: torch.Tensor, g: 
     h = x
     for i in range(4):
         gn = ops.groupnorm(h, g.b, g.t * g.hw, p["n"][i][0], p["n"][i][1], 1e-5, True, 32)
-        h = ops.tconv3(gn, g.b, g.t, g.hw, p["c"][i][0], p["c"][i][1], residual=x if i == 3 else None)
+        h = ops.tconv3(gn, g.b, g.t, g.hw, p["c"][i][0], p["c"][i][1], residual=x if i == 3 else None, stats=True)
     return h
 
 
@@ -254,7 +255,7 @@ def spatial_transformer_forward(ctx: Ctx, m: L.Transformer2DModel, x: torch.Tens
             hs = ops.linear(a, bp["o2"][0], bp["o2"][1], residual=hs)
         n3 = ops.layernorm(hs, bp["n3"][0], bp["n3"][1])
         hs = _ff(ctx, bp, hs, n3)
-    return ops.linear(hs, p["po"][0], p["po"][1], residual=x), g
+    return ops.linear(hs, p["po"][0], p["po"][1], residual=x, stats=True), g
 
 
 def temporal_transformer_forward(ctx: Ctx, m: L.TransformerTemporalModel, x: torch.Tensor, g: Geo):
@@ -276,7 +277,7 @@ def temporal_transformer_forward(ctx: Ctx, m: L.TransformerTemporalModel, x: tor
             hs = ops.linear(a, bp[ok][0], bp[ok][1], residual=hs)
         n3 = ops.layernorm(hs, bp["n3"][0], bp["n3"][1])
         hs = _ff(ctx, bp, hs, n3)
-    return ops.linear(hs, p["po"][0], p["po"][1], residual=x)
+    return ops.linear(hs, p["po"][0], p["po"][1], residual=x, stats=True)
 
 
 def downsample_forward(ctx: Ctx, m: L.Downsample2D, x: torch.Tensor, g: Geo, pad_mode="sym"):
@@ -288,7 +289,7 @@ def downsample_forward(ctx: Ctx, m: L.Downsample2D, x: torch.Tensor, g: Geo, pad
         if pad_mode != "sym":
             raise NotImplementedError("VAE encoder needs even feature-map sizes (image height/width multiples of 8)")
         x4 = ops.pad_to_even(x4)
-    out = ops.conv3x3_stride2(x4, p["c"][0], p["c"][1], pad_mode=pad_mode)
+    out = ops.conv3x3_stride2(x4, p["c"][0], p["c"][1], pad_mode=pad_mode, stats=True)
     return out
 
 
@@ -298,4 +299,4 @@ def upsample_forward(ctx: Ctx, m: L.Upsample2D, x: torch.Tensor, g: Geo, size=No
     p = ctx.prep.get(m)
     x4 = x.view(g.n, g.h, g.w, m.channels)
     up = ops.upsample2x(x4) if size is None or tuple(size) == (2 * g.h, 2 * g.w) else ops.upsample_nearest(x4, *size)
-    return ops.conv3x3(up, p["c"][0], p["c"][1])
+    return ops.conv3x3(up, p["c"][0], p["c"][1], stats=True)

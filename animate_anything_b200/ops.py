@@ -86,6 +86,22 @@ def pick_box(dims: Sequence[int], fixed_one: Sequence[int] = ()) -> list:
     return box
 
 
+def _tiles_cover_rows_in_order(dim_d, box) -> bool:
+    """True when m-tile i of the kernel's tile order holds exactly the output rows [128 i, 128 i + 128): every dim below
+    the first partially-boxed one is boxed whole, every dim above it has box 1, and the boxes divide the dims."""
+    i = 0
+    while i < 4 and box[i] == dim_d[i]:
+        i += 1
+    if i < 4:
+        if dim_d[i] % box[i]:
+            return False
+        i += 1
+    return all(box[j] == 1 for j in range(i, 4))
+
+
+GN_COLSTATS = os.environ.get("AAB_GN_COLSTATS", "1") != "0"
+
+
 def pick_block_n(n_out: int, m_tiles: int, geglu: bool = False, k_total: int = 1 << 30) -> int:
     """Tile width (GEMM columns, multiple of 32, <= 256).  Measured (profiles/r01_igemm_roles_small.log): a k-block
     costs ~520-660 clk whatever the tile width (operand feed, not MMA rate), so the widest tile wins wherever the main
@@ -114,8 +130,11 @@ def igemm(a: torch.Tensor, a_dims, a_strides, w: torch.Tensor, n: int, kc: int, 
           out: Optional[torch.Tensor] = None, ld_out: Optional[int] = None, *, bias=None, bias2=None, rows_per_bias2=1,
           residual=None, ld_res=None, act=ACT_NONE, out_scale=1.0, geglu=False, out_f32=False, a2=None, a2_dims=None,
           a2_strides=None, kc1=0, ld_b=None, b_batch=0, b_batch_stride=0, b_batch_dim=-1, block_n=None, direct=False,
-          max_ctas=0, out_rows=None, scale_acc=False):
-    """Generic launch of the implicit-GEMM kernel. `taps` is a list of 5-int offsets (channel, pix0..pix3)."""
+          max_ctas=0, out_rows=None, scale_acc=False, stats=False):
+    """Generic launch of the implicit-GEMM kernel. `taps` is a list of 5-int offsets (channel, pix0..pix3).
+    `stats=True`: the output feeds a GroupNorm -- have the epilogue also write per-(128-row tile, column) sums / sums of
+    squares of the rounded outputs (`out._aab_stats`, [m_tiles, n, 2] fp32) so that `groupnorm` can skip its statistics read.
+    Silently not produced when the launch takes an epilogue that cannot (the consumer then runs the two-pass GroupNorm)."""
     bf = _is_bf16(a)
     n_out = n // 2 if geglu else n
     rows = 1
@@ -191,6 +210,16 @@ def igemm(a: torch.Tensor, a_dims, a_strides, w: torch.Tensor, n: int, kc: int, 
     d.block_n = block_n
     d.max_ctas = max_ctas
     d.debug_cycles = None if IGEMM_DEBUG is None else IGEMM_DEBUG.data_ptr()
+    cstats = None
+    if stats and GN_COLSTATS and not geglu and _tiles_cover_rows_in_order(dim_d, box):
+        d.colstats = 1          # placeholder so that the C-side predicate sees "requested"
+        if _lib.load().aab_igemm_emits_colstats(C.byref(d)):
+            cstats = torch.empty((m_tiles, n_out, 2), device=a.device, dtype=torch.float32)
+            d.colstats = cstats.data_ptr()
+        else:
+            d.colstats = None
+    if cstats is not None:
+        out._aab_stats = cstats
     if IGEMM_PROFILE is not None:
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
@@ -332,6 +361,17 @@ def groupnorm(x: torch.Tensor, samples: int, rows: int, gamma: torch.Tensor, bet
     if need < 0:
         raise _lib.AabError("aab_groupnorm: unsupported channel count")
     ws = _gn_workspace(x.device, need)
+    st1 = getattr(x, "_aab_stats", None)
+    st2 = None if x2 is None else getattr(x2, "_aab_stats", None)
+    if GN_COLSTATS and st1 is not None and rows % 128 == 0 and (x2 is None or st2 is not None):
+        # statistics from the producing GEMMs' epilogues: finalize (tiny) + apply; bytes = one read + one write as before
+        assert st1.shape[0] * 128 == x.shape[0] and st1.shape[1] == c1
+        _profiled("groupnorm", 2.0 * 2 * x.shape[0] * (c1 + c2), 0.0,
+                  lambda: _lib.call("aab_groupnorm_colstats", _ptr(x), x.stride(0), c1, _ptr(st1), _ptr(x2),
+                                    0 if x2 is None else x2.stride(0), c2, _ptr(st2), samples, rows, groups, _ptr(gamma),
+                                    _ptr(beta), eps, int(silu), _ptr(y), y.stride(0), _ptr(ws), bf, _stream()),
+                  shape=(samples, rows, c1 + c2, int(silu), "colstats"))
+        return y
     # algorithmic bytes: one read + one write of the activation
     _profiled("groupnorm", 2.0 * 2 * x.shape[0] * (c1 + c2), 0.0,
               lambda: _lib.call("aab_groupnorm", _ptr(x), x.stride(0), c1, _ptr(x2), 0 if x2 is None else x2.stride(0), c2,
@@ -435,6 +475,13 @@ def dup_rows(x: torch.Tensor) -> torch.Tensor:
     assert x.is_contiguous()
     out = torch.empty((2 * x.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
     _lib.call("aab_dup_rows", _ptr(x), _ptr(out), x.numel() * x.element_size(), _stream())
+    st = getattr(x, "_aab_stats", None)
+    if st is not None and x.shape[0] % 128 == 0:
+        # the producer's per-tile column statistics travel with the rows (so that the duplicated tensor takes the same
+        # GroupNorm path, bit for bit, as a batch that was computed twice)
+        st2 = torch.empty((2 * st.shape[0],) + tuple(st.shape[1:]), device=st.device, dtype=st.dtype)
+        _lib.call("aab_dup_rows", _ptr(st), _ptr(st2), st.numel() * st.element_size(), _stream())
+        out._aab_stats = st2
     return out
 
 

@@ -284,7 +284,7 @@ class UNet3DConditionModel(ModelBase):
             mask = mask.to(dt)
         x8 = ops.unet_in_assemble(sample, condition_latent, mask if use_mask else None, g.t)
         wi = own["conv_in2"] if use_mask else own["conv_in"]
-        x = ops.conv3x3(x8.view(g.n, h, w, 8), wi[0], wi[1])
+        x = ops.conv3x3(x8.view(g.n, h, w, 8), wi[0], wi[1], stats=True)
         trace = self.__dict__.get("_trace")
         if trace is not None:
             trace.append(("conv_in", x, g))

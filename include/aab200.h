@@ -27,6 +27,10 @@ extern "C" {
  * FeedForward.net[2], Transformer*.proj_in/out, AutoencoderKL convs
  * (models/unet_3d_blocks.py:262-306,425-476,564-591,660-709,794-819; models/unet_3d_condition_mask.py:137-168,264). */
 int aab_igemm(const AabIgemmDesc* desc, void* stream);
+/* 1 when this launch will write desc->colstats (per m-tile column sums of the rounded outputs: the statistics of the GroupNorm
+ * that follows, diffusers ResnetBlock2D.norm2 / TemporalConvLayer / Transformer*Model.norm, taken in the producing GEMM's
+ * epilogue), 0 when its epilogue cannot (direct-store variants, GEGLU) and the caller must run the statistics pass. */
+int aab_igemm_emits_colstats(const AabIgemmDesc* desc);
 
 /* Spatial self-attention / text cross-attention, head_dim 64, flash-style on tcgen05
  * (diffusers AttnProcessor2_0 -> F.scaled_dot_product_attention; installed by train.py:124-138, blocks built at
@@ -53,6 +57,11 @@ long aab_groupnorm_workspace_bytes(long samples, long rows, int c, int groups);
 int aab_groupnorm(const void* x1, long ld1, int c1, const void* x2, long ld2, int c2, long samples, long rows, int groups,
                   const float* gamma, const float* beta, float eps, int silu, void* y, long ldy, void* workspace,
                   int is_bf16, void* stream);
+/* Same GroupNorm with the statistics pass replaced by the column sums the PRODUCING implicit GEMM wrote (AabIgemmDesc.colstats,
+ * [rows_total / 128][c][2] fp32): a tiny finalize kernel + the apply pass.  rows % 128 == 0 (every 128-row tile inside one sample). */
+int aab_groupnorm_colstats(const void* x1, long ld1, int c1, const float* colstats1, const void* x2, long ld2, int c2,
+                           const float* colstats2, long samples, long rows, int groups, const float* gamma, const float* beta,
+                           float eps, int silu, void* y, long ldy, void* workspace, int is_bf16, void* stream);
 
 /* LayerNorm over C per row (diffusers BasicTransformerBlock.norm1/2/3). */
 int aab_layernorm(const void* x, long ldx, void* y, long ldy, const float* gamma, const float* beta, long rows, int c,

@@ -197,3 +197,82 @@ def test_vae_boundary_kernels():
     vid = ops.vae_dec_finalize(y, b, f, 16, 16, False)
     ref = y[:, :3].to(dtype).float().reshape(b, f, 16, 16, 3).permute(0, 4, 1, 2, 3)
     assert torch.equal(vid, ref.contiguous())
+
+
+def _producer(ops, x, w, bias, mode, res=None, **kw):
+    if mode == "linear":
+        return ops.linear(x, w, bias, residual=res, stats=True, **kw)
+    return ops.conv3x3(x, w, bias, residual=res, stats=True, **kw)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("mode,m_or_shape,k,n,bn", [("linear", 1024, 320, 320, 64), ("linear", 4352, 640, 640, 128),
+                                                     ("linear", 2048, 1280, 1280, 256), ("conv", (3, 32, 32), 320, 320, 128),
+                                                     ("conv", (2, 16, 16), 640, 1280, 256)])
+def test_igemm_column_statistics(dtype, mode, m_or_shape, k, n, bn):
+    """`stats=True`: the epilogue's per-(128-row tile, column) sum / sum of squares of the ROUNDED output it stores."""
+    from animate_anything_b200 import ops
+    if mode == "linear":
+        m = m_or_shape
+        x = _rand((m, k), dtype, 1.0, 1)
+        w = _rand((n, k), dtype, k ** -0.5, 2)
+    else:
+        nb, h, wd = m_or_shape
+        m = nb * h * wd
+        x = _rand((nb, h, wd, k), dtype, 1.0, 1)
+        w = _rand((n, 9 * k), dtype, (9 * k) ** -0.5, 2)
+    bias = _rand((n,), torch.float32, 1.0, 3)
+    res = _rand((m, n), dtype, 1.0, 4)
+    for pair in ((False, "all") if bn == 256 else (False,)):
+        old = ops.IGEMM_PAIR
+        ops.IGEMM_PAIR = pair
+        try:
+            out = _producer(ops, x, w, bias, mode, res=res, block_n=bn)
+        finally:
+            ops.IGEMM_PAIR = old
+        st = getattr(out, "_aab_stats", None)
+        assert st is not None and tuple(st.shape) == (m // 128, n, 2)
+        o = out.double().reshape(m // 128, 128, n)
+        check(f"colstats sum {mode} {dtype} pair={pair}", st[..., 0], o.sum(1).float(), 1e-5, 1e-3)
+        check(f"colstats sumsq {mode} {dtype} pair={pair}", st[..., 1], (o * o).sum(1).float(), 1e-5, 1e-3)
+    # an epilogue that cannot emit them (fp32 output) must say so by not attaching anything
+    assert getattr(ops.linear(_rand((256, 64), dtype), _rand((64, 64), dtype), None, out_f32=True, stats=True), "_aab_stats", None) is None
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("samples,rows,c,silu", [(4, 256, 320, True), (2, 17 * 256, 640, False), (34, 1024, 640, True)])
+def test_groupnorm_from_producer_statistics(dtype, samples, rows, c, silu):
+    """GroupNorm fed by the producing GEMM's column statistics == the two-pass GroupNorm of the same tensor up to the
+    rounding of fp32 tile sums (well inside the fp32-reference tolerance), second source = virtual concat."""
+    from animate_anything_b200 import ops
+    m = samples * rows
+    x = _rand((m, 320), dtype, 1.0, 1)
+    w = _rand((c, 320), dtype, 320 ** -0.5, 2)
+    bias = _rand((c,), torch.float32, 0.5, 3)
+    h = ops.linear(x, w, bias, stats=True)
+    h2 = ops.linear(x, w.flip(0).contiguous(), bias, stats=True)
+    assert getattr(h, "_aab_stats", None) is not None
+    gamma = _rand((c,), torch.float32, 0.2, 2, shift=1.0)
+    beta = _rand((c,), torch.float32, 0.2, 3)
+    y = ops.groupnorm(h, samples, rows, gamma, beta, 1e-5, silu)
+    y_again = ops.groupnorm(h, samples, rows, gamma, beta, 1e-5, silu)
+    assert torch.equal(y, y_again)
+    plain = h.clone()                                  # no statistics attached -> two-pass kernel
+    y2 = ops.groupnorm(plain, samples, rows, gamma, beta, 1e-5, silu)
+    ref = F.group_norm(h.float().reshape(samples, rows, c).permute(0, 2, 1), 32, gamma, beta, 1e-5)
+    ref = (F.silu(ref) if silu else ref).permute(0, 2, 1).reshape(m, c)
+    check(f"groupnorm(colstats) s{samples} r{rows} c{c} {dtype}", y, ref, *TOL[dtype])
+    ulp = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
+    assert (y.float() - y2.float()).abs().max().item() <= 2 * ulp * max(1.0, y2.float().abs().max().item())
+    # virtual concat of two producers
+    g2 = _rand((2 * c,), torch.float32, 0.2, 5, shift=1.0)
+    b2 = _rand((2 * c,), torch.float32, 0.2, 6)
+    yc = ops.groupnorm(h, samples, rows, g2, b2, 1e-5, silu, x2=h2)
+    refc = F.group_norm(torch.cat([h, h2], 1).float().reshape(samples, rows, 2 * c).permute(0, 2, 1), 32, g2, b2, 1e-5)
+    refc = (F.silu(refc) if silu else refc).permute(0, 2, 1).reshape(m, 2 * c)
+    check(f"groupnorm(colstats, concat) {dtype}", yc, refc, *TOL[dtype])
+    # batch invariance: sample 1 alone gives the same bits as inside the batch
+    xs = x[rows:2 * rows].contiguous()
+    hs = ops.linear(xs, w, bias, stats=True)
+    ys = ops.groupnorm(hs, 1, rows, gamma, beta, 1e-5, silu)
+    assert torch.equal(ys, y[rows:2 * rows])

@@ -112,7 +112,7 @@ else:
     for t in table[:40]:
         print(f"rows={t['rows']:7d} n={t['n']:5d} k={t['k']:6d} taps={t['taps']} bn={t['block_n']:3d}{'p' if t['pair'] else ' '} x{t['count']:3d} "
               f"{t['ms']:8.3f} ms  {t['tflops']:7.1f} TFLOP/s")
-    json.dump(table, open(os.path.join(ROOT, "gpurun_out", "igemm_shapes.json"), "w"), indent=1)
+    json.dump(table, open(os.path.join(ROOT, "gpurun_out", "igemm_shapes%s.json" % os.environ.get("AAB_PROFILE_TAG", "")), "w"), indent=1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(3):
