@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("AAB_LIB_PATH") or os.path.join(_HERE, "libaab200.so")
 MAX_TAPS = 9
 ACT_NONE, ACT_SILU, ACT_GELU, ACT_QUICK_GELU = 0, 1, 2, 3
 F_BF16, F_DIRECT, F_OUT_F32, F_GEGLU, F_SCALE_ACC, F_PAIR = 1, 2, 4, 8, 16, 32
+F_QUAD = 16384
 
 
 class IgemmDesc(C.Structure):

@@ -34,6 +34,43 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// packed fp32 pairs (Blackwell FFMA2 / FADD2): half the issue slots of the softmax's scale-and-subtract, row-sum and O updates
+__device__ __forceinline__ float2 ffma2(float ax, float ay, float2 b, float2 c) {
+  float2 d;
+  asm("{\n.reg .b64 ra, rb, rc, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmov.b64 rc, {%6, %7};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\nmov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(ax), "f"(ay), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nadd.rn.f32x2 rd, ra, rb;\nmov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+
+// 2^t for a pair of t <= 0 on the FMA / ALU pipes instead of the MUFU (16 results / clk / SM, the busiest pipe of the d=64 softmax:
+// ncu 56 % of peak in round 2a): t = j + f, j = round(t) through the 1.5 * 2^23 magic add, f in [-0.5, 0.5], 2^f by a degree-4
+// polynomial (max relative error 2.7e-6, far below the 16-bit rounding of P), 2^j by an integer add into the exponent field.
+__device__ __forceinline__ float2 exp2_poly2(float2 t) {
+  t.x = fmaxf(t.x, -126.f);
+  t.y = fmaxf(t.y, -126.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f);
+  const float2 tt = fadd2(t, magic);
+  const float2 r = fadd2(tt, make_float2(-12582912.f, -12582912.f));
+  const float2 f = ffma2(r.x, r.y, make_float2(-1.f, -1.f), t);
+  float2 q = ffma2(f.x, f.y, make_float2(0.00956052f, 0.00956052f), make_float2(0.05591708f, 0.05591708f));
+  q = ffma2(q.x, q.y, f, make_float2(0.24024981f, 0.24024981f));
+  q = ffma2(q.x, q.y, f, make_float2(0.69312196f, 0.69312196f));
+  q = ffma2(q.x, q.y, f, make_float2(0.99999919f, 0.99999919f));
+  float2 o;
+  o.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(tt.x) << 23));
+  o.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(tt.y) << 23));
+  return o;
+}
+
 struct FaParams {
   int Lq, Lk, heads, kv_batch_div;
   int q_col0, k_col0, v_col0;
@@ -153,6 +190,10 @@ flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     mbar_wait(q_full, 0);
     mbar_wait(&kv_full[0], 0);
     tc_fence_after();
+    // (An in-phase order -- both tiles' MMAs interleaved instruction by instruction so that consecutive tcgen05.mma never share
+    // an accumulator, S(j+1) issued as soon as both warpgroups had loaded S(j) -- was built and measured: 1538 us against 1234
+    // for L = 4096.  The staggered order below lets one warpgroup's softmax overlap the other's MMAs, and the softmax, not the
+    // tensor pipe (28 % busy), is what this kernel waits for: profiles/r02_flash_softmax.md.)
     issue_s(0, 0);
     issue_s(1, 0);
     for (int j = 0; j < nkv; ++j) {
@@ -203,43 +244,74 @@ flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
       float alpha, lsum = 0.f;
       if (valid >= 128 && !p.causal) {
-        // ---------------- common case: no per-element predicates
-        float mx = -INFINITY;
+        // ---------------- common case (no per-element predicates).  Round 2b: four independent partial maxima / packed partial sums
+        // (the round-1 loops were one dependent chain each), packed fp32 scale-and-subtract; (a) the tcgen05.ld of chunk c + 1 is in flight
+        // while chunk c is processed (two 32-register buffers), the exponential pass walks the chunks 3, 0, 1, 2 so that the last
+        // chunk of the max pass is reused without a reload; (b) one pair in four of the exponentials is evaluated by
+        // exp2_poly2 on the FMA pipes.
+        uint32_t ra[32], rb[32];
+        float mxa = -INFINITY, mxb = -INFINITY, mxc = -INFINITY, mxd = -INFINITY;
+        auto max32 = [&](const uint32_t* r) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(t_s + c * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-        }
+          for (int i = 0; i < 32; i += 8) {
+            mxa = fmaxf(mxa, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
+            mxb = fmaxf(mxb, fmaxf(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
+            mxc = fmaxf(mxc, fmaxf(__uint_as_float(r[i + 4]), __uint_as_float(r[i + 5])));
+            mxd = fmaxf(mxd, fmaxf(__uint_as_float(r[i + 6]), __uint_as_float(r[i + 7])));
+          }
+        };
+        tmem_ld_32x32(t_s, ra);
+        tmem_ld_wait();
+        tmem_ld_32x32(t_s + 32, rb);
+        max32(ra);
+        tmem_ld_wait();
+        tmem_ld_32x32(t_s + 64, ra);
+        max32(rb);
+        tmem_ld_wait();
+        tmem_ld_32x32(t_s + 96, rb);
+        max32(ra);
+        tmem_ld_wait();
+        tmem_ld_32x32(t_s, ra);            // chunk 0 again, for the exponential pass (chunk 3 stays in rb)
+        max32(rb);
+        const float mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
         const float m_new = fmaxf(m_run, mx * p.scale_log2);
         alpha = fast_exp2(m_run - m_new);
         m_run = m_new;
         if (j > 0) mbar_wait(&p_free[tile], jph ^ 1);   // P.V(j-1) has read the P tile
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(t_s + c * 32, r);
-          tmem_ld_wait();
+        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+        const float2 nm2 = make_float2(-m_new, -m_new);
+        float2 ls[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        auto exp32 = [&](const uint32_t* r, int c) {
           uint8_t* hp = prow + (c >> 1) * FA_TILE_BYTES;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            float e[8];
+            float2 e[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              e[i] = fast_exp2(fmaf(__uint_as_float(r[g * 8 + i]), p.scale_log2, -m_new));
-              lsum += e[i];
+            for (int i = 0; i < 4; ++i) {
+              const float2 t = ffma2(__uint_as_float(r[g * 8 + 2 * i]), __uint_as_float(r[g * 8 + 2 * i + 1]), sc2, nm2);
+              e[i] = (i == 3) ? exp2_poly2(t) : make_float2(fast_exp2(t.x), fast_exp2(t.y));
+              ls[i] = fadd2(ls[i], e[i]);
             }
             uint4 u;
-            u.x = pack2(e[0], e[1], bf16);
-            u.y = pack2(e[2], e[3], bf16);
-            u.z = pack2(e[4], e[5], bf16);
-            u.w = pack2(e[6], e[7], bf16);
+            u.x = pack2(e[0].x, e[0].y, bf16);
+            u.y = pack2(e[1].x, e[1].y, bf16);
+            u.z = pack2(e[2].x, e[2].y, bf16);
+            u.w = pack2(e[3].x, e[3].y, bf16);
             const int chunk = (c & 1) * 4 + g;
             *reinterpret_cast<uint4*>(hp + ((chunk ^ (row & 7)) << 4)) = u;
           }
-        }
+        };
+        exp32(rb, 3);
+        tmem_ld_wait();
+        tmem_ld_32x32(t_s + 32, rb);
+        exp32(ra, 0);
+        tmem_ld_wait();
+        tmem_ld_32x32(t_s + 64, ra);
+        exp32(rb, 1);
+        tmem_ld_wait();
+        exp32(ra, 2);
+        const float2 l01 = fadd2(ls[0], ls[1]), l23 = fadd2(ls[2], ls[3]);
+        lsum = (l01.x + l01.y) + (l23.x + l23.y);
       } else {
         // ---------------- tail block: keys >= valid are masked to -inf / 0
         float mx = -INFINITY;
@@ -295,7 +367,12 @@ flash_attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           tmem_ld_32x32(t_o + c * 32, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; i += 2) {
+            const float2 t = ffma2(o_acc[c * 32 + i], o_acc[c * 32 + i + 1], make_float2(alpha_prev, alpha_prev),
+                                   make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
+            o_acc[c * 32 + i] = t.x;
+            o_acc[c * 32 + i + 1] = t.y;
+          }
         }
         tc_fence_before();
         mbar_arrive(&o_free[tile]);

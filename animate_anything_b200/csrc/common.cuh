@@ -194,10 +194,22 @@ __device__ __forceinline__ void umma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_
       : "memory");
 }
 // arrive (once all previously issued MMAs of the pair completed) on the same-offset barrier of BOTH CTAs
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+// arrive (once the MMAs issued so far have completed) on the copy of `bar` in every CTA of `cta_mask` (cluster ranks)
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask = 3) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
                : "memory");
+}
+// TMA load delivered to the same shared-memory offset of every CTA in `cta_mask`; each destination's transaction bytes are
+// credited to the LEADER of the destination's CTA pair (peer bit cleared in the barrier address)
+__device__ __forceinline__ void tma_load_3d_pair_mcast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                                       uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5, %6}], [%2], %3;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "h"(cta_mask), "r"(c0),
+      "r"(c1), "r"(c2)
+      : "memory");
 }
 
 // ---------------------------------------------------------------- named barriers

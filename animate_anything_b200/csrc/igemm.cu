@@ -109,10 +109,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // PAIR: the two CTAs of a cluster walk the same list of PAIR tiles (two consecutive m-tiles x one n-tile); CTA rank r owns
   // m-tile 2 * pm + r.  With an odd number of m-tiles the last pair's second m-tile does not exist: rank 1 then recomputes
   // m-tile 0 (coordinates wrap) and its epilogue stores nothing.
-  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
-  const int tile_first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int tile_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const int num_tiles = (PAIR ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * p.num_n_tiles;
+  // QUAD (p.cluster == 4, runtime): two pairs stacked along M share every weight tile -- each CTA fetches HALF of its pair-half
+  // (64 rows) and multicasts it to the CTA of the same pair rank in the other pair, so a k-block costs 24 KB of L2 reads per
+  // CTA instead of 32 KB (the L2 -> shared-memory feed is what paces this kernel, profiles/r02_igemm_split_issue.md).
+  const uint32_t clrank = PAIR ? cluster_ctarank() : 0u;        // rank in the cluster: m-tile offset inside the cluster tile
+  const uint32_t crank = clrank & 1u;                            // rank in the CTA pair (0 = leader, issues the MMAs)
+  const uint32_t qrank = clrank >> 1;                            // which pair of the cluster
+  const int CL = PAIR ? p.cluster : 1;
+  const bool quad = PAIR && CL == 4;
+  const int tile_first = static_cast<int>(blockIdx.x) / CL;
+  const int tile_step = static_cast<int>(gridDim.x) / CL;
+  const int num_tiles = ((p.num_m_tiles + CL - 1) / CL) * p.num_n_tiles;
   const int kb_per_tap = p.kb_per_tap;
   const int k_iters = p.num_taps * kb_per_tap;
 
@@ -127,7 +134,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (elect_one()) {
       for (int i = 0; i < STAGES; ++i) {
         mbar_init(&full_bar[i], 1);
-        mbar_init(&empty_bar[i], 1);
+        mbar_init(&empty_bar[i], quad ? 2 : 1);   // QUAD: a stage is refilled by two CTAs' loads, read by two pairs' MMAs
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull_bar[i], 1);
@@ -162,7 +169,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         const int nt = tile % p.num_n_tiles;
         int mt = tile / p.num_n_tiles;
-        if (PAIR) mt = 2 * mt + static_cast<int>(crank);
+        if (PAIR) mt = CL * mt + static_cast<int>(clrank);
         int cb[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -173,12 +180,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int n0 = nt * OUT_BN;
         // PAIR: this CTA stages rows [crank * n_mma / 2, (crank + 1) * n_mma / 2) of the weight tile (n_mma = valid columns
         // rounded up to 32); for GEGLU rank 0 holds the value rows and rank 1 the gate rows
-        int nb0 = n0;
+        int nb0 = n0, bq_off = 0;
         if (PAIR && !GEGLU) {
           int nv = p.N - n0;
           nv = nv < BN ? ((nv + 31) & ~31) : BN;
           nb0 = n0 + static_cast<int>(crank) * (nv / 2);
+          if (quad) nb0 += static_cast<int>(qrank) * (nv / 4);     // this CTA's quarter; lands nv/4 rows into the stage
+          bq_off = static_cast<int>(qrank) * (nv / 4) * 128;
         }
+        if (PAIR && GEGLU) {
+          nb0 = (crank ? p.N / 2 : 0) + n0 + (quad ? static_cast<int>(qrank) * 64 : 0);
+          bq_off = quad ? static_cast<int>(qrank) * 64 * 128 : 0;
+        }
+        const uint16_t bq_mask = static_cast<uint16_t>((1u << crank) | (1u << (crank + 2)));   // same pair rank, both pairs
         for (int tap = 0; tap < p.num_taps; ++tap) {
           const int o0 = p.tap_off[tap][0], o1 = p.tap_off[tap][1], o2 = p.tap_off[tap][2], o3 = p.tap_off[tap][3],
                     o4 = p.tap_off[tap][4];
@@ -204,8 +218,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               else
                 tma_load_5d_pair(smA + s * A_STAGE_BYTES, &tmA2, &full_bar[s], kc - p.Kc1 + o0, cb[0] + o1, cb[1] + o2,
                                  cb[2] + o3, cb[3] + o4);
-              if (GEGLU)
-                tma_load_3d_pair(smB + s * C::B_STAGE_BYTES, &tmB, &full_bar[s], kg, (crank ? p.N / 2 : 0) + n0, bbatch);
+              if (quad)     // 64-row box (8 KB) to this CTA and to its twin in the other pair; the twin sends the other one
+                tma_load_3d_pair_mcast(smB + s * C::B_STAGE_BYTES + bq_off, &tmB, &full_bar[s], kg, nb0, bbatch, bq_mask);
               else
                 tma_load_3d_pair(smB + s * C::B_STAGE_BYTES, &tmB, &full_bar[s], kg, nb0, bbatch);
               continue;
@@ -286,9 +300,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             else umma_f16_ss(tmem_d, da, db, idesc, (ki > 0 || k > 0) ? 1u : 0u);
             if (k == BK / 32 - 1) ready = !nosync && !(p.flags & AAB_F_DBG_NO_PEEK) && mbar_test_wait(&full_bar[s1], ph1);
           }
-          if (PAIR) {                       // release the stage / publish the accumulator in BOTH CTAs
-            umma_commit_pair(&empty_bar[s]);
-            if (ki == k_iters - 1) umma_commit_pair(&tfull_bar[as]);
+          if (PAIR) {                       // release the stage (QUAD: in all four CTAs) / publish the accumulator in BOTH CTAs
+            umma_commit_pair(&empty_bar[s], quad ? static_cast<uint16_t>(15) : static_cast<uint16_t>(3));
+            if (ki == k_iters - 1) umma_commit_pair(&tfull_bar[as], static_cast<uint16_t>(3u << (2 * qrank)));
           } else {
             if (!nosync) umma_commit(&empty_bar[s]);
             if (ki == k_iters - 1) umma_commit(&tfull_bar[as]);
@@ -344,7 +358,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t aph = (tl >> 1) & 1;
       const int nt = tile % p.num_n_tiles;
       int mt = tile / p.num_n_tiles;
-      if (PAIR) mt = 2 * mt + static_cast<int>(crank);
+      if (PAIR) mt = CL * mt + static_cast<int>(clrank);
       const bool tile_ok = !PAIR || mt < p.num_m_tiles;      // PAIR, odd m-tile count: rank 1 of the last pair stores nothing
       const int mt_lin = mt;                                  // linear m-tile index (row of the column-statistics table)
       int cb[4];
@@ -697,31 +711,51 @@ static int launch_bn(const CUtensorMap& a, const CUtensorMap& a2, const CUtensor
   return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }
 
-// CTA-pair launch: clusters of 2, persistent over pair tiles (two m-tiles x one n-tile)
+// CTA-pair launch: clusters of 2 (or 4: p.cluster), persistent over cluster tiles (p.cluster consecutive m-tiles x one n-tile)
 template <int EPI>
 static int launch_pair(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& d,
                        const CUtensorMap& r, const IgemmParams& p, int max_ctas, cudaStream_t stream) {
   using CF = Cfg<256, true>;
   static std::atomic<unsigned long long> attr_done{0};
   if (int rc = ensure_dyn_smem(igemm_kernel<256, EPI, true>, CF::SMEM_BYTES, attr_done)) return rc;
-  const int pair_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
-  int clusters = num_sms() / 2;
-  if (pair_tiles < clusters) clusters = pair_tiles;
-  if (max_ctas > 0 && clusters > max_ctas / 2) clusters = max_ctas / 2 > 0 ? max_ctas / 2 : 1;
+  const int cl = p.cluster;
+  const int cl_tiles = ((p.num_m_tiles + cl - 1) / cl) * p.num_n_tiles;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(static_cast<unsigned>(2 * clusters));
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = CF::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cl);
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int clusters = num_sms() / cl;
+  if (cl == 4) {
+    // clusters of 4 must fit inside a GPC: ask the driver how many can be resident at once (cached per device)
+    static std::atomic<int> max_quads[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int mq = max_quads[dev & 63].load(std::memory_order_acquire);
+    if (mq == 0) {
+      cfg.gridDim = dim3(static_cast<unsigned>(4 * (num_sms() / 4)));
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, igemm_kernel<256, EPI, true>, &cfg) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        n = 1;
+      }
+      mq = n;
+      max_quads[dev & 63].store(mq, std::memory_order_release);
+    }
+    if (clusters > mq) clusters = mq;
+  }
+  if (cl_tiles < clusters) clusters = cl_tiles;
+  if (max_ctas > 0 && clusters > max_ctas / cl) clusters = max_ctas / cl > 0 ? max_ctas / cl : 1;
+  cfg.gridDim = dim3(static_cast<unsigned>(cl * clusters));
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_kernel<256, EPI, true>, a, a2, b, d, r, p);
   return e == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
@@ -866,7 +900,8 @@ extern "C" int aab_igemm(const AabIgemmDesc* d, void* stream_) {
   if (pair) {
     long dimsb[3] = {static_cast<long>(d->num_taps) * d->kc, d->n, 1};
     long stridesb[3] = {1, d->ld_b, static_cast<long>(d->n) * d->ld_b};
-    int boxb[3] = {BK, 128, 1};
+    p.cluster = ((d->flags & AAB_F_QUAD) && p.num_m_tiles >= 4) ? 4 : 2;
+    int boxb[3] = {BK, p.cluster == 4 ? 64 : 128, 1};      // QUAD: every CTA fetches a quarter of the weight tile
     int rb = make_tmap_16(&tmB, d->b, 3, dimsb, stridesb, boxb, is_bf16, 128);
     if (rb) return rb;
     if (geglu) return launch_pair<1>(tmA, tmA2, tmB, tmD, tmR, p, d->max_ctas, stream);

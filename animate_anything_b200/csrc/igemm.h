@@ -17,6 +17,7 @@
 #define AAB_F_DBG_NO_SYNC 256 /* diagnostics only: with NO_LOAD, the MMA warp neither waits for stages nor commits them -> raw tcgen05.mma issue rate */
 #define AAB_F_DBG_NO_LOAD 128 /* diagnostics only (wrong results): no TMA loads, stages are always full -> pure MMA + epilogue rate */
 #define AAB_F_SCALE_ACC 16 /* out = act(acc + bias + bias2) * out_scale + residual (scale BEFORE the residual; direct store only) */
+#define AAB_F_QUAD 16384 /* with AAB_F_PAIR: clusters of 4 = two CTA pairs stacked along M; every weight tile is fetched once per cluster (TMA multicast) */
 #define AAB_F_PAIR 32     /* 256-column tiles on CTA pairs (cta_group::2): two m-tiles per tcgen05.mma, half a weight tile per CTA */
 #define AAB_F_GEGLU 8     /* B rows [0,N/2) are values, [N/2,N) gates: out = value * gelu(gate), N/2 columns */
 
@@ -90,6 +91,7 @@ struct IgemmParams {
   int flags;
   unsigned long long* dbg;
   float* colstats;
+  int cluster;     /* CTAs per cluster of the pair kernels: 2, or 4 (two pairs sharing the weight tile through TMA multicast) */
 };
 int make_tmap_16(CUtensorMap* out, const void* base, int rank, const long* dims, const long* strides, const int* box,
                  int is_bf16, int swizzle_bytes = 128);

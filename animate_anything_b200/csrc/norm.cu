@@ -515,6 +515,28 @@ static int gn_launch_cfg(int C, long samples, long rows, int* threads, int* rows
   return AAB_OK;
 }
 
+// The apply pass is elementwise: its row partition is free (unlike the statistics pass, whose partition fixes the summation
+// order).  The statistics partition gives 612 CTAs at level 0 = 1.38 waves of the 444 resident CTAs (3 per SM): the second wave
+// runs 38 % full.  Here the rows are cut so that the launch is ~6 waves of small CTAs (AAB_GN_APPLY_WAVES, 0 = the statistics
+// partition), each thread still walking >= 4 rows.
+static int gn_apply_rows_per_cta(int C, long samples, long rows, int stats_rpc) {
+  static int waves = -1;
+  if (waves < 0) {
+    const char* e = getenv("AAB_GN_APPLY_WAVES");
+    waves = e ? atoi(e) : 6;
+  }
+  if (waves <= 0) return stats_rpc;
+  const int V = C / 8;
+  int rpi = 256 / V;
+  if (rpi < 1) rpi = 1;
+  const long slots = 3L * num_sms() * waves;
+  long rpc = (rows * samples + slots - 1) / slots;
+  if (rpc < 4L * rpi) rpc = 4L * rpi;
+  rpc = ((rpc + rpi - 1) / rpi) * rpi;
+  if (rpc > stats_rpc) rpc = stats_rpc;
+  return static_cast<int>(rpc);
+}
+
 // Workspace layout (bytes): a FIXED 16 KiB header of tickets (one u32 per sample) that must be zero before the first use
 // and is self-resetting afterwards (fixed offset: calls with different sample counts share one workspace, and a ticket must
 // never alias another call's statistics); then mean/rstd floats [samples*groups*2], then double partials
@@ -564,7 +586,12 @@ extern "C" int aab_groupnorm(const void* x1, long ld1, int c1, const void* x2, l
   // CTA, while two plain launches let the hardware overlap the tail of one with the head of the next.  Not kept.
   dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(samples));
   launch_k(gn_stats_kernel, dim3(grid), dim3(threads), smem, stream, a, partial, mean_rstd, ticket, eps);
-  launch_k(gn_apply_kernel, dim3(grid), dim3(threads), 0, stream, a, mean_rstd, gamma, beta, silu, y, ldy);
+  {
+    GnArgs aa = a;
+    aa.rows_per_cta = gn_apply_rows_per_cta(C, samples, rows, rpc);
+    dim3 ga(static_cast<unsigned>((rows + aa.rows_per_cta - 1) / aa.rows_per_cta), static_cast<unsigned>(samples));
+    launch_k(gn_apply_kernel, dim3(ga), dim3(threads), 0, stream, aa, mean_rstd, gamma, beta, silu, y, ldy);
+  }
   return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }
 
@@ -594,7 +621,12 @@ extern "C" int aab_groupnorm_colstats(const void* x1, long ld1, int c1, const fl
   launch_k(gn_finalize_kernel, dim3(static_cast<unsigned>(groups), static_cast<unsigned>(samples)), dim3(fthreads), 0, stream,
            colstats1, c1, colstats2, c2, tps, rows, groups, eps, mean_rstd);
   dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(samples));
-  launch_k(gn_apply_kernel, dim3(grid), dim3(threads), 0, stream, a, mean_rstd, gamma, beta, silu, y, ldy);
+  {
+    GnArgs aa = a;
+    aa.rows_per_cta = gn_apply_rows_per_cta(C, samples, rows, rpc);
+    dim3 ga(static_cast<unsigned>((rows + aa.rows_per_cta - 1) / aa.rows_per_cta), static_cast<unsigned>(samples));
+    launch_k(gn_apply_kernel, dim3(ga), dim3(threads), 0, stream, aa, mean_rstd, gamma, beta, silu, y, ldy);
+  }
   return cudaGetLastError() == cudaSuccess ? AAB_OK : AAB_ERR_CUDA;
 }
 

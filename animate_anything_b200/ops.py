@@ -12,7 +12,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_NONE, ACT_QUICK_GELU, ACT_SILU, F_BF16, F_DIRECT, F_GEGLU, F_OUT_F32, F_PAIR, F_SCALE_ACC,
+from ._lib import (ACT_GELU, ACT_NONE, ACT_QUICK_GELU, ACT_SILU, F_BF16, F_DIRECT, F_GEGLU, F_OUT_F32, F_PAIR, F_QUAD, F_SCALE_ACC,
                    IgemmDesc)
 
 NUM_SMS = 148
@@ -99,6 +99,7 @@ def _tiles_cover_rows_in_order(dim_d, box) -> bool:
     return all(box[j] == 1 for j in range(i, 4))
 
 
+IGEMM_QUAD = os.environ.get("AAB_IGEMM_QUAD", "0") != "0"     # clusters of 4 with weight-tile multicast (see igemm.cu)
 GN_COLSTATS = os.environ.get("AAB_GN_COLSTATS", "1") != "0"
 
 
@@ -206,6 +207,8 @@ def igemm(a: torch.Tensor, a_dims, a_strides, w: torch.Tensor, n: int, kc: int, 
             block_n = pick_block_n(n_out, m_tiles, geglu, kc * len(taps))
     if block_n == 256 and use_pair(kc * len(taps), n):
         flags |= F_PAIR
+        if IGEMM_QUAD:
+            flags |= F_QUAD
     d.flags = flags | IGEMM_DBG_FLAGS
     d.block_n = block_n
     d.max_ctas = max_ctas

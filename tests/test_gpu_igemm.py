@@ -177,18 +177,21 @@ def test_batched_gemm_qk():
 
 
 # ------------------------------------------------------------------------------------------------ CTA pairs (cta_group::2)
-@pytest.fixture
-def pair_mode():
+@pytest.fixture(params=["pair", "quad"])
+def pair_mode(request):
+    """pair: clusters of 2; quad: clusters of 4 (two pairs, weight tile fetched once per cluster through TMA multicast; launches
+    with fewer than 4 m-tiles fall back to clusters of 2 by themselves)."""
     ops = _ops()
-    old = ops.IGEMM_PAIR
+    old, oldq = ops.IGEMM_PAIR, ops.IGEMM_QUAD
     ops.IGEMM_PAIR = "all"
+    ops.IGEMM_QUAD = request.param == "quad"
     yield ops
-    ops.IGEMM_PAIR = old
+    ops.IGEMM_PAIR, ops.IGEMM_QUAD = old, oldq
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("m,k,n", [(256, 64, 256), (4096, 512, 512), (1000, 640, 1280), (139264 // 8, 320, 320),
-                                   (384, 1280, 2560), (130, 320, 256), (8704, 1280, 1280)])
+                                   (384, 1280, 2560), (130, 320, 256), (8704, 1280, 1280), (640, 320, 576), (896, 2880, 320)])
 def test_pair_linear(pair_mode, dtype, m, k, n):
     """256-column tiles on CTA pairs: even / odd numbers of m-tiles (130 rows = 2 tiles, 1000 = 8, 384 = 3: rank 1 of the last
     pair stores nothing), ragged last n-tile (320 = 256 + 64), partial last m-tile; bit-identical to the single-CTA kernel

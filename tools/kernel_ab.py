@@ -93,3 +93,14 @@ if what in ("fa", "all"):
         print(f"| flash cross-attn | ({nb}, {heads}, {lq}, {lk}) | {us:.1f} | {by / us / 1e3:.0f} | {by / us / 1e3 / HBM:.2f} | "
               f"{fl / us / 1e6:.0f} TFLOP/s |")
         del qs
+if what in ("sa", "all"):
+    # spatial self-attention of a config-2 forward (fused qkv input): L = 4096 / 1024 / 256 / 64 tokens per frame
+    print("| flash self-attn | (nb, heads, L) | us / call | TFLOP/s |")
+    for nb, heads, l in [(34, 5, 4096), (34, 10, 1024), (34, 20, 256), (34, 20, 64)]:
+        c = heads * 64
+        nbuf = 2
+        qkvs = [torch.randn(nb * l, 3 * c, device=dev).to(dt) for _ in range(nbuf)]
+        us = timeit(lambda i: ops.flash_attn_d64(qkvs[i], 0, qkvs[i], c, 2 * c, nb, l, l, heads), nbuf, iters=8)
+        fl = 4.0 * nb * heads * l * l * 64
+        print(f"| flash self-attn | ({nb}, {heads}, {l}) | {us:.1f} | {fl / us / 1e6:.0f} |")
+        del qkvs
