@@ -517,13 +517,13 @@ static int gn_launch_cfg(int C, long samples, long rows, int* threads, int* rows
 
 // The apply pass is elementwise: its row partition is free (unlike the statistics pass, whose partition fixes the summation
 // order).  The statistics partition gives 612 CTAs at level 0 = 1.38 waves of the 444 resident CTAs (3 per SM): the second wave
-// runs 38 % full.  Here the rows are cut so that the launch is ~6 waves of small CTAs (AAB_GN_APPLY_WAVES, 0 = the statistics
+// runs 38 % full.  Here the rows are cut so that the launch is ~3 waves of CTAs (AAB_GN_APPLY_WAVES; measured 0 / 3 / 6 / 12: 73.4 / 70.7 / 73.5 / 79.7 us at level 0; 0 = the statistics
 // partition), each thread still walking >= 4 rows.
 static int gn_apply_rows_per_cta(int C, long samples, long rows, int stats_rpc) {
   static int waves = -1;
   if (waves < 0) {
     const char* e = getenv("AAB_GN_APPLY_WAVES");
-    waves = e ? atoi(e) : 6;
+    waves = e ? atoi(e) : 3;
   }
   if (waves <= 0) return stats_rpc;
   const int V = C / 8;

@@ -79,6 +79,42 @@ def test_pick_box_and_block_n():
     assert ops.pick_block_n(320, 1088, k_total=320) == 128
 
 
+def test_column_statistics_tile_order_predicate():
+    """`ops.igemm(stats=True)` only asks for the epilogue's column sums when m-tile i of the kernel's tile order is exactly the
+    output rows [128 i, 128 i + 128): the GroupNorm finalize kernel adds a sample's tiles by index."""
+    from animate_anything_b200 import ops
+    ok = ops._tiles_cover_rows_in_order
+    for dim_d in [(64, 64, 34, 1), (32, 32, 34, 1), (16, 16, 34, 1), (8, 8, 34, 1), (4096, 17, 2, 1), (256, 17, 2, 1),
+                  (139264, 1, 1, 1), (512, 512, 16, 1)]:
+        assert ok(dim_d, ops.pick_box(dim_d)), dim_d
+    assert ok((32, 1, 32, 34), ops.pick_box((32, 1, 32, 34), fixed_one=(1,)))       # stride-2 conv through space-to-depth
+    assert not ok((15, 17, 34, 1), ops.pick_box((15, 17, 34, 1)))                   # odd latent size: partial boxes
+    assert not ok((64, 17, 2, 1), ops.pick_box((64, 17, 2, 1)))                     # 8 x 8 level of the temporal conv: 17 % 2
+    assert not ok((100, 1, 1, 1), (128, 1, 1, 1))
+    # simulate the kernel's tile decode and check the claim itself on a few shapes
+    import itertools
+    for dim_d in [(16, 16, 3, 1), (8, 8, 4, 1), (256, 5, 2, 1), (15, 17, 2, 1), (64, 3, 2, 1)]:
+        box = ops.pick_box(dim_d)
+        tiles = [-(-d // b) for d, b in zip(dim_d, box)]
+        in_order = True
+        for mt in range(tiles[0] * tiles[1] * tiles[2] * tiles[3]):
+            m, cb = mt, []
+            for i in range(4):
+                cb.append((m % tiles[i]) * box[i])
+                m //= tiles[i]
+            rows = []
+            for r in range(128):
+                g, rr, valid = [], r, True
+                for i in range(4):
+                    g.append(cb[i] + rr % box[i])
+                    rr //= box[i]
+                    valid = valid and g[i] < dim_d[i]
+                if valid:
+                    rows.append(((g[3] * dim_d[2] + g[2]) * dim_d[1] + g[1]) * dim_d[0] + g[0])
+            in_order = in_order and rows == list(range(128 * mt, 128 * mt + 128))
+        assert in_order == ok(dim_d, box), (dim_d, box)
+
+
 def test_state_dict_keys_match_reference_naming():
     """Keys follow utils/convert_diffusers_to_original_ms_text_to_video.py:18-169 naming (and equal the oracle's, which is
     pinned to the verbatim reference model by tests/golden)."""
