@@ -427,9 +427,14 @@ __global__ void svd_out_finalize_kernel(const float* __restrict__ y, int ldc, vo
 // (EulerDiscreteScheduler.scale_model_input), then cat([mask, latent_model_input, image_latents], dim=2) with the
 // unconditional half seeing ZERO image latents (_encode_vae_image) -> channels-last [2B*F, h, w, 16] (9 used).
 // x [B, F, 4, h, w]; img_lat [B, 4, h, w] (positive half); mask [h, w]; `cfg` = 1: two halves, 0: one.
+// General form (TextStableVideoDiffusionPipeline, models/pipeline.py:596-606,654-661): the conditioning latents may differ per frame
+// and per CFG half (element strides cond_hs / cond_bs / cond_fs; 0 = broadcast), the unconditional half sees zeros only when they
+// come from `_encode_vae_image` (zero_uncond), the mask is per frame ([B, F, h, w], strides mask_bs / mask_fs) or absent (8-channel
+// UNet: cat([x, cond], dim=2)).
 template <bool BF16>
 __global__ void svd_in_assemble_kernel(const void* __restrict__ x, const void* __restrict__ img_lat, const void* __restrict__ mask,
-                                       float inv_scale, void* __restrict__ out, int B, int F, int H, int W, int cfg) {
+                                       float inv_scale, void* __restrict__ out, int B, int F, int H, int W, int cfg, long cond_hs,
+                                       long cond_bs, long cond_fs, int zero_uncond, long mask_bs, long mask_fs) {
   pdl_trigger();
   pdl_wait();
   const long per_half = static_cast<long>(B) * F * H * W;
@@ -446,18 +451,21 @@ __global__ void svd_in_assemble_kernel(const void* __restrict__ x, const void* _
   q /= H;
   const int f = q % F;
   const int b = q / F;
+  const int c_x = mask ? 1 : 0;                  // first latent channel
   float v[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = half8 * 8 + j;
     float val = 0.f;
-    if (c == 0) {
-      val = load_elem(mask, static_cast<long>(yy) * W + xx, BF16);
-    } else if (c <= 4) {
+    if (c < c_x) {
+      val = load_elem(mask, b * mask_bs + f * mask_fs + static_cast<long>(yy) * W + xx, BF16);
+    } else if (c < c_x + 4) {
       // torch: 16-bit tensor / 0-d fp32 tensor -> computed in fp32, rounded once to the 16-bit dtype
-      val = load_elem(x, (((static_cast<long>(b) * F + f) * 4 + (c - 1)) * H + yy) * W + xx, BF16) * inv_scale;
-    } else if (c <= 8) {
-      val = cond ? load_elem(img_lat, ((static_cast<long>(b) * 4 + (c - 5)) * H + yy) * W + xx, BF16) : 0.f;
+      val = load_elem(x, (((static_cast<long>(b) * F + f) * 4 + (c - c_x)) * H + yy) * W + xx, BF16) * inv_scale;
+    } else if (c < c_x + 8) {
+      if (cond || !zero_uncond)
+        val = load_elem(img_lat, (cond && cfg ? cond_hs : 0) + b * cond_bs + f * cond_fs +
+                                     (static_cast<long>(c - c_x - 4) * H + yy) * W + xx, BF16);
     }
     v[j] = val;
   }
@@ -858,8 +866,21 @@ extern "C" int aab_svd_in_assemble(const void* x, const void* img_lat, const voi
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!x || !img_lat || !mask || !out) return AAB_ERR_ARG;
   const long total = static_cast<long>(b) * f * h * w * (cfg ? 2 : 1) * 2;
-  if (is_bf16) launch_k(svd_in_assemble_kernel<true>, dim3(AAB_GRID(total, 256)), dim3(256), 0, stream, x, img_lat, mask, inv_scale, out, b, f, h, w, cfg);
-  else launch_k(svd_in_assemble_kernel<false>, dim3(AAB_GRID(total, 256)), dim3(256), 0, stream, x, img_lat, mask, inv_scale, out, b, f, h, w, cfg);
+  const long hw4 = 4L * h * w;
+  if (is_bf16) launch_k(svd_in_assemble_kernel<true>, dim3(AAB_GRID(total, 256)), dim3(256), 0, stream, x, img_lat, mask, inv_scale, out, b, f, h, w, cfg, 0L, hw4, 0L, 1, 0L, 0L);
+  else launch_k(svd_in_assemble_kernel<false>, dim3(AAB_GRID(total, 256)), dim3(256), 0, stream, x, img_lat, mask, inv_scale, out, b, f, h, w, cfg, 0L, hw4, 0L, 1, 0L, 0L);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_svd_in_assemble_frames(const void* x, const void* cond, long cond_half_stride, long cond_batch_stride,
+                                          long cond_frame_stride, int zero_uncond, const void* mask, long mask_batch_stride,
+                                          long mask_frame_stride, float inv_scale, void* out, int b, int f, int h, int w, int cfg,
+                                          int is_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !cond || !out) return AAB_ERR_ARG;
+  const long total = static_cast<long>(b) * f * h * w * (cfg ? 2 : 1) * 2;
+  if (is_bf16) launch_k(svd_in_assemble_kernel<true>, dim3(AAB_GRID(total, 256)), dim3(256), 0, stream, x, cond, mask, inv_scale, out, b, f, h, w, cfg, cond_half_stride, cond_batch_stride, cond_frame_stride, zero_uncond, mask_batch_stride, mask_frame_stride);
+  else launch_k(svd_in_assemble_kernel<false>, dim3(AAB_GRID(total, 256)), dim3(256), 0, stream, x, cond, mask, inv_scale, out, b, f, h, w, cfg, cond_half_stride, cond_batch_stride, cond_frame_stride, zero_uncond, mask_batch_stride, mask_frame_stride);
   AAB_LAUNCH_RET();
 }
 

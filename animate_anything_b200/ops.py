@@ -557,6 +557,25 @@ def svd_in_assemble(x: torch.Tensor, img_lat: torch.Tensor, mask: torch.Tensor, 
     return out
 
 
+def svd_in_assemble_frames(x: torch.Tensor, cond: torch.Tensor, mask: Optional[torch.Tensor], sigma: float, cfg: bool,
+                           zero_uncond: bool) -> torch.Tensor:
+    """General UNet input assembly of the SVD loops (TextStableVideoDiffusionPipeline): x [B, F, 4, h, w]; cond [Hc, B, F', 4, h, w]
+    with Hc in (1, 2) CFG halves and F' in (1, F) frames (1 = broadcast); mask [B, F, h, w] or None (8-channel UNet).
+    -> [(2)B*F, h, w, 16] channels-last (9 or 8 channels used)."""
+    b, f, _, h, w = x.shape
+    assert x.is_contiguous() and cond.is_contiguous() and cond.dim() == 6 and cond.shape[1] == b and cond.shape[3:] == (4, h, w)
+    hc, _, fc = cond.shape[:3]
+    assert hc in (1, 2) and fc in (1, f)
+    if mask is not None:
+        assert mask.is_contiguous() and tuple(mask.shape) == (b, f, h, w) and mask.dtype == x.dtype
+    out = torch.empty(((2 if cfg else 1) * b * f, h, w, 16), device=x.device, dtype=x.dtype)
+    _lib.call("aab_svd_in_assemble_frames", _ptr(x), _ptr(cond), cond.stride(0) if hc == 2 else 0, cond.stride(1),
+              cond.stride(2) if fc == f and f > 1 else 0, int(zero_uncond), _ptr(mask), 0 if mask is None else mask.stride(0),
+              0 if mask is None else mask.stride(1), 1.0 / math.sqrt(sigma * sigma + 1.0), _ptr(out), b, f, h, w, int(cfg),
+              _is_bf16(x), _stream())
+    return out
+
+
 def svd_cfg_euler_step(pred: torch.Tensor, cfg: bool, gs: Optional[torch.Tensor], x: torch.Tensor, sigma: float,
                        sigma_next: float) -> torch.Tensor:
     b, f, _, h, w = x.shape

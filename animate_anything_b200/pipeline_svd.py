@@ -164,3 +164,118 @@ class MaskStableVideoDiffusionPipeline:
         if not return_dict:
             return frames
         return StableVideoDiffusionPipelineOutput(frames=frames)
+
+
+class TextStableVideoDiffusionPipeline(MaskStableVideoDiffusionPipeline):
+    """B200 mirror of the reference's `TextStableVideoDiffusionPipeline.__call__` (models/pipeline.py:468-731): the SVD loop
+    conditioned on the CLIP image embedding (`condition_type="image"`), on text embeddings (`"text"`: prompt_embeds [B, 77, D]
+    replace the image embedding, :579-582) or on both (any other value: image token + text tokens concatenated, 78 keys, :583-587);
+    per-frame mask `[B, F, 1, h, w]` duplicated for the two CFG halves (:590), conditioning latents either from the image
+    (`_encode_vae_image`, zeros in the unconditional half, :598-601) or the caller's `condition_latent` [B, F, 4, h, w] used for both
+    halves (:602-604); 9-channel UNets get cat([mask, x, cond]), 8-channel ones cat([x, cond]) (:657-660).
+    The call the reference makes (app_svd.py:120-133) is condition_type="image" with `condition_latent` and a per-frame mask.  A
+    multi-token context ("text" / both) is passed to the UNet as the reference does -- and fails there exactly as it does under
+    the pinned diffusers 0.24, whose temporal transformer broadcasts the context with a literal 1 token (RuntimeError)."""
+
+    @torch.no_grad()
+    def __call__(self, image, prompt_embeds=None, negative_prompt_embeds=None, height: int = 576, width: int = 1024,
+                 num_frames: Optional[int] = None, num_inference_steps: int = 25, min_guidance_scale: float = 1.0,
+                 max_guidance_scale: float = 3.0, fps: int = 7, motion_bucket_id: int = 127, noise_aug_strength: float = 0.02,
+                 decode_chunk_size: Optional[int] = None, num_videos_per_prompt: Optional[int] = 1,
+                 generator: Optional[Union[torch.Generator, List[torch.Generator]]] = None,
+                 latents: Optional[torch.Tensor] = None, output_type: Optional[str] = "pil",
+                 callback_on_step_end: Optional[Callable[[int, int, Dict], None]] = None,
+                 callback_on_step_end_tensor_inputs: List[str] = ["latents"], return_dict: bool = True, mask=None,
+                 condition_type="image", condition_latent=None, image_embeddings: Optional[torch.Tensor] = None):
+        from . import _lib
+        launches0 = _lib.launch_count()
+        height = height or self.unet.config.sample_size * self.vae_scale_factor
+        width = width or self.unet.config.sample_size * self.vae_scale_factor
+        num_frames = num_frames if num_frames is not None else self.unet.config.num_frames
+        decode_chunk_size = decode_chunk_size if decode_chunk_size is not None else num_frames
+        self.check_inputs(image, height, width)
+        device, dtype = self.unet.device, self.unet.dtype
+        cfg = max_guidance_scale > 1.0
+        image_t = self.image_processor.preprocess(image, height=height, width=width).to(device)
+        batch_size = image_t.shape[0]
+        if batch_size * num_videos_per_prompt != 1:
+            raise NotImplementedError("one video per call on the sm_100a path")
+
+        def _text():
+            if prompt_embeds is None or (cfg and negative_prompt_embeds is None):
+                raise TypeError("condition_type != 'image' needs prompt_embeds (and negative_prompt_embeds under guidance)")
+            pe = prompt_embeds.to(device=device, dtype=dtype)
+            return torch.cat([negative_prompt_embeds.to(device=device, dtype=dtype), pe]) if cfg else pe
+
+        def _img():
+            if image_embeddings is None:
+                return self._encode_image(image_t, device, num_videos_per_prompt, cfg)
+            e = image_embeddings.to(device=device, dtype=dtype)
+            return torch.cat([torch.zeros_like(e), e]) if cfg and e.shape[0] == batch_size else e
+
+        if condition_type == "image":
+            emb = _img()
+        elif condition_type == "text":
+            emb = _text()
+        else:
+            emb = torch.cat([_img(), _text()], dim=1)
+        motion_mask = self.unet.config.in_channels == 9
+        if cfg and mask is None:
+            raise TypeError("expected Tensor as element 0 in argument 0, but got NoneType (torch.cat([mask] * 2), "
+                            "models/pipeline.py:590)")
+        fps = fps - 1
+        noise = torch.randn(image_t.shape, generator=generator, device=generator.device if generator is not None else device,
+                            dtype=image_t.dtype).to(device)
+        image_t = image_t + noise_aug_strength * noise
+        lat_h, lat_w = height // self.vae_scale_factor, width // self.vae_scale_factor
+        if condition_latent is None:
+            il = self.vae.encode(image_t.to(dtype)).latent_dist.mode().to(dtype).contiguous()          # [1, 4, h, w]
+            cond = il.reshape(1, batch_size, 1, 4, lat_h, lat_w)
+            zero_uncond = True
+        else:
+            cond = condition_latent.to(device=device, dtype=dtype).reshape(1, batch_size, num_frames, 4, lat_h, lat_w).contiguous()
+            zero_uncond = False
+        ids = torch.tensor([[fps, motion_bucket_id, noise_aug_strength]], dtype=dtype).repeat(batch_size, 1)
+        ids = (torch.cat([ids, ids]) if cfg else ids).to(device)
+        self.scheduler.set_timesteps(num_inference_steps, device=device)
+        timesteps = self.scheduler.timesteps
+        sigmas = [float(s) for s in self.scheduler.sigmas]
+        shape = (batch_size, num_frames, self.unet.config.in_channels // 2, lat_h, lat_w)
+        if latents is None:
+            latents = torch.randn(shape, generator=generator, device=generator.device if generator is not None else device,
+                                  dtype=dtype).to(device)
+        else:
+            latents = latents.to(device=device, dtype=dtype)
+        latents = (latents * float(self.scheduler.init_noise_sigma)).contiguous()
+        gs = torch.linspace(min_guidance_scale, max_guidance_scale, num_frames).unsqueeze(0).to(device, latents.dtype)
+        self._guidance_scale = _append_dims(gs.repeat(batch_size, 1), latents.ndim)
+        gs_f32 = gs[0].float().contiguous()
+        m16 = None
+        if motion_mask:
+            if mask is None:
+                raise TypeError("a 9-channel UNet needs `mask` [B, F, 1, h, w] (models/pipeline.py:657)")
+            if tuple(mask.shape) != (batch_size, num_frames, 1, lat_h, lat_w):
+                raise RuntimeError(f"Sizes of tensors must match except in dimension 2: mask {tuple(mask.shape)} vs latents "
+                                   f"{(batch_size, num_frames, 4, lat_h, lat_w)} (models/pipeline.py:657)")
+            m16 = mask.to(device=device, dtype=dtype).reshape(batch_size, num_frames, lat_h, lat_w).contiguous()
+        in_ch = self.unet.config.in_channels
+        b_unet = (2 if cfg else 1) * batch_size
+        self._num_timesteps = len(timesteps)
+        for i, t in enumerate(timesteps):
+            x16 = ops.svd_in_assemble_frames(latents, cond, m16, sigmas[i], cfg, zero_uncond)
+            pred, _ = self.unet(None, t, emb, ids, _raw=True, _x16=x16, _shape=(b_unet, num_frames, in_ch, lat_h, lat_w))
+            latents = ops.svd_cfg_euler_step(pred, cfg, gs_f32, latents, sigmas[i], sigmas[i + 1])
+            if callback_on_step_end is not None:
+                callback_kwargs = {k: locals()[k] for k in callback_on_step_end_tensor_inputs}
+                callback_outputs = callback_on_step_end(self, i, t, callback_kwargs)
+                latents = callback_outputs.pop("latents", latents)
+        if output_type != "latent":
+            frames = self.decode_latents(latents, num_frames, decode_chunk_size)
+            frames = [self.image_processor.postprocess(frames[b].permute(1, 0, 2, 3), output_type)
+                      for b in range(frames.shape[0])]
+        else:
+            frames = latents
+        self.last_gpu_launches = _lib.launch_count() - launches0
+        if not return_dict:
+            return frames
+        return StableVideoDiffusionPipelineOutput(frames=frames)

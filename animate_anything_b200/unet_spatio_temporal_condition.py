@@ -524,8 +524,16 @@ class UNetSpatioTemporalConditionModel(ModelBase):
         if any(s % (2 ** self.num_upsamplers) for s in (h, w)):
             raise ValueError("latent height/width must be multiples of 2**num_upsamplers (diffusers' SVD UNet has no "
                              "upsample_size path either)")
-        if encoder_hidden_states.shape[0] != b or encoder_hidden_states.shape[1] != 1:
+        if encoder_hidden_states.dim() != 3 or encoder_hidden_states.shape[0] != b:
             raise ValueError("encoder_hidden_states must be [batch, 1, cross_attention_dim] (one image embedding per sample)")
+        if encoder_hidden_states.shape[1] != 1:
+            # diffusers 0.24 TransformerSpatioTemporalModel.forward broadcasts the first frame's context to
+            # (h*w, batch, 1, dim) with a literal 1: a multi-token context (TextStableVideoDiffusionPipeline with
+            # condition_type != "image", models/pipeline.py:579-587) fails there with exactly this error
+            raise RuntimeError(f"The expanded size of the tensor (1) must match the existing size "
+                               f"({encoder_hidden_states.shape[1]}) at non-singleton dimension 2.  Target sizes: "
+                               f"[{h // 1 * w}, {b}, 1, {encoder_hidden_states.shape[-1]}].  Tensor sizes: "
+                               f"[1, {b}, {encoder_hidden_states.shape[1]}, {encoder_hidden_states.shape[-1]}]")
         if added_time_ids.shape != (b, cfg.projection_class_embeddings_input_dim // cfg.addition_time_embed_dim):
             raise ValueError(
                 f"Model expects an added time embedding vector of length {cfg.projection_class_embeddings_input_dim}, but a "

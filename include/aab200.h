@@ -100,6 +100,14 @@ int aab_svd_out_finalize(const float* y, int ldc, void* out, long bf, int h, int
  * per-frame guidance + Euler step (v-prediction) in one pass.  gs: fp32 [f] = linspace(min, max, f) (:405-408). */
 int aab_svd_in_assemble(const void* x, const void* img_lat, const void* mask, float inv_scale, void* out, int b, int f, int h,
                         int w, int cfg, int is_bf16, void* stream);
+/* General form for TextStableVideoDiffusionPipeline.__call__ (models/pipeline.py:596-606 conditioning latents per frame, either
+ * `_encode_vae_image` output (zero_uncond = 1) or the caller's `condition_latent` duplicated for both halves; :590 mask
+ * `torch.cat([mask] * 2)`, per frame; :654-661 cat([mask, x, cond], dim=2) or, for an 8-channel UNet (mask == NULL), cat([x, cond])).
+ * Strides in elements; 0 = broadcast. */
+int aab_svd_in_assemble_frames(const void* x, const void* cond, long cond_half_stride, long cond_batch_stride,
+                               long cond_frame_stride, int zero_uncond, const void* mask, long mask_batch_stride,
+                               long mask_frame_stride, float inv_scale, void* out, int b, int f, int h, int w, int cfg, int is_bf16,
+                               void* stream);
 int aab_svd_cfg_euler_step(const float* pred, int ldc, int cfg, const float* gs, const void* x, void* x_out, float sigma,
                            float sigma_next, int b, int f, int h, int w, int is_bf16, void* stream);
 

@@ -278,19 +278,28 @@ SVD_SCHED = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linea
 @torch.no_grad()
 def oracle_svd_sampling_loop(unet, scheduler, vae, image_embeddings, image_latents, mask, latents, num_inference_steps=25,
                              min_guidance_scale=1.0, max_guidance_scale=3.0, fps=6, motion_bucket_id=127,
-                             noise_aug_strength=0.02, decode_chunk_size=None, decode=True):
+                             noise_aug_strength=0.02, decode_chunk_size=None, decode=True, frame_mask=None,
+                             condition_latent=None):
     """Restates the loop of MaskStableVideoDiffusionPipeline.__call__ (models/pipeline.py:375-459) from the point where the
     image has been encoded: `image_embeddings` [B, 1, D] (CLIP image embedding, positive half), `image_latents` [B, 4, h, w]
     (`vae.encode(image + noise).latent_dist.mode()`, NOT scaled), `mask` [1, h, w], `latents` [B, F, 4, h, w] unit
     noise.  Classifier-free guidance with zeroed negative conditioning (:343,_encode_vae_image), per-frame guidance
     scale linspace(min, max, F) (:405-408), 9-channel input cat([mask, latents, image_latents], dim=2) (:422), Euler
-    step (:439), chunked temporal-VAE decode (:456).  Returns (frames [B, 3, F, H, W] fp32 or None, latents)."""
+    step (:439), chunked temporal-VAE decode (:456).  Returns (frames [B, 3, F, H, W] fp32 or None, latents).
+    TextStableVideoDiffusionPipeline.__call__ with condition_type="image" (models/pipeline.py:468-731, the call of
+    app_svd.py:120-133) is the same loop with `frame_mask` [B, F, 1, h, w] used as given for both halves (:590) instead of `mask`,
+    and, when `condition_latent` [B, F, 4, h, w] is passed, that tensor for BOTH halves (:602-604) instead of the image latents."""
     b, nf = latents.shape[:2]
     cfg = max_guidance_scale > 1.0
     emb = torch.cat([torch.zeros_like(image_embeddings), image_embeddings]) if cfg else image_embeddings
     il = torch.cat([torch.zeros_like(image_latents), image_latents]) if cfg else image_latents
     il = il.unsqueeze(1).repeat(1, nf, 1, 1, 1)
-    m = mask[None, None].repeat(2, nf, 1, 1, 1).reshape(2, nf, 1, *mask.shape[-2:])      # '1 h w -> 2 f 1 h w'
+    if condition_latent is not None:
+        il = torch.cat([condition_latent] * 2) if cfg else condition_latent
+    if frame_mask is not None:
+        m = torch.cat([frame_mask] * 2) if cfg else frame_mask
+    else:
+        m = mask[None, None].repeat(2, nf, 1, 1, 1).reshape(2, nf, 1, *mask.shape[-2:])      # '1 h w -> 2 f 1 h w'
     ids = torch.tensor([[fps, motion_bucket_id, noise_aug_strength]], dtype=emb.dtype).repeat(b, 1)
     ids = (torch.cat([ids, ids]) if cfg else ids).to(latents.device)
     scheduler.set_timesteps(num_inference_steps, device=latents.device)

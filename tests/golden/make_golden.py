@@ -285,9 +285,51 @@ def svd_goldens():
     print("svd_pipeline_tiny_ref.pt", tuple(frames[0].shape), tuple(lat.shape), float(lat.abs().mean()))
 
 
+def svd_text_goldens():
+    """The VERBATIM `TextStableVideoDiffusionPipeline.__call__` (models/pipeline.py:468-731) on the tiny SVD models, called the way
+    app_svd.py:120-133 calls it (condition_type="image", caller-supplied per-frame `condition_latent`, per-frame mask), plus the
+    branch that encodes the image itself; and the error the pinned diffusers 0.24 raises for a multi-token (text) context."""
+    import diffusers
+    from models.pipeline import TextStableVideoDiffusionPipeline                 # verbatim reference
+    from oracle.composition import SVD_SCHED
+    unet = fill_deterministic(diffusers.UNetSpatioTemporalConditionModel(**SVD_TINY).eval(), 0)
+    vae = fill_deterministic(diffusers.AutoencoderKLTemporalDecoder(**SVD_TINY_VAE).eval(), 1)
+    enc = fill_deterministic(SvdImageEncoderStub().eval(), 2)
+    sched = diffusers.EulerDiscreteScheduler(**SVD_SCHED)
+    pipe = TextStableVideoDiffusionPipeline(vae=vae, image_encoder=enc, unet=unet, scheduler=sched)
+    g = torch.Generator().manual_seed(3)
+    img = torch.randn(1, 3, 64, 128, generator=g).clamp(-1, 1)
+    mask = (torch.rand(1, 5, 1, 8, 16, generator=g) > 0.5).float()
+    mask[:, 0] = 0                                                               # app_svd.py:111
+    lat0 = torch.randn(1, 5, 4, 8, 16, generator=g)
+    pe = torch.randn(1, 7, 64, generator=g)
+    ne = torch.randn(1, 7, 64, generator=g)
+    cl = torch.randn(1, 5, 4, 8, 16, generator=g)
+    kw = dict(height=64, width=128, num_frames=5, num_inference_steps=3, decode_chunk_size=3, noise_aug_strength=0.0,
+              latents=lat0, mask=mask, return_dict=False, output_type="latent")
+    out = {"unet_config": SVD_TINY, "vae_config": SVD_TINY_VAE, "image": img, "mask": mask, "latents_in": lat0,
+           "prompt_embeds": pe, "negative_prompt_embeds": ne, "condition_latent": cl}
+    out["latents_image_condlat"] = pipe(img, condition_type="image", condition_latent=cl, **kw)
+    out["latents_image"] = pipe(img, condition_type="image", **kw)
+    kwf = dict(kw, output_type="pt")
+    out["frames_image_condlat"] = torch.stack(pipe(img, condition_type="image", condition_latent=cl, **kwf))
+    try:
+        pipe(img, condition_type="text", prompt_embeds=pe, negative_prompt_embeds=ne, **kw)
+        out["text_error"] = None
+    except RuntimeError as e:
+        out["text_error"] = str(e)
+    torch.save(out, os.path.join(HERE, "svd_text_pipeline_tiny_ref.pt"))
+    for k in ("latents_image_condlat", "latents_image", "frames_image_condlat"):
+        print("svd_text_pipeline_tiny_ref.pt", k, tuple(out[k].shape), float(out[k].abs().mean()))
+    print("text context ->", out["text_error"])
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "svd":
         svd_goldens()
+    elif len(sys.argv) > 1 and sys.argv[1] == "svd_text":
+        import diffusers  # noqa: F401  (the shim)
+        svd_text_goldens()
     elif len(sys.argv) > 1 and sys.argv[1] == "oddsize":
         import diffusers  # noqa: F401  (the shim)
         oddsize_unet_golden()

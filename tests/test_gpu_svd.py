@@ -177,3 +177,87 @@ def test_svd_pipeline_loop_matches_oracle():
     stock = (sf[0].permute(1, 0, 2, 3) / 2 + 0.5).clamp(0, 1)
     assert_vs_stock(record_parity(case, "frames", got, want, stock), mean_factor=3.0, max_factor=4.0, mean_floor=2e-3,
                     max_floor=2e-2)
+
+
+def test_svd_text_pipeline_image_branch():
+    """`TextStableVideoDiffusionPipeline.__call__` mirror, called as app_svd.py:120-133 calls the reference's (condition_type="image",
+    caller-supplied per-frame `condition_latent`, per-frame mask with frame 0 cleared), and with the image's own latents: against
+    the oracle loop (pinned to the verbatim reference class by tests/golden/svd_text_pipeline_tiny_ref.pt on CPU).  A multi-token
+    context fails in the UNet exactly as it does under the pinned diffusers 0.24."""
+    from oracle.composition import EulerDiscreteScheduler as OEuler, SVD_SCHED, oracle_svd_sampling_loop
+    from animate_anything_b200.pipeline_svd import TextStableVideoDiffusionPipeline
+    from animate_anything_b200.schedulers import EulerDiscreteScheduler
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dtype = torch.float16
+    ounet, unet = _pair(dtype)
+    ovae, vae = _vae_pair(dtype)
+    g = torch.Generator().manual_seed(8)
+    img = torch.randn(1, 3, 128, 192, generator=g).clamp(-1, 1)
+    mask = (torch.rand(1, 6, 1, 16, 24, generator=g) > 0.5).float()
+    mask[:, 0] = 0
+    lat0 = torch.randn(1, 6, 4, 16, 24, generator=g)
+    cl = torch.randn(1, 6, 4, 16, 24, generator=g)
+    emb = torch.randn(1, 1, 96, generator=g)
+    pipe = TextStableVideoDiffusionPipeline(vae=vae, image_encoder=None, unet=unet, scheduler=EulerDiscreteScheduler(**SVD_SCHED))
+    kw = dict(height=128, width=192, num_frames=6, num_inference_steps=3, decode_chunk_size=3, noise_aug_strength=0.0,
+              latents=lat0, mask=mask, image_embeddings=emb, return_dict=False, output_type="latent")
+    lat_c = pipe(img, condition_type="image", condition_latent=cl, **kw)
+    lat_i = pipe(img, condition_type="image", **kw)
+    torch.cuda.synchronize()
+    assert pipe.last_gpu_launches > 500
+    okw = dict(num_inference_steps=3, noise_aug_strength=0.0, decode=False)
+    with torch.no_grad():
+        il32 = ovae.encode(img.to(dtype).float().cuda()).latent_dist.mode()
+        m32, l32, c32 = mask.cuda(), lat0.to(dtype).float().cuda(), cl.to(dtype).float().cuda()
+        e32 = emb.to(dtype).float().cuda()
+        _, r_c = oracle_svd_sampling_loop(ounet, OEuler(**SVD_SCHED), ovae, e32, il32, None, l32, frame_mask=m32,
+                                          condition_latent=c32, **okw)
+        _, r_i = oracle_svd_sampling_loop(ounet, OEuler(**SVD_SCHED), ovae, e32, il32, None, l32, frame_mask=m32, **okw)
+        o16u, o16v = ounet.to(dtype), ovae.to(dtype)
+        il16 = o16v.encode(img.to(dtype).cuda()).latent_dist.mode()
+        _, s_c = oracle_svd_sampling_loop(o16u, OEuler(**SVD_SCHED), o16v, emb.to(dtype).cuda(), il16, None, lat0.to(dtype).cuda(),
+                                          frame_mask=mask.to(dtype).cuda(), condition_latent=cl.to(dtype).cuda(), **okw)
+        _, s_i = oracle_svd_sampling_loop(o16u, OEuler(**SVD_SCHED), o16v, emb.to(dtype).cuda(), il16, None, lat0.to(dtype).cuda(),
+                                          frame_mask=mask.to(dtype).cuda(), **okw)
+    case = "SVD Text pipeline (image branch) fp16 3 Euler steps"
+    assert_vs_stock(record_parity(case, "latents, condition_latent", lat_c, r_c, s_c), mean_factor=3.0, max_factor=4.0,
+                    mean_floor=5e-4, max_floor=5e-3)
+    assert_vs_stock(record_parity(case, "latents, image latents", lat_i, r_i, s_i), mean_factor=3.0, max_factor=4.0,
+                    mean_floor=5e-4, max_floor=5e-3)
+    # the two branches really differ (condition_latent feeds both CFG halves, the image latents only the conditional one)
+    assert (lat_c.float() - lat_i.float()).abs().mean().item() > 1e-2
+    with pytest.raises(RuntimeError, match="expanded size of the tensor"):
+        pipe(img, condition_type="text", prompt_embeds=torch.randn(1, 7, 96), negative_prompt_embeds=torch.randn(1, 7, 96),
+             **{k: v for k, v in kw.items() if k != "image_embeddings"})
+    with pytest.raises(TypeError):
+        pipe(img, condition_type="image", **{**kw, "mask": None})
+
+
+def test_svd_in_assemble_frames_kernel():
+    """`aab_svd_in_assemble_frames` against the torch statement of models/pipeline.py:590,596-606,654-661 (per-frame mask and
+    conditioning latents, zero or duplicated unconditional half, 9- and 8-channel inputs)."""
+    from animate_anything_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    for dtype in (torch.float16, torch.bfloat16):
+        x = torch.randn(1, 5, 4, 8, 12, generator=g).to(dtype).cuda()
+        cond_f = torch.randn(1, 1, 5, 4, 8, 12, generator=g).to(dtype).cuda()
+        cond_1 = torch.randn(1, 1, 1, 4, 8, 12, generator=g).to(dtype).cuda()
+        mask = (torch.rand(1, 5, 8, 12, generator=g) > 0.5).to(dtype).cuda()
+        sigma = 3.7
+        xs = (x.float() * torch.tensor(1.0 / (sigma * sigma + 1.0) ** 0.5, dtype=torch.float32)).to(dtype)   # the kernel's form
+        for cond, zero_uncond, m in ((cond_f, False, mask), (cond_1, True, mask), (cond_f, False, None), (cond_1, True, None)):
+            for cfg in (True, False):
+                out = ops.svd_in_assemble_frames(x, cond, m, sigma, cfg, zero_uncond)
+                c5 = cond[0].expand(1, 5, 4, 8, 12)
+                if cfg:
+                    cc = torch.cat([torch.zeros_like(c5) if zero_uncond else c5, c5])
+                    xx = torch.cat([xs, xs])
+                    mm = None if m is None else torch.cat([m, m])[:, :, None]
+                else:
+                    cc, xx, mm = c5, xs, None if m is None else m[:, :, None]
+                want = torch.cat(([mm] if mm is not None else []) + [xx, cc], dim=2)           # [B', F, 9|8, h, w]
+                nch = want.shape[2]
+                got = out.view(want.shape[0], 5, 8, 12, 16).permute(0, 1, 4, 2, 3)
+                assert torch.equal(got[:, :, :nch], want), (dtype, zero_uncond, m is None, cfg)
+                assert not got[:, :, nch:].any()

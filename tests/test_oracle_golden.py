@@ -175,3 +175,31 @@ def test_svd_loop_matches_reference_pipeline():
     want = gold["frames"][0]
     got = (frames[0].permute(1, 0, 2, 3) / 2 + 0.5).clamp(0, 1)
     assert torch.allclose(got, want, rtol=1e-5, atol=1e-5), float((got - want).abs().max())
+
+
+def test_svd_text_pipeline_image_branch_matches_reference():
+    """`TextStableVideoDiffusionPipeline.__call__` (models/pipeline.py:468-731) as app_svd.py:120-133 calls it: the oracle loop with
+    a per-frame mask and the caller's `condition_latent`, and with the image's own latents; plus the diffusers-0.24 failure for
+    a multi-token context, which the product mirrors."""
+    from make_golden import SvdImageEncoderStub
+    from oracle.composition import (AutoencoderKLTemporalDecoder, EulerDiscreteScheduler, SVD_SCHED,
+                                    UNetSpatioTemporalConditionModel, oracle_svd_sampling_loop)
+    gold = torch.load(os.path.join(HERE, "golden", "svd_text_pipeline_tiny_ref.pt"))
+    unet = fill_deterministic(UNetSpatioTemporalConditionModel(**gold["unet_config"]).eval(), 0)
+    vae = fill_deterministic(AutoencoderKLTemporalDecoder(**gold["vae_config"]).eval(), 1)
+    enc = fill_deterministic(SvdImageEncoderStub().eval(), 2)
+    with torch.no_grad():
+        emb = enc(gold["image"]).unsqueeze(1)
+        il = vae.encode(gold["image"]).latent_dist.mode()
+    kw = dict(num_inference_steps=3, noise_aug_strength=0.0, decode_chunk_size=3, frame_mask=gold["mask"])
+    frames, lat = oracle_svd_sampling_loop(unet, EulerDiscreteScheduler(**SVD_SCHED), vae, emb, il, None, gold["latents_in"],
+                                           condition_latent=gold["condition_latent"], **kw)
+    assert torch.allclose(lat, gold["latents_image_condlat"], rtol=1e-5, atol=1e-5)
+    got = (frames[0].permute(1, 0, 2, 3) / 2 + 0.5).clamp(0, 1)
+    assert torch.allclose(got, gold["frames_image_condlat"][0], rtol=1e-5, atol=1e-5)
+    _, lat2 = oracle_svd_sampling_loop(unet, EulerDiscreteScheduler(**SVD_SCHED), vae, emb, il, None, gold["latents_in"],
+                                       decode=False, **kw)
+    assert torch.allclose(lat2, gold["latents_image"], rtol=1e-5, atol=1e-5)
+    assert gold["text_error"] is not None and "expanded size of the tensor (1) must match the existing size (7)" in gold["text_error"]
+    with pytest.raises(RuntimeError, match="expanded size"):
+        unet(torch.zeros(2, 5, 9, 8, 16), 1.0, torch.zeros(2, 7, 64), torch.zeros(2, 3))
