@@ -98,6 +98,10 @@ _SIGS = {
     "aab_add_noise": [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_long,
                       C.c_int, C.c_void_p],
     "aab_cast_f32": [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p],
+    "aab_video_f32_to_nhwc8": [C.c_void_p, C.c_long, C.c_long, C.c_long, C.c_long, C.c_long, C.c_void_p, C.c_int, C.c_int,
+                               C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
+    "aab_rgba_finalize_u8": [C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_int, C.c_void_p],
+    "aab_pad_cols": [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p],
 }
 
 EXPORTS = tuple(_SIGS.keys())

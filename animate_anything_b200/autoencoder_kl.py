@@ -250,6 +250,9 @@ class AutoencoderKL(ModelBase):
         c0 = self.decoder.conv_out.in_channels
         h = ops.groupnorm(h, g.n, g.hw, own["dec_norm"][0], own["dec_norm"][1], 1e-6, True, 32)
         y = ops.conv3x3(h.view(g.n, g.h, g.w, c0), own["dec_out"][0], own["dec_out"][1], out_f32=True)   # [rows, 3]
+        if as_uint8 == "both":         # MaskedLatentToVideoPipeline needs the fp32 video (alpha decoder input) AND the frames
+            return (ops.vae_dec_finalize(y, b, f, g.h, g.w, prep.dtype == torch.bfloat16),
+                    ops.vae_dec_finalize_u8(y, b, f, g.h, g.w, prep.dtype == torch.bfloat16))
         if as_uint8:
             return ops.vae_dec_finalize_u8(y, b, f, g.h, g.w, prep.dtype == torch.bfloat16)
         return ops.vae_dec_finalize(y, b, f, g.h, g.w, prep.dtype == torch.bfloat16)
@@ -314,3 +317,18 @@ class AutoencoderKL(ModelBase):
         outs = [self._decode_chunk(prep, latents[:, :, i: i + self.frame_chunk].contiguous(), inv_scale, as_uint8=True)
                 for i in range(0, f, self.frame_chunk)]
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+    @torch.no_grad()
+    def decode_video_and_frames_uint8(self, latents: torch.Tensor, inv_scale: Optional[float] = None):
+        """One decoder pass, both tails: (fp32 video [b, 3, f, H, W], uint8 tensor2vid frames [f, H, b*W, 3]) — what
+        models/pipeline_stage2.py:299 (`decode_latents`) and :330 (`tensor2vid`) produce from the same latents."""
+        prep = self._prepared()
+        if inv_scale is None:
+            inv_scale = 1.0 / self.config.scaling_factor
+        latents = latents.to(prep.dtype).contiguous()
+        f = latents.shape[2]
+        outs = [self._decode_chunk(prep, latents[:, :, i: i + self.frame_chunk].contiguous(), inv_scale, as_uint8="both")
+                for i in range(0, f, self.frame_chunk)]
+        if len(outs) == 1:
+            return outs[0]
+        return torch.cat([o[0] for o in outs], dim=2), torch.cat([o[1] for o in outs], dim=0)

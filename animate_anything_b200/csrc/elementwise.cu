@@ -661,6 +661,71 @@ __global__ void cast_f32_kernel(const float* __restrict__ x, void* __restrict__ 
   if (i < n) store_elem(y, i, x[i], BF16);
 }
 
+// ------------------------------------------------------------------------------------------------ transparent-video branch
+// decode_latents output (fp32 video [B, 3, F, H, W], any strides) -> channels-last 16-bit [B*F, H, W, 8] zero padded: the
+// `video_tensor.permute(0, 2, 1, 3, 4).reshape(b*f, c, h, w).to(dtype)` of models/pipeline_stage2.py:305 fused with the
+// layout change the alpha decoder's conv_in wants.
+template <bool BF16>
+__global__ void video_f32_to_nhwc8_kernel(const float* __restrict__ v, long sb, long sc, long sf, long sy, long sx,
+                                          void* __restrict__ out, int B, int C, int F, int H, int W) {
+  pdl_trigger();
+  pdl_wait();
+  const long total = static_cast<long>(B) * F * H * W;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = i % W;
+  long r = i / W;
+  const int y = r % H;
+  r /= H;
+  const int f = r % F;
+  const long b = r / F;
+  const float* src = v + b * sb + f * sf + y * sy + x * sx;
+  float e[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) e[j] = (j < C) ? src[j * sc] : 0.f;
+  reinterpret_cast<uint4*>(out)[i] =
+      make_uint4(pack2(e[0], e[1], BF16), pack2(e[2], e[3], BF16), pack2(e[4], e[5], BF16), pack2(e[6], e[7], BF16));
+}
+
+// RGBA post-processing of MaskedLatentToVideoPipeline.__call__ (models/pipeline_stage2.py:311-324) on the alpha decoder's
+// conv_out result y [pixels, ldc] (fp32 accumulators, 4 valid channels: r, g, b, alpha) -> uint8 [pixels, 4]:
+//   v     = round16(y)                       (the decoder output in the model dtype)
+//   alpha = round16(v3 * 255);  alpha > 127 -> 255, else 0
+//   fg    = round16(round16(v + 1) * 127.5)  -> float -> clip(0, 255) -> truncate   (numpy astype(uint8))
+template <bool BF16>
+__global__ void rgba_finalize_u8_kernel(const float* __restrict__ y, int ldc, uint8_t* __restrict__ out, long pixels) {
+  pdl_trigger();
+  pdl_wait();
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= pixels) return;
+  const float* src = y + i * ldc;
+  uint32_t px = 0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = round16(src[c], BF16);
+    v = round16(__fadd_rn(v, 1.0f), BF16);
+    v = round16(__fmul_rn(v, 127.5f), BF16);
+    v = fminf(fmaxf(v, 0.0f), 255.0f);
+    px |= static_cast<uint32_t>(static_cast<uint8_t>(v)) << (8 * c);
+  }
+  const float a = round16(__fmul_rn(round16(src[3], BF16), 255.0f), BF16);
+  if (a > 127.0f) px |= 0xFF000000u;
+  reinterpret_cast<uint32_t*>(out)[i] = px;
+}
+
+// dst [rows, ldd] = src [rows, cols] with columns cols..dcols-1 zero: widens a 32-channel activation to the 64-channel K
+// block of the stride-2 implicit GEMM (UNet384 level-0 Downsample2D, LatentTransparencyOffsetEncoder 32 -> 64 conv).
+__global__ void pad_cols_kernel(const uint4* __restrict__ src, long lds8, uint4* __restrict__ dst, long rows, int cols8, int dcols8) {
+  pdl_trigger();
+  pdl_wait();
+  const long total = rows * dcols8;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % dcols8);
+  const long r = i / dcols8;
+  dst[i] = c < cols8 ? src[r * lds8 + c] : make_uint4(0, 0, 0, 0);
+}
+
 }  // namespace aab
 
 using namespace aab;
@@ -950,5 +1015,32 @@ extern "C" int aab_cast_f32(const float* x, void* y, long n, int is_bf16, void* 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (is_bf16) launch_k(cast_f32_kernel<true>, dim3(AAB_GRID(n, 256)), dim3(256), 0, stream, x, y, n);
   else launch_k(cast_f32_kernel<false>, dim3(AAB_GRID(n, 256)), dim3(256), 0, stream, x, y, n);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_video_f32_to_nhwc8(const float* video, long sb, long sc, long sf, long sy, long sx, void* out, int b, int c,
+                                      int f, int h, int w, int is_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!video || !out || c < 1 || c > 8 || b < 1 || f < 1 || h < 1 || w < 1) return AAB_ERR_ARG;
+  const long total = static_cast<long>(b) * f * h * w;
+  if (is_bf16) launch_k(video_f32_to_nhwc8_kernel<true>, dim3(AAB_GRID(total, 256)), dim3(256), 0, stream, video, sb, sc, sf, sy, sx, out, b, c, f, h, w);
+  else launch_k(video_f32_to_nhwc8_kernel<false>, dim3(AAB_GRID(total, 256)), dim3(256), 0, stream, video, sb, sc, sf, sy, sx, out, b, c, f, h, w);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_rgba_finalize_u8(const float* y, int ldc, void* out, long pixels, int is_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!y || !out || ldc < 4 || pixels < 1) return AAB_ERR_ARG;
+  if (is_bf16) launch_k(rgba_finalize_u8_kernel<true>, dim3(AAB_GRID(pixels, 256)), dim3(256), 0, stream, y, ldc, reinterpret_cast<uint8_t*>(out), pixels);
+  else launch_k(rgba_finalize_u8_kernel<false>, dim3(AAB_GRID(pixels, 256)), dim3(256), 0, stream, y, ldc, reinterpret_cast<uint8_t*>(out), pixels);
+  AAB_LAUNCH_RET();
+}
+
+extern "C" int aab_pad_cols(const void* src, long lds, void* dst, long rows, int cols, int dst_cols, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!src || !dst || rows < 1 || (cols % 8) || (dst_cols % 8) || (lds % 8) || cols > dst_cols || cols < 8) return AAB_ERR_ARG;
+  const long total = rows * (dst_cols / 8);
+  launch_k(pad_cols_kernel, dim3(AAB_GRID(total, 256)), dim3(256), 0, stream, reinterpret_cast<const uint4*>(src), lds / 8,
+           reinterpret_cast<uint4*>(dst), rows, cols / 8, dst_cols / 8);
   AAB_LAUNCH_RET();
 }

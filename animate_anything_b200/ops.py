@@ -310,9 +310,12 @@ def tconv3(x: torch.Tensor, b: int, t: int, hw: int, w: torch.Tensor, bias=None,
 
 # ---------------------------------------------------------------------------------------------- attention
 def flash_attn_d64(q: torch.Tensor, q_col0: int, kv: torch.Tensor, k_col0: int, v_col0: int, nb: int, lq: int, lk: int,
-                   heads: int, kv_batch_div: int = 1, out: Optional[torch.Tensor] = None, causal: bool = False) -> torch.Tensor:
+                   heads: int, kv_batch_div: int = 1, out: Optional[torch.Tensor] = None, causal: bool = False,
+                   scale: Optional[float] = None) -> torch.Tensor:
     """q: [nb*lq, q_cols]; kv: [nb_kv*lk, kv_cols]; head h uses columns col0 + 64*h.  Returns [nb*lq, heads*64].
-    `causal` (lq == lk <= 128): key j is visible to query i iff j <= i (CLIP text tower)."""
+    `causal` (lq == lk <= 128): key j is visible to query i iff j <= i (CLIP text tower).
+    `scale`: softmax scale, default 1/sqrt(64); heads narrower than 64 are run zero-padded to 64 columns with their own
+    1/sqrt(head_dim) (UNet384's head dim 8: zero columns add exact zeros to Q.K^T and produce zero output columns)."""
     bf = _is_bf16(q) | (2 if causal else 0)
     if out is None:
         out = torch.empty((nb * lq, heads * 64), device=q.device, dtype=q.dtype)
@@ -321,7 +324,8 @@ def flash_attn_d64(q: torch.Tensor, q_col0: int, kv: torch.Tensor, k_col0: int, 
               lambda: _lib.call("aab_flash_attn_d64", _ptr(q), q.stride(0), lq * q.stride(0), q.shape[1], q_col0,
                                 _ptr(kv), kv.stride(0), lk * kv.stride(0), kv.shape[1], k_col0, v_col0,
                                 _ptr(out), out.stride(0), lq * out.stride(0), 0, nb, nb_kv, kv_batch_div, heads, lq, lk,
-                                1.0 / math.sqrt(64.0), bf, _stream()), shape=(nb, heads, lq, lk))
+                                1.0 / math.sqrt(64.0) if scale is None else float(scale), bf, _stream()),
+              shape=(nb, heads, lq, lk))
     return out
 
 
@@ -622,4 +626,43 @@ def vae_dec_finalize_u8(y: torch.Tensor, b, f, h, w, bf16: bool) -> torch.Tensor
     """conv_out result -> uint8 frames [f, h, b*w, 3] (diffusers tensor2vid layout and rounding)."""
     out = torch.empty((f, h, b * w, 3), device=y.device, dtype=torch.uint8)
     _lib.call("aab_vae_dec_finalize_u8", _ptr(y), y.stride(0), _ptr(out), b, f, h, w, int(bf16), _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- transparent-video branch
+def video_f32_to_nhwc8(video: torch.Tensor, dtype) -> torch.Tensor:
+    """fp32 video [b, c<=8, f, H, W] (any strides) -> channels-last 16-bit [b*f, H, W, 8], zero padded
+    (models/pipeline_stage2.py:305)."""
+    assert video.dtype == torch.float32 and video.dim() == 5
+    b, c, f, h, w = video.shape
+    out = torch.empty((b * f, h, w, 8), device=video.device, dtype=dtype)
+    sb, sc, sf, sy, sx = video.stride()
+    _lib.call("aab_video_f32_to_nhwc8", _ptr(video), sb, sc, sf, sy, sx, _ptr(out), b, c, f, h, w,
+              1 if dtype == torch.bfloat16 else 0, _stream())
+    return out
+
+
+def rgba_finalize_u8(y: torch.Tensor, pixels: int, bf16: bool) -> torch.Tensor:
+    """alpha decoder conv_out result [>= pixels, >= 4] fp32 -> uint8 [pixels, 4] (models/pipeline_stage2.py:311-324)."""
+    assert y.dtype == torch.float32 and y.shape[0] >= pixels and y.shape[1] >= 4
+    out = torch.empty((pixels, 4), device=y.device, dtype=torch.uint8)
+    _lib.call("aab_rgba_finalize_u8", _ptr(y), y.stride(0), _ptr(out), pixels, int(bf16), _stream())
+    return out
+
+
+def pad_cols(x: torch.Tensor, dst_cols: int) -> torch.Tensor:
+    """[rows, C] -> [rows, dst_cols] with zero columns appended."""
+    out = torch.empty((x.shape[0], dst_cols), device=x.device, dtype=x.dtype)
+    _lib.call("aab_pad_cols", _ptr(x), x.stride(0), _ptr(out), x.shape[0], x.shape[1], dst_cols, _stream())
+    return out
+
+
+def cat_cols(x: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+    """Materialised channel concat [rows, C1 + C2] (two strided copies): used where the virtual concat of the implicit GEMM
+    cannot be (C1 not a multiple of the 64-channel K block)."""
+    c1, c2 = x.shape[1], x2.shape[1]
+    out = torch.empty((x.shape[0], c1 + c2), device=x.device, dtype=x.dtype)
+    _lib.call("aab_copy2d", _ptr(x), x.stride(0), _ptr(out), out.stride(0), x.shape[0], c1, _stream())
+    _lib.call("aab_copy2d", _ptr(x2), x2.stride(0), C.c_void_p(out.data_ptr() + 2 * c1), out.stride(0), x2.shape[0], c2,
+              _stream())
     return out

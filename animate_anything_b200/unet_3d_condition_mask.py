@@ -198,7 +198,7 @@ class UNet3DConditionModel(ModelBase):
             raise ValueError(f"`{name}` has {count} values for a batch of {b}: expected 1 or {b}"
                              + (f" (or {n_shared}, one per prompt)" if n_shared else ""))
 
-    def _time_embedding(self, prep, timestep, motion, b, device, n_shared=0):
+    def _time_embedding(self, prep, timestep, motion, b, device, n_shared=0, timestep_cond=None):
         """reference :391-420.  Returns fp32 [B, sum(Cout)] = time_emb_proj_r(silu(emb)) for every resnet r."""
         own = prep.get(self)
         te = prep.get(self.time_embedding)
@@ -217,6 +217,13 @@ class UNet3DConditionModel(ModelBase):
             self._check_per_batch("motion", motion.numel(), b, n_shared)
             m_emb = ops.timestep_embed(motion, b, c0, dt)
             t_emb = ops.linear(m_emb, te["cp"], None, residual=t_emb)         # sample + cond_proj(condition)
+        elif timestep_cond is not None:
+            # :418-419 `self.time_embedding(t_emb, timestep_cond)` when no motion value is in play: [1 | B, C0] broadcast over B
+            tc = timestep_cond.to(device=device, dtype=dt).reshape(-1, c0)
+            self._check_per_batch("timestep_cond", tc.shape[0], b, n_shared)
+            if tc.shape[0] != b:
+                tc = tc.repeat(b // tc.shape[0], 1)
+            t_emb = ops.linear(tc.contiguous(), te["cp"], None, residual=t_emb)
         h = ops.linear(t_emb, te["l1"][0], te["l1"][1], act=ops.ACT_SILU)
         semb = ops.linear(h, te["l2"][0], te["l2"][1], act=ops.ACT_SILU)      # silu(emb): what every resnet consumes
         return ops.linear(semb, own["temb_w"], own["temb_b"], out_f32=True)
@@ -246,10 +253,13 @@ class UNet3DConditionModel(ModelBase):
         (unconditional first).  Both guidance halves see identical latents / condition / timestep, so every layer before
         the first text cross-attention is evaluated once and duplicated there; the result equals the reference's
         `torch.cat([latents] * 2)` evaluation (models/pipeline.py:165) up to the summation order inside GroupNorm."""
-        if (class_labels is not None or timestep_cond is not None or attention_mask is not None or
-                down_block_additional_residuals is not None or mid_block_additional_residual is not None):
-            raise NotImplementedError("class_labels / timestep_cond / attention_mask / ControlNet residuals are not "
-                                      "used by the reference's eval path and are not implemented")
+        # `attention_mask` and `class_labels` are accepted and IGNORED, exactly like the reference: its forward turns the
+        # mask into a -10000 bias (:385-388) and hands it to blocks whose forward never reads the argument
+        # (models/unet_3d_blocks.py:340,489,720), and `class_labels` is never read at all (there is no class embedding).
+        # `timestep_cond` feeds `time_embedding.cond_proj` when no motion value is used (:414-419).
+        if down_block_additional_residuals is not None or mid_block_additional_residual is not None:
+            raise NotImplementedError("ControlNet residuals (:456-479) are not used by any caller in the reference tree and "
+                                      "are not implemented")
         prep = self._prepared()
         own = prep.get(self)
         dt = prep.dtype
@@ -270,7 +280,7 @@ class UNet3DConditionModel(ModelBase):
         ctx.fuse_geglu = self.fuse_geglu
         ctx.temb_off = own["temb_off"]
         ctx.dup_pending = bool(_cfg_shared_prefix)
-        ctx.temb_all = self._time_embedding(prep, timestep, motion, b_full, dev, b if _cfg_shared_prefix else 0)
+        ctx.temb_all = self._time_embedding(prep, timestep, motion, b_full, dev, b if _cfg_shared_prefix else 0, timestep_cond)
         ehs = encoder_hidden_states
         if ehs.dtype != dt:
             ehs = ehs.to(dt)

@@ -145,6 +145,20 @@ int aab_vae_dec_finalize_u8(const float* y, int ldc, void* out, int b, int f, in
 int aab_add_noise(const void* x0, const void* noise, float sa, float sb, void* out, long bc, int f, int fx, long hw,
                   int is_bf16, void* stream);
 
+/* Transparent-video branch: models/pipeline_stage2.py:171-337 MaskedLatentToVideoPipeline.__call__ +
+ * models/layerdiffuse_VAE.py:44-177 UNet384 (the alpha decoder; its convolutions / GroupNorm(4) / head-dim-8 attention run on
+ * aab_igemm / aab_groupnorm / aab_flash_attn_d64 with zero-padded heads).
+ * :305 `video_tensor.permute(0,2,1,3,4).reshape(b*f,c,h,w).to(dtype)`: fp32 video [b, c<=8, f, h, w] (strides in elements)
+ *      -> channels-last 16-bit [b*f, h, w, 8], zero padded;
+ * :311-324 RGBA post-processing of the decoder's conv_out result y [pixels, ldc] (fp32, channels r g b alpha) -> uint8
+ *      [pixels, 4]: alpha*255 thresholded at 127 to {0,255}, (fg+1)*127.5 with torch's 16-bit roundings, clip, truncate;
+ * pad_cols: dst [rows, dst_cols] = src [rows, cols] | zeros (32-channel activations in front of a stride-2 conv, whose
+ *      space-to-depth K block is 64 channels wide). */
+int aab_video_f32_to_nhwc8(const float* video, long sb, long sc, long sf, long sy, long sx, void* out, int b, int c, int f,
+                           int h, int w, int is_bf16, void* stream);
+int aab_rgba_finalize_u8(const float* y, int ldc, void* out, long pixels, int is_bf16, void* stream);
+int aab_pad_cols(const void* src, long lds, void* dst, long rows, int cols, int dst_cols, void* stream);
+
 int aab_cast_f32(const float* x, void* y, long n, int is_bf16, void* stream);
 int aab_num_sms(void);
 

@@ -142,13 +142,13 @@ class OracleUNet3D(nn.Module):
     def dtype(self):
         return self.conv_out.weight.dtype
 
-    def forward(self, sample, timestep, encoder_hidden_states, condition_latent, mask, motion=None):
+    def forward(self, sample, timestep, encoder_hidden_states, condition_latent, mask, motion=None, timestep_cond=None):
         x = torch.cat([condition_latent, sample], dim=2)                      # b c T h w, T = F + 1
         b, _, nf, hh, ww = x.shape
         ts = timestep if torch.is_tensor(timestep) else torch.tensor([timestep], device=x.device)
         ts = ts.reshape(-1).to(x.device).expand(b)
         t_emb = self.time_proj(ts).to(self.dtype)
-        cond = None
+        cond = timestep_cond                                                  # :418-419: used as given when no motion value
         if self.motion_strength and motion is not None:
             cond = self.motion_proj(motion).to(self.dtype)
         emb = self.time_embedding(t_emb, cond).repeat_interleave(nf, dim=0)
@@ -323,3 +323,118 @@ def oracle_svd_sampling_loop(unet, scheduler, vae, image_embeddings, image_laten
                         for i in range(0, z.shape[0], chunk)], dim=0)
     frames = frames.reshape(-1, nf, *frames.shape[1:]).permute(0, 2, 1, 3, 4).float()
     return frames, latents
+
+
+# ---------------------------------------------------------------------------------------------- transparent-video branch (row f4)
+from diffusers._unet2d import (AttnDownBlock2D, AttnUpBlock2D, DownBlock2D, UpBlock2D,  # noqa: E402
+                               UNetMidBlock2D as UNetMidBlock2D_024)
+
+
+class OracleLatentTransparencyOffsetEncoder(nn.Module):
+    """models/layerdiffuse_VAE.py:17-41: RGBA image [b, 4, H, W] -> latent offset [b, 4, H/8, W/8]; nine 3x3 convs
+    (strides 1,1,2,1,2,1,2,1,1) with SiLU between them, none after the last."""
+
+    def __init__(self):
+        super().__init__()
+        spec = [(4, 32, 1), (32, 32, 1), (32, 64, 2), (64, 64, 1), (64, 128, 2), (128, 128, 1), (128, 256, 2),
+                (256, 256, 1), (256, 4, 1)]
+        mods = []
+        for i, (ci, co, st) in enumerate(spec):
+            mods.append(nn.Conv2d(ci, co, 3, padding=1, stride=st))
+            if i < len(spec) - 1:
+                mods.append(nn.SiLU())
+        self.blocks = nn.Sequential(*mods)
+
+    def forward(self, x):
+        return self.blocks(x)
+
+
+class OracleUNet384(nn.Module):
+    """models/layerdiffuse_VAE.py:44-177 (`UNet384`, the LayerDiffuse alpha decoder): a 2-D UNet without time embedding,
+    GroupNorm(4), 3 DownBlock2D + 1 AttnDownBlock2D (head dim 8), mid block with attention, AttnUpBlock2D + 3 UpBlock2D;
+    the SD latent enters through a 1x1 conv and is added before the last down block (:152-153, the 8x-downsampled level)."""
+
+    def __init__(self, in_channels=3, out_channels=4, block_out_channels=(32, 64, 128, 256), layers_per_block=2,
+                 attention_head_dim=8, norm_num_groups=4, norm_eps=1e-5):
+        super().__init__()
+        ch, g, e, hd = list(block_out_channels), norm_num_groups, norm_eps, attention_head_dim
+        n = len(ch)
+        self.conv_in = nn.Conv2d(in_channels, ch[0], 3, padding=1)
+        self.latent_conv_in = nn.Conv2d(4, ch[2], 1)
+        self.down_blocks = nn.ModuleList()
+        prev = ch[0]
+        for i in range(n):
+            kw = dict(num_layers=layers_per_block, in_channels=prev, out_channels=ch[i], temb_channels=None, resnet_eps=e,
+                      resnet_act_fn="silu", resnet_groups=g, downsample_padding=1)
+            if i < n - 1:
+                self.down_blocks.append(DownBlock2D(add_downsample=True, **kw))
+            else:
+                self.down_blocks.append(AttnDownBlock2D(attention_head_dim=hd, downsample_type=None, **kw))
+            prev = ch[i]
+        self.mid_block = UNetMidBlock2D_024(in_channels=ch[-1], temb_channels=None, resnet_eps=e, resnet_act_fn="silu",
+                                            output_scale_factor=1, attention_head_dim=hd, resnet_groups=g)
+        self.up_blocks = nn.ModuleList()
+        rev = ch[::-1]
+        out_c = rev[0]
+        for i in range(n):
+            prev_out, out_c = out_c, rev[i]
+            in_c = rev[min(i + 1, n - 1)]
+            kw = dict(num_layers=layers_per_block + 1, in_channels=in_c, out_channels=out_c, prev_output_channel=prev_out,
+                      temb_channels=None, resnet_eps=e, resnet_act_fn="silu", resnet_groups=g)
+            if i == 0:
+                self.up_blocks.append(AttnUpBlock2D(attention_head_dim=hd, upsample_type="conv", **kw))
+            else:
+                self.up_blocks.append(UpBlock2D(add_upsample=i < n - 1, **kw))
+        self.conv_norm_out = nn.GroupNorm(num_channels=ch[0], num_groups=g, eps=e)
+        self.conv_act = nn.SiLU()
+        self.conv_out = nn.Conv2d(ch[0], out_channels, 3, padding=1)
+
+    def forward(self, x, latent):
+        sample_latent = self.latent_conv_in(latent)
+        sample = self.conv_in(x)
+        skips = (sample,)
+        for i, blk in enumerate(self.down_blocks):
+            if i == 3:
+                sample = sample + sample_latent
+            sample, res = blk(hidden_states=sample, temb=None)
+            skips += res
+        sample = self.mid_block(sample, None)
+        for blk in self.up_blocks:
+            res = skips[-len(blk.resnets):]
+            skips = skips[:-len(blk.resnets)]
+            sample = blk(sample, res, None)
+        return self.conv_out(self.conv_act(self.conv_norm_out(sample)))
+
+
+def oracle_rgba_postprocess(decoded_rgba_bf, b, f):
+    """models/pipeline_stage2.py:300-318: decoder output [(b f), 4, H, W] (model dtype) -> uint8 RGBA frames [f, H, W, 4]:
+    alpha * 255 thresholded at 127 to {0, 255}; foreground (fg + 1) * 127.5; float -> clip(0, 255) -> truncate."""
+    import numpy as np
+    h, w = decoded_rgba_bf.shape[-2:]
+    d = decoded_rgba_bf.reshape(b, f, 4, h, w).permute(0, 2, 1, 3, 4)
+    alpha = d[:, 3:] * 255.0
+    alpha[alpha > 127] = 255
+    alpha[alpha <= 127] = 0
+    fg = (d[:, :3] + 1.0) * 127.5
+    pngs = torch.cat((fg, alpha), dim=1)[0].permute(1, 0, 2, 3).permute(0, 2, 3, 1)
+    return pngs.detach().cpu().float().numpy().clip(0, 255).astype(np.uint8)
+
+
+@torch.no_grad()
+def oracle_masked_sampling_loop(unet, scheduler, vae, vae_alpha_decoder, latents, prompt_embeds, negative_prompt_embeds,
+                                condition_latent, mask, motion, guidance_scale=9.0, num_inference_steps=50, timesteps=None):
+    """Restates MaskedLatentToVideoPipeline.__call__ (models/pipeline_stage2.py:171-337) as train_transparent_i2v_stage2.py:500-515
+    calls it (`image_embeds=None`): the denoising loop is LatentToVideoPipeline's (:252-296 equals models/pipeline.py:156-197 once
+    `encode_prompt`'s tuple is re-concatenated [negative, positive] at :232); then decode_latents (:299), the alpha decoder on the
+    decoded frames + final latents (:305-309) and the RGBA post-processing (:311-324).
+    Returns (video fp32 [b,3,f,H,W], latents, pngs uint8 [f,H,W,4])."""
+    video, latents = oracle_sampling_loop(unet, scheduler, latents, prompt_embeds, negative_prompt_embeds, condition_latent,
+                                          mask, motion, guidance_scale=guidance_scale,
+                                          num_inference_steps=num_inference_steps, timesteps=timesteps, vae=vae,
+                                          output_type="pt")
+    b, c, f, h, w = video.shape
+    dtype = latents.dtype
+    x = video.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w).to(dtype)
+    lat = latents.permute(0, 2, 1, 3, 4).reshape(b * f, 4, *latents.shape[-2:])
+    rgba = vae_alpha_decoder(x, lat)
+    return video, latents, oracle_rgba_postprocess(rgba, b, f)

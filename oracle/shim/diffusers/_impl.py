@@ -1222,6 +1222,25 @@ class TextToVideoSDPipeline(DiffusionPipeline, TextualInversionLoaderMixin, Lora
             prompt_embeds = torch.cat([negative_prompt_embeds, prompt_embeds])
         return prompt_embeds
 
+    def encode_prompt(self, prompt, device, num_images_per_prompt, do_classifier_free_guidance, negative_prompt=None,
+                      prompt_embeds=None, negative_prompt_embeds=None, lora_scale=None, clip_skip=None):
+        """diffusers 0.24 `encode_prompt` (what models/pipeline_stage2.py:230-232 calls): the tuple
+        `(prompt_embeds, negative_prompt_embeds)`; `_encode_prompt` above is its deprecated wrapper that concatenates
+        `[negative, positive]`.  Pre-computed embeddings only, like `_encode_prompt`."""
+        if prompt_embeds is None:
+            raise NotImplementedError("oracle supports prompt_embeds only (CLIP encode is SURVEY 8f 'next')")
+        bs_embed, seq_len, _ = prompt_embeds.shape
+        prompt_embeds = prompt_embeds.repeat(1, num_images_per_prompt, 1).view(
+            bs_embed * num_images_per_prompt, seq_len, -1)
+        if do_classifier_free_guidance:
+            if negative_prompt_embeds is None:
+                raise NotImplementedError("oracle needs negative_prompt_embeds under CFG")
+            seq_len = negative_prompt_embeds.shape[1]
+            negative_prompt_embeds = negative_prompt_embeds.to(dtype=prompt_embeds.dtype, device=device)
+            negative_prompt_embeds = negative_prompt_embeds.repeat(1, num_images_per_prompt, 1).view(
+                bs_embed * num_images_per_prompt, seq_len, -1)
+        return prompt_embeds, negative_prompt_embeds
+
     def prepare_extra_step_kwargs(self, generator, eta):
         accepts_eta = "eta" in set(inspect.signature(self.scheduler.step).parameters.keys())
         extra_step_kwargs = {}

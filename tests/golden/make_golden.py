@@ -83,6 +83,9 @@ def main():
     product_shape_goldens()
     oddsize_unet_golden()
     svd_goldens()
+    svd_text_goldens()
+    transparent_goldens()
+    forward_branches_golden()
 
 
 SMALL = dict(sample_size=16, block_out_channels=(64, 128, 256, 256), attention_head_dim=64, cross_attention_dim=128,
@@ -324,12 +327,120 @@ def svd_text_goldens():
     print("text context ->", out["text_error"])
 
 
+def transparent_goldens():
+    """Row f4, the transparent-video branch, from the VERBATIM reference files: `models/layerdiffuse_VAE.py` (`UNet384`,
+    `LatentTransparencyOffsetEncoder`) and `models/pipeline_stage2.py` `MaskedLatentToVideoPipeline.__call__`, called unbound on a
+    `TextToVideoSDPipeline` object the way train_transparent_i2v_stage2.py:500-515 does (single-frame condition latent and mask,
+    `return_dict=False`).  The reference passes `image_embeds=` to the UNet (:282), which `models/unet_3d_condition_mask.py` does
+    not accept: the fixture UNet is the verbatim class with that one keyword swallowed (it is None in the trainer's call)."""
+    import types
+    import diffusers
+    sys.modules.setdefault("imageio", types.ModuleType("imageio"))
+    from models.layerdiffuse_VAE import LatentTransparencyOffsetEncoder, UNet384   # verbatim reference
+    from models.pipeline_stage2 import MaskedLatentToVideoPipeline                 # verbatim reference
+    from models.unet_3d_condition_mask import UNet3DConditionModel                 # verbatim reference
+
+    class UNetDroppingImageEmbeds(UNet3DConditionModel):
+        def forward(self, *a, image_embeds=None, **k):
+            assert image_embeds is None
+            return super().forward(*a, **k)
+
+    out = {}
+    # --- the two models alone, bf16-rounded weights and inputs, fp32 math (what the GPU parity test loads into the sm_100a mirror)
+    dec = fill_deterministic(UNet384().eval(), seed=7)
+    dec.load_state_dict({k: v.bfloat16().float() for k, v in dec.state_dict().items()})
+    enc = fill_deterministic(LatentTransparencyOffsetEncoder().eval(), seed=8)
+    enc.load_state_dict({k: v.bfloat16().float() for k, v in enc.state_dict().items()})
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(2, 3, 64, 96, generator=g).clamp(-1, 1).bfloat16().float()
+    lat = torch.randn(2, 4, 8, 12, generator=g).bfloat16().float()
+    rgba_in = torch.cat([torch.randn(1, 3, 64, 96, generator=g).clamp(-1, 1), torch.rand(1, 1, 64, 96, generator=g)], dim=1)
+    rgba_in = rgba_in.bfloat16().float()
+    with torch.no_grad():
+        out["dec_out"] = dec(x, lat)
+        out["enc_out"] = enc(rgba_in)
+    out.update(dec_x=x, dec_latent=lat, enc_in=rgba_in, dec_keys=sorted(dec.state_dict().keys()),
+               enc_keys=sorted(enc.state_dict().keys()), dec_config=dict(dec.config))
+    print("transparent: UNet384", tuple(out["dec_out"].shape), float(out["dec_out"].abs().mean()), "encoder",
+          tuple(out["enc_out"].shape), float(out["enc_out"].abs().mean()))
+
+    # --- the pipeline call: tiny UNet3D + tiny VAE + full-size UNet384 (it is small), DDIM 3 steps, CFG 9
+    unet = fill_deterministic(UNetDroppingImageEmbeds(**TINY).eval(), seed=0)
+    vae = fill_deterministic(diffusers.AutoencoderKL(**TINY_VAE).eval(), seed=1)
+    dec32 = fill_deterministic(UNet384().eval(), seed=7)
+    sched = diffusers.DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                                    clip_sample=False, set_alpha_to_one=False, steps_offset=1)
+    pipe = diffusers.TextToVideoSDPipeline(vae=vae, text_encoder=None, tokenizer=None, unet=unet, scheduler=sched)
+    g = torch.Generator().manual_seed(9)
+    lat0 = torch.randn(1, 4, 4, 16, 16, generator=g)
+    cond = torch.randn(1, 4, 1, 16, 16, generator=g)
+    pe = torch.randn(1, 7, 32, generator=g)
+    ne = torch.randn(1, 7, 32, generator=g)
+    mask1 = (torch.rand(1, 1, 1, 16, 16, generator=g) > 0.5).float()          # mask_1_frame, train_transparent_i2v_stage2.py:441
+    video, latents, pngs, alpha_jpg, pngs_rgb = MaskedLatentToVideoPipeline.__call__(
+        pipe, clean_latents=None, vae_alpha_decoder=dec32, prompt_embeds=pe, negative_prompt_embeds=ne, latents=lat0,
+        width=128, height=128, num_frames=4, num_inference_steps=3, guidance_scale=9.0, motion=[5], return_dict=False,
+        condition_latent=cond, mask=mask1, output_type="pt")
+    out.update(pipe_latents_in=lat0, pipe_cond=cond, pipe_pe=pe, pipe_ne=ne, pipe_mask=mask1, pipe_video=video.half(),
+               pipe_latents=latents, pipe_pngs=torch.from_numpy(pngs.copy()), pipe_alpha=torch.from_numpy(alpha_jpg.copy()))
+    # the call as the reference wrote it, on its own UNet: the TypeError the mirror documents
+    plain = fill_deterministic(UNet3DConditionModel(**TINY).eval(), seed=0)
+    pipe2 = diffusers.TextToVideoSDPipeline(vae=vae, text_encoder=None, tokenizer=None, unet=plain, scheduler=sched)
+    try:
+        MaskedLatentToVideoPipeline.__call__(pipe2, vae_alpha_decoder=dec32, prompt_embeds=pe, negative_prompt_embeds=ne,
+                                             latents=lat0, width=128, height=128, num_frames=4, num_inference_steps=3,
+                                             motion=[5], return_dict=False, condition_latent=cond, mask=mask1)
+        out["image_embeds_error"] = None
+    except TypeError as e:
+        out["image_embeds_error"] = str(e)
+    torch.save(out, os.path.join(HERE, "transparent_ref.pt"))
+    print("transparent: pipeline video", tuple(video.shape), "latents", float(latents.abs().mean()), "pngs", pngs.shape,
+          "alpha on:", float((alpha_jpg == 255).mean()), "| as-written call ->", out["image_embeds_error"])
+
+
+def forward_branches_golden():
+    """The remaining keyword branches of the VERBATIM UNet3DConditionModel.forward (models/unet_3d_condition_mask.py:338-526):
+    `attention_mask` (:385-388 builds a bias that no block ever reads: models/unet_3d_blocks.py:340,489,720) and `class_labels`
+    (never read) leave the output bit-identical; `timestep_cond` enters time_embedding.cond_proj when no motion value is used
+    (:418-419)."""
+    from models.unet_3d_condition_mask import UNet3DConditionModel            # verbatim reference
+    torch.manual_seed(0)
+    ref = fill_deterministic(UNet3DConditionModel(**TINY).eval(), seed=0)
+    inp = tiny_inputs()
+    g = torch.Generator().manual_seed(12)
+    tc = torch.randn(2, 32, generator=g)
+    am = (torch.rand(2, 7, generator=g) > 0.3).float()
+    with torch.no_grad():
+        base = ref(inp["sample"], inp["timestep"], inp["ehs"], condition_latent=inp["cond"], mask=inp["mask"],
+                   motion=inp["motion"]).sample
+        with_am = ref(inp["sample"], inp["timestep"], inp["ehs"], condition_latent=inp["cond"], mask=inp["mask"],
+                      motion=inp["motion"], attention_mask=am).sample
+        with_cl = ref(inp["sample"], inp["timestep"], inp["ehs"], condition_latent=inp["cond"], mask=inp["mask"],
+                      motion=inp["motion"], class_labels=torch.tensor([1, 2])).sample
+        out_tc = ref(inp["sample"], inp["timestep"], inp["ehs"], condition_latent=inp["cond"], mask=inp["mask"],
+                     motion=None, timestep_cond=tc).sample
+        out_tc_motion = ref(inp["sample"], inp["timestep"], inp["ehs"], condition_latent=inp["cond"], mask=inp["mask"],
+                            motion=inp["motion"], timestep_cond=tc).sample
+    torch.save({"attention_mask_noop": bool(torch.equal(base, with_am)), "class_labels_noop": bool(torch.equal(base, with_cl)),
+                "timestep_cond_overridden_by_motion": bool(torch.equal(base, out_tc_motion)),
+                "timestep_cond": tc, "out_timestep_cond": out_tc}, os.path.join(HERE, "unet_forward_branches_ref.pt"))
+    print("unet_forward_branches_ref.pt: attention_mask noop", torch.equal(base, with_am), "| class_labels noop",
+          torch.equal(base, with_cl), "| motion overrides timestep_cond", torch.equal(base, out_tc_motion),
+          "| timestep_cond changes output by", float((out_tc - base).abs().mean()))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "svd":
         svd_goldens()
     elif len(sys.argv) > 1 and sys.argv[1] == "svd_text":
         import diffusers  # noqa: F401  (the shim)
         svd_text_goldens()
+    elif len(sys.argv) > 1 and sys.argv[1] == "branches":
+        import diffusers  # noqa: F401  (the shim)
+        forward_branches_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "transparent":
+        import diffusers  # noqa: F401  (the shim)
+        transparent_goldens()
     elif len(sys.argv) > 1 and sys.argv[1] == "oddsize":
         import diffusers  # noqa: F401  (the shim)
         oddsize_unet_golden()

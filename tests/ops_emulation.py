@@ -1,0 +1,168 @@
+"""TEST INFRASTRUCTURE (CPU): plain-torch stand-ins for the `animate_anything_b200.ops` wrappers, with the semantics their
+docstrings state (channels-last activations, tap-major conv weights, `D = act(acc + bias + bias2 + residual) * out_scale`).
+They exist so that the HOST logic of a mirror class — weight-layout conversion, head padding, skip bookkeeping, geometry —
+can be executed and compared with the oracle in the CPU suite, where no kernel can run.  They say nothing about the kernels
+(those are compared with PyTorch references by the `-m gpu` tests) and the product never imports this file.
+
+    with emulated_ops():
+        prep = model._build_prepared(torch.float32, torch.device("cpu"))
+        y = model._forward_chunk(prep, ...)
+"""
+from __future__ import annotations
+
+import contextlib
+import math
+
+import torch
+import torch.nn.functional as F
+
+from animate_anything_b200 import ops
+from animate_anything_b200._lib import ACT_GELU, ACT_NONE, ACT_QUICK_GELU, ACT_SILU
+
+
+def _act(x, act):
+    if act == ACT_NONE:
+        return x
+    if act == ACT_SILU:
+        return F.silu(x)
+    if act == ACT_GELU:
+        return F.gelu(x)
+    if act == ACT_QUICK_GELU:
+        return x * torch.sigmoid(1.702 * x)
+    raise ValueError(act)
+
+
+def _epilogue(acc, bias=None, bias2=None, rows_per_bias2=1, residual=None, act=ACT_NONE, out_scale=1.0, out_f32=False,
+              stats=False, **unused):
+    bad = set(unused) - {"block_n", "max_ctas", "direct", "ld_res", "out_rows"}
+    assert not bad, bad
+    if bias is not None:
+        acc = acc + bias
+    if bias2 is not None:
+        acc = acc + bias2.repeat_interleave(rows_per_bias2, dim=0)
+    if residual is not None:
+        acc = acc + residual
+    return _act(acc, act) * out_scale
+
+
+def linear(x, w, bias=None, geglu=False, **kw):
+    acc = x.float() @ w.float().t()
+    if geglu:
+        nh = acc.shape[1] // 2
+        b = 0 if bias is None else bias
+        acc = acc + b
+        return acc[:, :nh] * F.gelu(acc[:, nh:])
+    return _epilogue(acc, bias, **kw)
+
+
+def conv1x1_cat(x, x2, w, bias=None, **kw):
+    return linear(x if x2 is None else torch.cat([x, x2], dim=1), w, bias, **kw)
+
+
+def _w4(w, cin):
+    co = w.shape[0]
+    return w.float().view(co, 3, 3, cin).permute(0, 3, 1, 2)
+
+
+def conv3x3(x, w, bias=None, x2=None, **kw):
+    if x2 is not None:
+        x = torch.cat([x, x2], dim=-1)
+    n, h, wd, c = x.shape
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), _w4(w, c), padding=1)
+    return _epilogue(y.permute(0, 2, 3, 1).reshape(n * h * wd, -1), bias, **kw)
+
+
+def conv3x3_stride2(x, w, bias=None, pad_mode="sym", **kw):
+    n, h, wd, c = x.shape
+    assert h % 2 == 0 and wd % 2 == 0 and c % 64 == 0          # the wrapper's own assertion
+    xi = x.float().permute(0, 3, 1, 2)
+    if pad_mode == "sym":
+        y = F.conv2d(xi, _w4(w, c), stride=2, padding=1)
+    else:
+        y = F.conv2d(F.pad(xi, (0, 1, 0, 1)), _w4(w, c), stride=2)
+    return _epilogue(y.permute(0, 2, 3, 1).reshape(-1, y.shape[1]), bias, **kw)
+
+
+def groupnorm(x, samples, rows, gamma, beta, eps, silu, groups=32, x2=None):
+    if x2 is not None:
+        x = torch.cat([x, x2], dim=1)
+    c = x.shape[1]
+    assert x.shape[0] == samples * rows and c % groups == 0
+    v = x.float().view(samples, rows, groups, c // groups)
+    mean = v.mean(dim=(1, 3), keepdim=True)
+    var = v.var(dim=(1, 3), keepdim=True, unbiased=False)
+    y = ((v - mean) / torch.sqrt(var + eps)).view(samples * rows, c) * gamma + beta
+    return F.silu(y) if silu else y
+
+
+def flash_attn_d64(q, q_col0, kv, k_col0, v_col0, nb, lq, lk, heads, kv_batch_div=1, out=None, causal=False, scale=None):
+    assert not causal and out is None
+    scale = 1.0 / math.sqrt(64.0) if scale is None else scale
+    nb_kv = kv.shape[0] // lk
+
+    def heads_of(t, col0, n, l):
+        return t[:, col0: col0 + heads * 64].float().view(n, l, heads, 64).permute(0, 2, 1, 3)
+    qq = heads_of(q, q_col0, nb, lq)
+    idx = torch.arange(nb) // kv_batch_div
+    kk = heads_of(kv, k_col0, nb_kv, lk)[idx]
+    vv = heads_of(kv, v_col0, nb_kv, lk)[idx]
+    p = torch.softmax(qq @ kk.transpose(-1, -2) * scale, dim=-1)
+    return (p @ vv).permute(0, 2, 1, 3).reshape(nb * lq, heads * 64)
+
+
+def image_to_nhwc8(img):
+    n, c, h, w = img.shape
+    out = torch.zeros((n, h, w, 8), dtype=img.dtype)
+    out[..., :c] = img.permute(0, 2, 3, 1)
+    return out
+
+
+def video_f32_to_nhwc8(video, dtype):
+    b, c, f, h, w = video.shape
+    out = torch.zeros((b * f, h, w, 8), dtype=dtype)
+    out[..., :c] = video.permute(0, 2, 3, 4, 1).reshape(b * f, h, w, c).to(dtype)
+    return out
+
+
+def upsample2x(x):
+    return x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+
+
+def pad_cols(x, dst_cols):
+    assert x.shape[1] % 8 == 0 and dst_cols % 8 == 0
+    return F.pad(x, (0, dst_cols - x.shape[1]))
+
+
+def cat_cols(x, x2):
+    return torch.cat([x, x2], dim=1)
+
+
+def svd_out_finalize(y, b, f, h, w, dtype):
+    return y[:, :4].reshape(b, f, h, w, 4).permute(0, 1, 4, 2, 3).to(dtype)
+
+
+def rgba_finalize_u8(y, pixels, bf16):
+    dt = torch.bfloat16 if bf16 else torch.float16
+    v = y[:pixels, :4].to(dt)
+    fg = ((v[:, :3] + 1.0) * 127.5).float().clamp(0, 255)
+    a = v[:, 3:] * 255.0
+    a = torch.where(a > 127, torch.full_like(a, 255.0), torch.zeros_like(a)).float()
+    return torch.cat([fg, a], dim=1).to(torch.uint8)
+
+
+_EMULATED = dict(linear=linear, conv1x1_cat=conv1x1_cat, conv3x3=conv3x3, conv3x3_stride2=conv3x3_stride2, groupnorm=groupnorm,
+                 flash_attn_d64=flash_attn_d64, image_to_nhwc8=image_to_nhwc8, video_f32_to_nhwc8=video_f32_to_nhwc8,
+                 upsample2x=upsample2x, pad_cols=pad_cols, cat_cols=cat_cols, svd_out_finalize=svd_out_finalize,
+                 rgba_finalize_u8=rgba_finalize_u8)
+
+
+@contextlib.contextmanager
+def emulated_ops():
+    saved = {k: getattr(ops, k) for k in _EMULATED}
+    try:
+        for k, fn in _EMULATED.items():
+            setattr(ops, k, fn)
+        yield
+    finally:
+        for k, fn in saved.items():
+            setattr(ops, k, fn)

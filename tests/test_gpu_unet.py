@@ -222,3 +222,39 @@ def test_unet_odd_latent_size_upsample_size_path():
     assert (o32 - ref).abs().max().item() <= 5e-3 * ref.abs().mean().item()
     assert out.shape == ref.shape == (1, 4, 3, 15, 17)
     assert_vs_stock(record_parity("unet SMALL fp16 odd 15x17", "output (golden)", out, ref, stock))
+
+
+def test_unet_forward_keyword_branches():
+    """`attention_mask` / `class_labels` are accepted and ignored like the reference forward does (its blocks never read the
+    mask: models/unet_3d_blocks.py:340,489,720; fixture unet_forward_branches_ref.pt records the verbatim behaviour), and
+    `timestep_cond` (:418-419, no motion value) goes through time_embedding.cond_proj."""
+    dtype = torch.float16
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    oracle, ours = _models(SMALL, dtype)
+    inp = _inputs(2, 4, 16, 77, 128, dtype)
+    mot = torch.tensor([4.0], device="cuda")
+    base = ours(inp["sample"], 500, inp["ehs"], condition_latent=inp["cond"], mask=inp["mask"], motion=mot).sample
+    same = ours(inp["sample"], 500, inp["ehs"], condition_latent=inp["cond"], mask=inp["mask"], motion=mot,
+                attention_mask=torch.ones(2, 77, device="cuda"), class_labels=torch.tensor([1, 2], device="cuda"),
+                timestep_cond=torch.randn(2, 64, device="cuda")).sample          # a motion value overrides timestep_cond
+    assert torch.equal(base, same)
+    g = torch.Generator().manual_seed(8)
+    for rows in (2, 1):
+        tc = torch.randn(rows, 64, generator=g).to(dtype).cuda()
+        out = ours(inp["sample"], 500, inp["ehs"], condition_latent=inp["cond"], mask=inp["mask"], motion=None,
+                   timestep_cond=tc).sample
+        with torch.no_grad():
+            ref = oracle.float()(inp["sample"].float(), 500, inp["ehs"].float(), inp["cond"].float(), inp["mask"].float(),
+                                 motion=None, timestep_cond=tc.float())
+            stock = oracle.to(dtype)(inp["sample"], 500, inp["ehs"], inp["cond"], inp["mask"], motion=None,
+                                     timestep_cond=tc).float()
+        e, es, sc = (out.float() - ref).abs(), (stock - ref).abs(), ref.abs().mean().item()
+        assert (out.float() - base.float()).abs().mean().item() > 1e-3            # the branch is live
+        assert e.mean().item() <= 1.5 * es.mean().item() + 2e-4 * sc and e.max().item() <= 2.0 * es.max().item() + 2e-3 * sc
+    with pytest.raises(ValueError):
+        ours(inp["sample"], 500, inp["ehs"], condition_latent=inp["cond"], mask=inp["mask"], motion=None,
+             timestep_cond=torch.randn(3, 64, device="cuda"))
+    with pytest.raises(NotImplementedError):
+        ours(inp["sample"], 500, inp["ehs"], condition_latent=inp["cond"], mask=inp["mask"], motion=mot,
+             mid_block_additional_residual=torch.zeros(1, device="cuda"))

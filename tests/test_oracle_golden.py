@@ -203,3 +203,96 @@ def test_svd_text_pipeline_image_branch_matches_reference():
     assert gold["text_error"] is not None and "expanded size of the tensor (1) must match the existing size (7)" in gold["text_error"]
     with pytest.raises(RuntimeError, match="expanded size"):
         unet(torch.zeros(2, 5, 9, 8, 16), 1.0, torch.zeros(2, 7, 64), torch.zeros(2, 3))
+
+
+# ---------------------------------------------------------------------------------------------- transparent-video branch (row f4)
+def test_transparent_models_match_reference_files():
+    """OracleUNet384 / OracleLatentTransparencyOffsetEncoder (what travels to the GPU box) against the outputs of the VERBATIM
+    models/layerdiffuse_VAE.py classes (tests/golden/make_golden.py::transparent_goldens): same keys, same numbers."""
+    from oracle.composition import OracleLatentTransparencyOffsetEncoder, OracleUNet384
+    gold = torch.load(os.path.join(HERE, "golden", "transparent_ref.pt"))
+    dec = OracleUNet384().eval()
+    assert sorted(dec.state_dict().keys()) == gold["dec_keys"]
+    fill_deterministic(dec, seed=7)
+    dec.load_state_dict({k: v.bfloat16().float() for k, v in dec.state_dict().items()})
+    enc = OracleLatentTransparencyOffsetEncoder().eval()
+    assert sorted(enc.state_dict().keys()) == gold["enc_keys"]
+    fill_deterministic(enc, seed=8)
+    enc.load_state_dict({k: v.bfloat16().float() for k, v in enc.state_dict().items()})
+    with torch.no_grad():
+        y = dec(gold["dec_x"], gold["dec_latent"])
+        e = enc(gold["enc_in"])
+    assert torch.allclose(y, gold["dec_out"], rtol=1e-5, atol=1e-5), float((y - gold["dec_out"]).abs().max())
+    assert torch.allclose(e, gold["enc_out"], rtol=1e-5, atol=1e-6)
+
+
+def test_masked_pipeline_matches_reference_pipeline_stage2():
+    """oracle_masked_sampling_loop against the VERBATIM MaskedLatentToVideoPipeline.__call__ (models/pipeline_stage2.py:171-337)
+    called unbound like train_transparent_i2v_stage2.py:500-515: final latents, decoded video, uint8 RGBA frames; and the
+    TypeError the as-written call raises on the repository's own UNet (`image_embeds`, :282)."""
+    from oracle.composition import OracleUNet384, oracle_masked_sampling_loop
+    gold_u = torch.load(os.path.join(HERE, "golden", "unet_tiny_ref.pt"))
+    gold_p = torch.load(os.path.join(HERE, "golden", "pipeline_tiny_ref.pt"))
+    gold = torch.load(os.path.join(HERE, "golden", "transparent_ref.pt"))
+    unet = _tiny_unet(gold_u)
+    vae = fill_deterministic(AutoencoderKL(**gold_p["vae_config"]).eval(), seed=1)
+    dec = fill_deterministic(OracleUNet384().eval(), seed=7)
+    sched = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
+                          set_alpha_to_one=False, steps_offset=1)
+    video, lat, pngs = oracle_masked_sampling_loop(unet, sched, vae, dec, gold["pipe_latents_in"], gold["pipe_pe"],
+                                                   gold["pipe_ne"], gold["pipe_cond"], gold["pipe_mask"], [5],
+                                                   guidance_scale=9.0, num_inference_steps=3)
+    assert torch.allclose(lat, gold["pipe_latents"], rtol=1e-4, atol=1e-4), float((lat - gold["pipe_latents"]).abs().max())
+    assert torch.allclose(video, gold["pipe_video"].float(), rtol=2e-3, atol=2e-3)
+    ref = gold["pipe_pngs"].numpy().astype(int)
+    assert pngs.shape == ref.shape == (4, 128, 128, 4)
+    d = abs(pngs.astype(int) - ref)
+    assert d[..., :3].max() <= 1 and (d[..., 3] != 0).mean() < 1e-3        # foreground: truncation ties; alpha: threshold ties
+    assert (gold["pipe_alpha"].numpy() == gold["pipe_pngs"].numpy()[..., 3]).all()
+    assert "image_embeds" in gold["image_embeds_error"]
+
+
+def test_unet2d_shim_recalled_facts():
+    """One assertion per recalled diffusers-0.24 `unet_2d_blocks` fact listed in oracle/shim/diffusers/_unet2d.py."""
+    from diffusers.models.unet_2d_blocks import UNetMidBlock2D, get_down_block, get_up_block
+    kw = dict(num_layers=2, in_channels=16, out_channels=32, temb_channels=None, resnet_eps=1e-5, resnet_act_fn="silu",
+              resnet_groups=4, downsample_padding=1, attention_head_dim=8)
+    d = get_down_block("DownBlock2D", add_downsample=True, **kw).eval()
+    x = torch.randn(1, 16, 8, 8)
+    h, states = d(hidden_states=x, temb=None)
+    assert len(states) == 3 and states[-1] is h and h.shape == (1, 32, 4, 4)         # downsampler output is a skip too
+    a = get_down_block("AttnDownBlock2D", add_downsample=False, **kw).eval()
+    assert a.downsamplers is None and len(a.attentions) == 2                         # add_downsample False -> type None
+    at = a.attentions[0]
+    assert at.heads == 4 and at.group_norm.num_groups == 4 and at.group_norm.eps == 1e-5 and at.residual_connection
+    assert at.to_q.bias is not None and abs(at.scale - 8 ** -0.5) < 1e-9
+    a2 = get_down_block("AttnDownBlock2D", add_downsample=True, **kw).eval()
+    assert a2.downsamplers is not None                                               # default downsample_type "conv"
+    ukw = dict(num_layers=3, in_channels=16, out_channels=32, prev_output_channel=64, temb_channels=None, resnet_eps=1e-5,
+               resnet_act_fn="silu", resnet_groups=4, attention_head_dim=8)
+    u = get_up_block("UpBlock2D", add_upsample=True, **ukw).eval()
+    assert [r.in_channels for r in u.resnets] == [64 + 32, 32 + 32, 32 + 16]
+    au = get_up_block("AttnUpBlock2D", add_upsample=False, **ukw).eval()
+    assert au.upsamplers is None and len(au.attentions) == 3
+    m = UNetMidBlock2D(in_channels=32, temb_channels=None, resnet_eps=1e-5, resnet_act_fn="silu", output_scale_factor=1,
+                       resnet_time_scale_shift="default", attention_head_dim=8, resnet_groups=4, attn_groups=None,
+                       add_attention=True, dropout=0.0)
+    assert m.attentions[0].group_norm.num_groups == 4 and m.attentions[0].heads == 4 and len(m.resnets) == 2
+
+
+def test_forward_keyword_branches_match_reference():
+    """models/unet_3d_condition_mask.py:338-526 keyword branches recorded from the VERBATIM class: `attention_mask` and
+    `class_labels` do not change the output (no block reads them), a motion value overrides `timestep_cond`, and `timestep_cond`
+    alone enters time_embedding.cond_proj — which the oracle restates."""
+    gold_u = torch.load(os.path.join(HERE, "golden", "unet_tiny_ref.pt"))
+    gold = torch.load(os.path.join(HERE, "golden", "unet_forward_branches_ref.pt"))
+    assert gold["attention_mask_noop"] and gold["class_labels_noop"] and gold["timestep_cond_overridden_by_motion"]
+    m = _tiny_unet(gold_u)
+    inp = tiny_inputs()
+    with torch.no_grad():
+        out = m(inp["sample"], inp["timestep"], inp["ehs"], inp["cond"], inp["mask"], motion=None,
+                timestep_cond=gold["timestep_cond"])
+        out_m = m(inp["sample"], inp["timestep"], inp["ehs"], inp["cond"], inp["mask"], motion=inp["motion"],
+                  timestep_cond=gold["timestep_cond"])
+    assert torch.allclose(out, gold["out_timestep_cond"], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(out_m, gold_u["out"], rtol=1e-5, atol=1e-6)
