@@ -13,5 +13,7 @@ for f in igemm attention norm elementwise; do
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -arch=sm_100a -shared -o ../libaab200.so ../_build/igemm.o ../_build/attention.o ../_build/norm.o ../_build/elementwise.o -lcudart
+# link under a temporary name and rename: a reader (dlopen, a repository snapshot) never sees a half-written library
+$NVCC -arch=sm_100a -shared -o ../libaab200.so.tmp ../_build/igemm.o ../_build/attention.o ../_build/norm.o ../_build/elementwise.o -lcudart
+mv -f ../libaab200.so.tmp ../libaab200.so
 echo "built $(realpath ../libaab200.so)"

@@ -217,6 +217,18 @@ __global__ void copy2d_kernel(const uint16_t* __restrict__ src, long lds, uint16
   dst[r * ldd + c] = src[r * lds + c];
 }
 
+// same copy in 16-byte units (cols, both row strides and both base addresses multiples of 8 elements)
+__global__ void copy2d_v8_kernel(const uint4* __restrict__ src, long lds8, uint4* __restrict__ dst, long ldd8, long rows, int cols8) {
+  pdl_trigger();
+  pdl_wait();
+  const long total = rows * cols8;
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long r = i / cols8;
+  const int c = static_cast<int>(i % cols8);
+  dst[r * ldd8 + c] = src[r * lds8 + c];
+}
+
 // out[0:n16] = out[n16:2*n16] = src (16-byte units): duplicates the rows of the unconditional half for the text half when
 // the CFG pair shares its prefix (see UNet3DConditionModel.forward, `_cfg_shared_prefix`)
 __global__ void dup_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long n16) {
@@ -827,6 +839,12 @@ extern "C" int aab_pad_br(const void* x, void* y, long n, int h, int w, int ph, 
 extern "C" int aab_copy2d(const void* src, long lds, void* dst, long ldd, long rows, int cols, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const long total = rows * cols;
+  if (cols % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(src) % 16) == 0 &&
+      (reinterpret_cast<uintptr_t>(dst) % 16) == 0) {
+    launch_k(copy2d_v8_kernel, dim3(AAB_GRID(total / 8, 256)), dim3(256), 0, stream, reinterpret_cast<const uint4*>(src), lds / 8,
+             reinterpret_cast<uint4*>(dst), ldd / 8, rows, cols / 8);
+    AAB_LAUNCH_RET();
+  }
   launch_k(copy2d_kernel, dim3(AAB_GRID(total, 256)), dim3(256), 0, stream, reinterpret_cast<const uint16_t*>(src), lds,
                                                           reinterpret_cast<uint16_t*>(dst), ldd, rows, cols);
   AAB_LAUNCH_RET();
