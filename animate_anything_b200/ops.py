@@ -202,7 +202,13 @@ def igemm(a: torch.Tensor, a_dims, a_strides, w: torch.Tensor, n: int, kc: int, 
     d.flags = flags | IGEMM_DBG_FLAGS
     if block_n is None:
         if n_out < 64 and not geglu:
-            block_n = 32 if n_out <= 32 else 64
+            # 32-column tiles only have the direct-store epilogue (measured on UNet384's 32-channel level, 4.2 M rows:
+            # 2.1-2.4 ms per launch whatever K, profiles/r02c_alpha_tail_kernels_before.md); an output that qualifies for
+            # the staged epilogue (TMA store in 32-column boxes) takes a 64-column tile whose upper half is a ragged,
+            # zero-filled N remainder instead
+            staged_ok = (n_out % 32 == 0 and not out_f32 and not direct and not scale_acc and ld_out % 8 == 0 and
+                         os.environ.get("AAB_IGEMM_N32_DIRECT", "0") == "0")
+            block_n = 64 if (n_out > 32 or staged_ok) else 32
         else:
             block_n = pick_block_n(n_out, m_tiles, geglu, kc * len(taps))
     if block_n == 256 and use_pair(kc * len(taps), n):

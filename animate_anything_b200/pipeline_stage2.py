@@ -15,7 +15,8 @@ needs the attributes of `LatentToVideoPipeline`, which is what `TextToVideoSDPip
 
 Deviation, stated: the reference passes `image_embeds=image_embeds` to the UNet unconditionally (:282), a keyword that
 `models/unet_3d_condition_mask.py:338-353` does not accept — as written the call raises TypeError with the repository's own
-UNet.  The mirror forwards the keyword only when it is not None (the trainer leaves it at None); a non-None value raises.
+UNet (recorded in tests/golden/transparent_ref.pt).  The mirror does not forward the keyword (the trainer leaves it at None);
+a non-None value raises NotImplementedError.
 `ImageToVideoPipeline` (:11-169, an `_encode_prompt` variant with image embeddings) and `ConcatLatentToVideoPipeline`
 (:339-590, an 8-channel UNet called without `condition_latent`) drive UNet variants that are not in the reference tree and
 are not mirrored.
