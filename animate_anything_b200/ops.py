@@ -101,6 +101,7 @@ def _tiles_cover_rows_in_order(dim_d, box) -> bool:
 
 IGEMM_QUAD = os.environ.get("AAB_IGEMM_QUAD", "0") != "0"     # clusters of 4 with weight-tile multicast (see igemm.cu)
 GN_COLSTATS = os.environ.get("AAB_GN_COLSTATS", "1") != "0"
+N64_NARROW = os.environ.get("AAB_IGEMM_N64_NARROW", "1") != "0"
 
 
 def pick_block_n(n_out: int, m_tiles: int, geglu: bool = False, k_total: int = 1 << 30) -> int:
@@ -112,6 +113,11 @@ def pick_block_n(n_out: int, m_tiles: int, geglu: bool = False, k_total: int = 1
         return 256 if n_out > 64 else 128
     if m_tiles <= 2:
         return 64           # weight-streaming (GEMV-like: text K/V, time embedding): spread the weight rows over many CTAs
+    if n_out <= 64 and N64_NARROW:
+        # a 64-column output on a 256-column tile stages 32 KiB of (mostly zero-filled) weight rows per k-block and leaves
+        # room for one CTA per SM; UNet384's 64-channel levels (1-4 M rows) are HBM / latency bound and want the narrow tile
+        # (A/B: profiles/r02c_alpha_tail_kernels_*.md).  No shape of the SD UNet / VAE / SVD / CLIP paths has N <= 64.
+        return 64
     if k_total <= 384 and n_out <= 640:
         # epilogue/HBM-bound (tiny K): more CTAs in flight hide the store drain; BN=128 has 6 stages, BN=64 has 8
         return 128 if m_tiles * -(-n_out // 128) >= NUM_SMS else 64
