@@ -159,7 +159,11 @@ class LatencyShardedPipeline:
         r = dist.get_rank(self.pair)
         lo, hi = frame_range(f, r, 2)
         per = -(-f // 2)
-        local = self.pipe.vae.decode_frames_uint8(lat[:, :, lo:hi].contiguous())
+        if hi > lo:
+            local = self.pipe.vae.decode_frames_uint8(lat[:, :, lo:hi].contiguous())
+        else:                                                     # a one-frame clip: the second rank of the pair has nothing to decode
+            sf = self.pipe.vae_scale_factor
+            local = torch.zeros((0, lat.shape[3] * sf, lat.shape[0] * lat.shape[4] * sf, 3), dtype=torch.uint8, device=lat.device)
         if local.shape[0] < per:
             local = torch.cat([local, torch.zeros((per - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype,
                                                   device=local.device)], dim=0)
