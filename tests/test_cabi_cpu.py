@@ -77,6 +77,23 @@ def test_pick_box_and_block_n():
     assert ops.pick_block_n(1280, 17) == 256          # widest tile even with fewer tiles than SMs (measured 1.7x)
     assert ops.pick_block_n(2560, 2) == 64            # GEMV-like: spread weight rows
     assert ops.pick_block_n(320, 1088, k_total=320) == 128
+    # round 2c (UNet384's 32 / 64-channel levels, profiles/r02c_alpha_tail_kernels_*.md): N <= 64 takes 64-column tiles
+    assert ops.pick_block_n(64, 8192, k_total=576) == 64 and ops.pick_block_n(128, 8192, k_total=1152) == 256
+
+
+def test_new_entry_points_reject_bad_arguments_without_a_gpu():
+    """Argument checks of the round-2c entry points run before any CUDA call: status 1 (bad argument) on a box with no GPU."""
+    import ctypes as C
+    from animate_anything_b200 import _lib
+    lib = _lib.load()
+    buf = (C.c_float * 64)()
+    p = C.cast(buf, C.c_void_p)
+    assert lib.aab_video_f32_to_nhwc8(None, 0, 0, 0, 0, 0, p, 1, 3, 1, 8, 8, 1, None) == 1
+    assert lib.aab_video_f32_to_nhwc8(p, 0, 0, 0, 0, 0, p, 1, 9, 1, 8, 8, 1, None) == 1            # more than 8 channels
+    assert lib.aab_rgba_finalize_u8(p, 3, p, 16, 1, None) == 1                                      # needs 4 channels per pixel
+    assert lib.aab_rgba_finalize_u8(p, 4, None, 16, 1, None) == 1
+    assert lib.aab_pad_cols(p, 32, p, 4, 32, 16, None) == 1                                         # destination narrower than source
+    assert lib.aab_pad_cols(p, 30, p, 4, 32, 64, None) == 1                                         # row stride not a multiple of 8
 
 
 def test_column_statistics_tile_order_predicate():
