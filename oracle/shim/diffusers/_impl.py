@@ -9,6 +9,11 @@ golden vectors for this path.  The reference's own compos
 (`models/unet_3d_condition_mask.py`, `models/unet_3d_blocks.py`, `models/pipeline.py`) are imported
 verbatim on top of this shim by `tests/golden/make_golden.py` to generate golden vectors.
 
+Partial third-party pins that do exist (tests/test_oracle_third_party_pin.py, tests/test_gpu_clip.py): the VAE leaf
+modules and topologies below reproduce `transformers`' implementation of the same LDM autoencoder
+(JanusVQVAEEncoder / Decoder) to 1e-5 with shared weights; the CLIP text tower is compared with the real
+`transformers.CLIPTextModel`.  Everything else stays recalled.
+
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py` (cpu_baseline / --impl reference) may import
 this package.  The product (`animate_anything_b200`) never does.
 
