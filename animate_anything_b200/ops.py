@@ -672,6 +672,8 @@ def pad_cols(x: torch.Tensor, dst_cols: int) -> torch.Tensor:
 def cat_cols(x: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
     """Materialised channel concat [rows, C1 + C2] (two strided copies): used where the virtual concat of the implicit GEMM
     cannot be (C1 not a multiple of the 64-channel K block)."""
+    _is_bf16(x)                                                   # 16-bit only: the second copy is addressed in 2-byte elements
+    assert x2.dtype == x.dtype and x2.shape[0] == x.shape[0]
     c1, c2 = x.shape[1], x2.shape[1]
     out = torch.empty((x.shape[0], c1 + c2), device=x.device, dtype=x.dtype)
     _lib.call("aab_copy2d", _ptr(x), x.stride(0), _ptr(out), out.stride(0), x.shape[0], c1, _stream())

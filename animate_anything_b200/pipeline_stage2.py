@@ -45,6 +45,10 @@ class MaskedLatentToVideoPipeline(LatentToVideoPipeline):
                                       "(the reference's own call at models/pipeline_stage2.py:282 raises TypeError)")
         if vae_alpha_decoder is None:
             raise TypeError("'NoneType' object is not callable")       # what :308 raises without a decoder
+        if not hasattr(vae_alpha_decoder, "decode_rgba_u8"):
+            raise TypeError("vae_alpha_decoder must be animate_anything_b200.layerdiffuse_VAE.UNet384 (the sm_100a mirror of "
+                            "models/layerdiffuse_VAE.py:UNet384); a torch module would mean an eager fallback, which this "
+                            "path does not have")
         _, latents = LatentToVideoPipeline.__call__(
             self, prompt=prompt, height=height, width=width, num_frames=num_frames,
             num_inference_steps=num_inference_steps, guidance_scale=guidance_scale, negative_prompt=negative_prompt, eta=eta,

@@ -39,7 +39,7 @@ def _epilogue(acc, bias=None, bias2=None, rows_per_bias2=1, residual=None, act=A
     if bias is not None:
         acc = acc + bias
     if bias2 is not None:
-        acc = acc + bias2.repeat_interleave(rows_per_bias2, dim=0)
+        acc = acc + bias2[torch.arange(acc.shape[0]) // rows_per_bias2]      # row / rows_per_bias2 selects the sample
     if residual is not None:
         acc = acc + residual
     return _act(acc, act) * out_scale
@@ -150,7 +150,75 @@ def rgba_finalize_u8(y, pixels, bf16):
     return torch.cat([fg, a], dim=1).to(torch.uint8)
 
 
-_EMULATED = dict(linear=linear, conv1x1_cat=conv1x1_cat, conv3x3=conv3x3, conv3x3_stride2=conv3x3_stride2, groupnorm=groupnorm,
+# ---------------------------------------------------------------------------------------------- main UNet3D path
+def unet_in_assemble(sample, cond, mask, t_frames):
+    """[B,4,F,h,w] + [B,4,1,h,w] (+ mask [Bm,1,1,h,w], batch b reads mask b % Bm) -> [B, T, h, w, 8], channels (mask, c0..c3, 0...)."""
+    b, _, f, h, w = sample.shape
+    x = torch.cat([cond, sample], dim=2).permute(0, 2, 3, 4, 1)            # [B, T, h, w, 4]
+    out = torch.zeros((b, f + 1, h, w, 8), dtype=sample.dtype)
+    if mask is not None:
+        idx = torch.arange(b) % mask.shape[0]
+        out[..., 0] = mask[idx, 0, 0][:, None].expand(b, f + 1, h, w)
+        out[..., 1:5] = x
+    else:
+        out[..., :4] = x
+    return out
+
+
+def unet_out_finalize(y, b, t, h, w, dtype):
+    return y[:, :4].reshape(b, t, h, w, 4)[:, 1:].permute(0, 4, 1, 2, 3).to(dtype).contiguous()
+
+
+def timestep_embed(t, b, dim, dtype):
+    half = dim // 2
+    freq = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    tv = t.float().reshape(-1)[torch.arange(b) % t.numel()]
+    a = tv[:, None] * freq[None]
+    return torch.cat([torch.cos(a), torch.sin(a)], dim=1).to(dtype)
+
+
+def layernorm(x, gamma, beta, eps=1e-5):
+    return F.layer_norm(x.float(), (x.shape[1],), gamma, beta, eps)
+
+
+def temporal_attn_d64(qkv, b, t, hw, heads, q_col0, k_col0, v_col0):
+    """rows ordered (b, t, hw); attention over t for every (b, pixel, head)."""
+    def pick(col0):
+        return qkv[:, col0: col0 + heads * 64].float().view(b, t, hw, heads, 64).permute(0, 2, 3, 1, 4)   # b hw heads t 64
+    q, k, v = pick(q_col0), pick(k_col0), pick(v_col0)
+    p = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(64.0), dim=-1)
+    return (p @ v).permute(0, 3, 1, 2, 4).reshape(b * t * hw, heads * 64)
+
+
+def tconv3(x, b, t, hw, w, bias=None, **kw):
+    c = x.shape[1]
+    xi = x.float().view(b, t, hw, c).permute(0, 3, 1, 2)                   # b c t hw
+    w5 = w.float().view(w.shape[0], 3, c).permute(0, 2, 1)[..., None]      # [Cout, C, 3, 1]
+    y = F.conv2d(xi, w5, padding=(1, 0))
+    return _epilogue(y.permute(0, 2, 3, 1).reshape(b * t * hw, -1), bias, **kw)
+
+
+def dup_rows(x):
+    return torch.cat([x, x], dim=0)
+
+
+def geglu(x):
+    nh = x.shape[1] // 2
+    return x[:, :nh] * F.gelu(x[:, nh:].float())
+
+
+def upsample_nearest(x, oh, ow):
+    return F.interpolate(x.float().permute(0, 3, 1, 2), size=(oh, ow), mode="nearest").permute(0, 2, 3, 1).contiguous()
+
+
+def pad_to_even(x):
+    n, h, w, c = x.shape
+    return F.pad(x, (0, 0, 0, w & 1, 0, h & 1))
+
+
+_EMULATED = dict(unet_in_assemble=unet_in_assemble, unet_out_finalize=unet_out_finalize, timestep_embed=timestep_embed,
+                 layernorm=layernorm, temporal_attn_d64=temporal_attn_d64, tconv3=tconv3, dup_rows=dup_rows, geglu=geglu,
+                 upsample_nearest=upsample_nearest, pad_to_even=pad_to_even, linear=linear, conv1x1_cat=conv1x1_cat, conv3x3=conv3x3, conv3x3_stride2=conv3x3_stride2, groupnorm=groupnorm,
                  flash_attn_d64=flash_attn_d64, image_to_nhwc8=image_to_nhwc8, video_f32_to_nhwc8=video_f32_to_nhwc8,
                  upsample2x=upsample2x, pad_cols=pad_cols, cat_cols=cat_cols, svd_out_finalize=svd_out_finalize,
                  rgba_finalize_u8=rgba_finalize_u8)
