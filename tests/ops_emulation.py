@@ -216,7 +216,25 @@ def pad_to_even(x):
     return F.pad(x, (0, 0, 0, w & 1, 0, h & 1))
 
 
-_EMULATED = dict(unet_in_assemble=unet_in_assemble, unet_out_finalize=unet_out_finalize, timestep_embed=timestep_embed,
+def cfg_scheduler_step(eps, ldc, cfg, guidance, x, x_out, x0_hist, coef, step_idx):
+    """eps fp32 [Bu*T*h*w, >=4] channels-last with T = F + 1 (frame 0 = the condition frame, dropped), CFG halves ordered
+    [uncond..., text...]; x, x_out [n, 4, F, h, w]; coef one row of 6 (or a table indexed by step_idx)."""
+    n, _, f, h, w = x.shape
+    k = (coef if step_idx is None else coef[int(step_idx)]).reshape(-1)[:6].double()
+    e = eps[:, :4].double().reshape(-1, f + 1, h, w, 4)[:, 1:].permute(0, 4, 1, 2, 3)      # [Bu, 4, F, h, w]
+    if cfg:
+        e = e[:n] + guidance * (e[n:] - e[:n])
+    xv = x.double()
+    x0 = k[0] * xv + k[1] * e
+    xn = k[2] * xv + k[3] * e + k[4] * x0
+    if x0_hist is not None:
+        xn = xn + k[5] * x0_hist.double()
+        x0_hist.copy_(x0.to(x0_hist.dtype))
+    x_out.copy_(xn.to(x_out.dtype))
+    return x_out
+
+
+_EMULATED = dict(cfg_scheduler_step=cfg_scheduler_step, unet_in_assemble=unet_in_assemble, unet_out_finalize=unet_out_finalize, timestep_embed=timestep_embed,
                  layernorm=layernorm, temporal_attn_d64=temporal_attn_d64, tconv3=tconv3, dup_rows=dup_rows, geglu=geglu,
                  upsample_nearest=upsample_nearest, pad_to_even=pad_to_even, linear=linear, conv1x1_cat=conv1x1_cat, conv3x3=conv3x3, conv3x3_stride2=conv3x3_stride2, groupnorm=groupnorm,
                  flash_attn_d64=flash_attn_d64, image_to_nhwc8=image_to_nhwc8, video_f32_to_nhwc8=video_f32_to_nhwc8,
