@@ -234,7 +234,60 @@ def cfg_scheduler_step(eps, ldc, cfg, guidance, x, x_out, x0_hist, coef, step_id
     return x_out
 
 
-_EMULATED = dict(cfg_scheduler_step=cfg_scheduler_step, unet_in_assemble=unet_in_assemble, unet_out_finalize=unet_out_finalize, timestep_embed=timestep_embed,
+# ---------------------------------------------------------------------------------------------- SD VAE path
+def igemm(a, a_dims, a_strides, w, n, kc, dim_d, box, taps, out=None, ld_out=None, *, b_batch=0, b_batch_stride=0, b_batch_dim=-1,
+          ld_b=None, **kw):
+    """Only the form AutoencoderKL._mid_attention uses: no taps, A a 2-D [rows, >= kc] matrix, B batched over output dim 1
+    (`b_batch` matrices of `n` rows x `kc` columns, `b_batch_stride` elements apart inside `w`'s storage)."""
+    assert len(taps) == 1 and not any(taps[0]) and b_batch >= 1 and b_batch_dim == 1 and out is None
+    rows_per = dim_d[0]
+    a2 = a.float()[:, :kc]
+    ld = ld_b if ld_b is not None else w.stride(-2)
+    outs = []
+    for b in range(b_batch):
+        wb = torch.as_strided(w, (n, kc), (ld, 1), w.storage_offset() + b * b_batch_stride).float()
+        outs.append(a2[b * rows_per:(b + 1) * rows_per] @ wb.t())
+    return _epilogue(torch.cat(outs, dim=0), **kw)
+
+
+def softmax_rows(s, dtype, pad_to=None):
+    p = torch.softmax(s.float(), dim=1).to(dtype)
+    return p if not pad_to or pad_to == p.shape[1] else F.pad(p, (0, pad_to - p.shape[1]))
+
+
+def transpose_batched(src, col0, nb, rows, cols, ld=None):
+    ld = ld or rows
+    dst = torch.zeros((nb, cols, ld), dtype=src.dtype)
+    dst[:, :, :rows] = src[:, col0: col0 + cols].reshape(nb, rows, cols).permute(0, 2, 1)
+    return dst
+
+
+def vae_enc_finalize(mom, wq, bq, scale, b, f, h, w):
+    m = mom[:, :8].float() @ wq.float().t() + bq                                    # quant_conv 1x1
+    return (m * scale).reshape(b, f, h, w, 8).permute(0, 4, 1, 2, 3).to(mom.dtype).contiguous()
+
+
+def vae_dec_in(lat, inv_scale, wp, bp):
+    b, _, f, h, w = lat.shape
+    z = (lat.float() * inv_scale).permute(0, 2, 3, 4, 1).reshape(-1, 4) @ wp.float().t() + bp     # post_quant_conv 1x1
+    out = torch.zeros((b * f, h, w, 8), dtype=lat.dtype)
+    out[..., :4] = z.reshape(b * f, h, w, 4).to(lat.dtype)
+    return out
+
+
+def vae_dec_finalize(y, b, f, h, w, bf16):
+    return y[:, :3].float().reshape(b, f, h, w, 3).permute(0, 4, 1, 2, 3).contiguous()
+
+
+def vae_dec_finalize_u8(y, b, f, h, w, bf16):
+    v = y[:, :3].float().reshape(b, f, h, w, 3)
+    v = ((v * 0.5 + 0.5).clamp(0, 1) * 255).to(torch.uint8)
+    return v.permute(1, 2, 0, 3, 4).reshape(f, h, b * w, 3).contiguous()
+
+
+_EMULATED = dict(igemm=igemm, softmax_rows=softmax_rows, transpose_batched=transpose_batched, vae_enc_finalize=vae_enc_finalize,
+                 vae_dec_in=vae_dec_in, vae_dec_finalize=vae_dec_finalize, vae_dec_finalize_u8=vae_dec_finalize_u8,
+                 cfg_scheduler_step=cfg_scheduler_step, unet_in_assemble=unet_in_assemble, unet_out_finalize=unet_out_finalize, timestep_embed=timestep_embed,
                  layernorm=layernorm, temporal_attn_d64=temporal_attn_d64, tconv3=tconv3, dup_rows=dup_rows, geglu=geglu,
                  upsample_nearest=upsample_nearest, pad_to_even=pad_to_even, linear=linear, conv1x1_cat=conv1x1_cat, conv3x3=conv3x3, conv3x3_stride2=conv3x3_stride2, groupnorm=groupnorm,
                  flash_attn_d64=flash_attn_d64, image_to_nhwc8=image_to_nhwc8, video_f32_to_nhwc8=video_f32_to_nhwc8,

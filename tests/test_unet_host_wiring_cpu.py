@@ -139,3 +139,35 @@ def test_pipeline_host_logic_matches_oracle_loop(sched_name, steps, trunc):
     err = float((out - ref).abs().max())
     assert out.shape == ref.shape and err < 2e-3 * max(sc, 1.0), (err, sc)
     assert float((out - out2).abs().max()) < 1e-4 * max(sc, 1.0)
+
+
+def test_autoencoder_kl_mirror_wiring_matches_oracle():
+    """`AutoencoderKL` mirror (encode / `encode_video_latents` / `decode_video` / `decode_frames_uint8`, frame chunking, the
+    single-head mid-block attention as two batched GEMMs around a row softmax incl. the H*W % 8 != 0 padding) over the emulated
+    kernels against the oracle VAE — whose leaf modules and topology are pinned to `transformers`' LDM autoencoder
+    (tests/test_oracle_third_party_pin.py) and whose entry points are pinned to the verbatim reference calls."""
+    from oracle.composition import AutoencoderKL as OVAE, oracle_decode_latents, oracle_encode_image
+    from animate_anything_b200.autoencoder_kl import AutoencoderKL
+    cfg = dict(block_out_channels=(64, 64, 128, 128), layers_per_block=1, sample_size=64)
+    o = fill_deterministic(OVAE(**cfg).eval(), seed=1)
+    m = AutoencoderKL(**cfg).eval()
+    assert sorted(m.state_dict().keys()) == sorted(o.state_dict().keys())
+    m.load_state_dict(o.state_dict())
+    g = torch.Generator().manual_seed(2)
+    frames = torch.randn(1, 3, 3, 40, 56, generator=g).clamp(-1, 1)           # latent 5 x 7: H*W = 35, not a multiple of 8
+    lat = torch.randn(1, 4, 3, 5, 7, generator=g)
+    with torch.no_grad():
+        ref_lat = oracle_encode_image(o, frames)
+        ref_mean = o.encode(frames[0]).latent_dist.mode()
+        ref_vid = oracle_decode_latents(o, lat)
+    with emulated_ops():
+        _host_prepared(m)
+        m.frame_chunk = 2                                                     # 3 frames -> chunks of 2 + 1
+        got_lat = m.encode_video_latents(frames, scale=0.18215)
+        got_mean = m.encode(frames[0]).latent_dist.mode()
+        got_vid = m.decode_video(lat)
+        got_u8 = m.decode_frames_uint8(lat)
+    assert float((got_lat - ref_lat).abs().max()) < 2e-4 and float((got_mean - ref_mean).abs().max()) < 2e-4
+    assert got_vid.shape == ref_vid.shape == (1, 3, 3, 40, 56) and float((got_vid - ref_vid).abs().max()) < 5e-4
+    want_u8 = ((ref_vid * 0.5 + 0.5).clamp(0, 1) * 255).to(torch.uint8).permute(2, 3, 0, 4, 1).reshape(3, 40, 56, 3)
+    assert got_u8.shape == (3, 40, 56, 3) and int((got_u8.int() - want_u8.int()).abs().max()) <= 1
