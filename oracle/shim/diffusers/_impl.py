@@ -12,7 +12,8 @@ verbatim on top of this shim by `tests/golden/make_golden.py` to generate golden
 Partial third-party pins that do exist (tests/test_oracle_third_party_pin.py, tests/test_gpu_clip.py): the VAE leaf
 modules and topologies below reproduce `transformers`' implementation of the same LDM autoencoder
 (JanusVQVAEEncoder / Decoder) to 1e-5 with shared weights; the CLIP text tower is compared with the real
-`transformers.CLIPTextModel`.  Everything else stays recalled.
+`transformers.CLIPTextModel`; the DDIM / DPM-Solver++ / Euler step arithmetic satisfies the implementation-independent
+trajectory invariant of tests/test_scheduler_invariants_cpu.py.  Everything else stays recalled.
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py` (cpu_baseline / --impl reference) may import
 this package.  The product (`animate_anything_b200`) never does.
