@@ -122,3 +122,60 @@ def test_attention_block_is_live_in_the_comparison():
         torch.nn.init.zeros_(enc.mid_block.attentions[0].to_out[0].weight)
         b = enc(x)
     assert (a - b).abs().max() > 1e-4
+
+
+# ---------------------------------------------------------------------------------------------- the reference's own key map
+def test_reference_key_map_fixes_resnet_and_head_layer_order():
+    """The reference ships one artefact that states the leaf STRUCTURE independently of diffusers: the ModelScope <-> diffusers key
+    map of utils/convert_diffusers_to_original_ms_text_to_video.py.  Its index pairs (:22-25 `time_embed.0 / .2` = linear_1 /
+    linear_2; :34-37 `out.0 / .2` = conv_norm_out / conv_out; :44-49 `in_layers.0 / .2` = norm1 / conv1, `emb_layers.1` =
+    time_emb_proj, `out_layers.0 / .3` = norm2 / conv2, `skip_connection` = conv_shortcut) are the Sequential positions of the
+    original (guided-diffusion style) blocks, so the op order between the parametrised layers is fixed: GroupNorm, SiLU, conv |
+    SiLU, Linear | GroupNorm, SiLU, Dropout, conv.  Blocks built from exactly those positions and loaded through exactly those
+    pairs must equal the shim's ResnetBlock2D (time-embedding path included), TimestepEmbedding and output head."""
+    import torch.nn as nn
+    from diffusers._impl import ResnetBlock2D, TimestepEmbedding
+
+    res_map = [("in_layers.0", "norm1"), ("in_layers.2", "conv1"), ("out_layers.0", "norm2"), ("out_layers.3", "conv2"),
+               ("emb_layers.1", "time_emb_proj"), ("skip_connection", "conv_shortcut")]           # :44-49, verbatim pairs
+
+    class OriginalResBlock(nn.Module):
+        def __init__(self, cin, cout, temb, eps):
+            super().__init__()
+            self.in_layers = nn.Sequential(nn.GroupNorm(32, cin, eps=eps), nn.SiLU(), nn.Conv2d(cin, cout, 3, padding=1))
+            self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(temb, cout))
+            self.out_layers = nn.Sequential(nn.GroupNorm(32, cout, eps=eps), nn.SiLU(), nn.Dropout(0.0),
+                                            nn.Conv2d(cout, cout, 3, padding=1))
+            self.skip_connection = nn.Conv2d(cin, cout, 1) if cin != cout else nn.Identity()
+
+        def forward(self, x, emb):
+            h = self.in_layers(x)
+            h = h + self.emb_layers(emb)[:, :, None, None]
+            return self.skip_connection(x) + self.out_layers(h)
+
+    g = torch.Generator().manual_seed(0)
+    for cin, cout in ((64, 128), (64, 64)):
+        shim = fill_deterministic(ResnetBlock2D(in_channels=cin, out_channels=cout, temb_channels=96, eps=1e-5).eval(), seed=cin + cout)
+        orig = OriginalResBlock(cin, cout, 96, 1e-5).eval()
+        sd = {}
+        for k, v in shim.state_dict().items():
+            for o_name, hf_name in res_map:
+                if k.startswith(hf_name + "."):
+                    sd[o_name + k[len(hf_name):]] = v
+        assert len(sd) == len(shim.state_dict())
+        orig.load_state_dict(sd, strict=True)
+        x, emb = torch.randn(2, cin, 8, 8, generator=g), torch.randn(2, 96, generator=g)
+        with torch.no_grad():
+            assert torch.allclose(shim(x, emb), orig(x, emb), rtol=1e-5, atol=1e-5)
+    # time_embed = Sequential(Linear, SiLU, Linear) (:22-25): no activation after linear_2
+    te = fill_deterministic(TimestepEmbedding(32, 64, act_fn="silu").eval(), seed=5)
+    seq = nn.Sequential(nn.Linear(32, 64), nn.SiLU(), nn.Linear(64, 64)).eval()
+    seq.load_state_dict({"0.weight": te.linear_1.weight, "0.bias": te.linear_1.bias, "2.weight": te.linear_2.weight,
+                         "2.bias": te.linear_2.bias})
+    t = torch.randn(3, 32, generator=g)
+    with torch.no_grad():
+        assert torch.allclose(te(t), seq(t), rtol=1e-6, atol=1e-6)
+    # out = Sequential(GroupNorm, SiLU, conv) (:34-37) is how both the oracle and the mirror end the UNet (conv_norm_out, conv_act, conv_out)
+    from oracle.composition import OracleUNet3D
+    u = OracleUNet3D(block_out_channels=(32, 32, 32, 32), attention_head_dim=8, cross_attention_dim=16)
+    assert isinstance(u.conv_norm_out, nn.GroupNorm) and isinstance(u.conv_act, nn.SiLU) and isinstance(u.conv_out, nn.Conv2d)
