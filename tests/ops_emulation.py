@@ -285,7 +285,36 @@ def vae_dec_finalize_u8(y, b, f, h, w, bf16):
     return v.permute(1, 2, 0, 3, 4).reshape(f, h, b * w, 3).contiguous()
 
 
-_EMULATED = dict(igemm=igemm, softmax_rows=softmax_rows, transpose_batched=transpose_batched, vae_enc_finalize=vae_enc_finalize,
+# ---------------------------------------------------------------------------------------------- SVD path
+def image_to_nhwc16(img):
+    n, c, h, w = img.shape
+    out = torch.zeros((n, h, w, 16), dtype=img.dtype)
+    out[..., :c] = img.permute(0, 2, 3, 1)
+    return out
+
+
+def add_rowvec(x, vec, rows_per_vec, mod, mode=0, mod2=1, inplace=False):
+    """x[r] + vec[idx(r)]; mode 0: idx = (r // rows_per_vec) % mod; mode 1 (rows (b, f, s), S = rows_per_vec, F = mod2):
+    idx = (b * S + s) % mod."""
+    r = torch.arange(x.shape[0])
+    if mode == 0:
+        idx = (r // rows_per_vec) % mod
+    else:
+        s_ = r % rows_per_vec
+        b_ = r // (rows_per_vec * mod2)
+        idx = (b_ * rows_per_vec + s_) % mod
+    out = x + vec.to(x.dtype)[idx]
+    if inplace:
+        x.copy_(out)
+        return x
+    return out
+
+
+def axpby(x, y, a, b):
+    return a * x + b * y
+
+
+_EMULATED = dict(image_to_nhwc16=image_to_nhwc16, add_rowvec=add_rowvec, axpby=axpby, igemm=igemm, softmax_rows=softmax_rows, transpose_batched=transpose_batched, vae_enc_finalize=vae_enc_finalize,
                  vae_dec_in=vae_dec_in, vae_dec_finalize=vae_dec_finalize, vae_dec_finalize_u8=vae_dec_finalize_u8,
                  cfg_scheduler_step=cfg_scheduler_step, unet_in_assemble=unet_in_assemble, unet_out_finalize=unet_out_finalize, timestep_embed=timestep_embed,
                  layernorm=layernorm, temporal_attn_d64=temporal_attn_d64, tconv3=tconv3, dup_rows=dup_rows, geglu=geglu,

@@ -171,3 +171,59 @@ def test_autoencoder_kl_mirror_wiring_matches_oracle():
     assert got_vid.shape == ref_vid.shape == (1, 3, 3, 40, 56) and float((got_vid - ref_vid).abs().max()) < 5e-4
     want_u8 = ((ref_vid * 0.5 + 0.5).clamp(0, 1) * 255).to(torch.uint8).permute(2, 3, 0, 4, 1).reshape(3, 40, 56, 3)
     assert got_u8.shape == (3, 40, 56, 3) and int((got_u8.int() - want_u8.int()).abs().max()) <= 1
+
+
+def test_svd_unet_mirror_wiring_matches_oracle():
+    """Config-4 leg: `UNetSpatioTemporalConditionModel` mirror (SpatioTemporalResBlock with AlphaBlender, the single-key image
+    cross-attention as a per-sample vector, frame position embedding, temporal blocks incl. diffusers' (h*w, batch)-ordered
+    `time_context` quirk, added time ids) over the emulated kernels against the oracle restatement (oracle/shim/diffusers/_svd.py;
+    composition pinned to the verbatim reference SVD pipelines)."""
+    from oracle.composition import UNetSpatioTemporalConditionModel as OUNet
+    from animate_anything_b200.unet_spatio_temporal_condition import UNetSpatioTemporalConditionModel
+    cfg = dict(in_channels=9, block_out_channels=(64, 128, 128, 128), num_attention_heads=(1, 2, 2, 2), cross_attention_dim=96,
+               addition_time_embed_dim=32, projection_class_embeddings_input_dim=96, num_frames=4, sample_size=16)
+    o = fill_deterministic(OUNet(**cfg).eval(), seed=0)
+    m = UNetSpatioTemporalConditionModel(**cfg).eval()
+    m.load_state_dict(o.state_dict(), strict=True)
+    g = torch.Generator().manual_seed(3)
+    b, nf, h, w = 2, 4, 8, 16
+    x = torch.randn(b, nf, 9, h, w, generator=g)
+    emb = torch.randn(1, 1, 96, generator=g)
+    ehs = torch.cat([torch.zeros_like(emb), emb])
+    ids = torch.tensor([[6.0, 127.0, 0.02]] * 2)
+    t = torch.tensor(1.6378)
+    with torch.no_grad():
+        ref = o(x, t, ehs, ids, return_dict=False)[0]
+    with emulated_ops():
+        _host_prepared(m)
+        out = m(x, t, ehs, ids).sample
+    assert out.shape == ref.shape == (b, nf, 4, h, w)
+    err = float((out - ref).abs().max())
+    assert err < 5e-4 * max(1.0, float(ref.abs().mean())), err
+
+
+def test_svd_temporal_vae_mirror_wiring_matches_oracle():
+    """`AutoencoderKLTemporalDecoder` mirror: 2-D encoder, temporal decoder (spatio-temporal resblocks with the 'learned' blend
+    and image-only indicator handling, mid attention, the trailing frame-axis conv `time_conv_out`) over the emulated kernels
+    against the oracle restatement."""
+    from oracle.composition import AutoencoderKLTemporalDecoder as OVAE
+    from animate_anything_b200.autoencoder_kl_temporal_decoder import AutoencoderKLTemporalDecoder
+    cfg = dict(block_out_channels=(64, 64, 128, 128), layers_per_block=1)
+    o = fill_deterministic(OVAE(**cfg).eval(), seed=1)
+    m = AutoencoderKLTemporalDecoder(**cfg).eval()
+    assert sorted(m.state_dict().keys()) == sorted(o.state_dict().keys())
+    m.load_state_dict(o.state_dict())
+    g = torch.Generator().manual_seed(4)
+    z = torch.randn(3, 4, 6, 8, generator=g)
+    img = torch.randn(1, 3, 48, 64, generator=g).clamp(-1, 1)
+    with torch.no_grad():
+        ref = o.decode(z, num_frames=3).sample
+        ref_mean = o.encode(img).latent_dist.mode()
+    with emulated_ops():
+        _host_prepared(m)
+        out = m.decode(z, num_frames=3).sample
+        vid = m.decode_chunk_video(z, 3)
+        mean = m.encode(img).latent_dist.mode()
+    assert out.shape == ref.shape == (3, 3, 48, 64)
+    assert float((out.float() - ref).abs().max()) < 5e-4 and float((mean - ref_mean).abs().max()) < 2e-4
+    assert vid.shape == (1, 3, 3, 48, 64) and float((vid[0].permute(1, 0, 2, 3) - ref).abs().max()) < 5e-4
