@@ -162,3 +162,22 @@ def test_save_and_from_pretrained_roundtrip(tmp_path):
     assert m2.config.motion_mask is True and m2.config.motion_strength is True and m2.config.sample_size == 8
     for (k1, v1), (k2, v2) in zip(m.state_dict().items(), m2.state_dict().items()):
         assert k1 == k2 and torch.equal(v1, v2)
+
+
+def test_built_library_contains_blackwell_tensor_core_and_tma_sass():
+    """The shipped `libaab200.so` is sm_100a code whose SASS holds the 5th-generation tensor-core and TMA instructions the design
+    claims (B200_PROFILING.md mnemonics): UTCHMMA = tcgen05.mma (fp16 / bf16), LDTM = tcgen05.ld (TMEM -> registers), UTMALDG /
+    UTMASTG = cp.async.bulk.tensor load / store, UTCBAR = tcgen05.commit.  HMMA (mma.sync) only serves the T <= 32 temporal attention."""
+    import shutil
+    import subprocess
+    from animate_anything_b200 import _lib
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        import pytest
+        pytest.skip("cuobjdump not available")
+    arch = subprocess.run([tool, "-lelf", _lib.LIB_PATH], capture_output=True, text=True, timeout=120).stdout
+    assert "sm_100a" in arch, arch[:400]
+    sass = subprocess.run([tool, "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    count = {m: sass.count(m) for m in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UTCBAR", "HMMA")}
+    assert count["UTCHMMA"] >= 100 and count["LDTM"] >= 40 and count["UTMALDG"] >= 50 and count["UTMASTG"] >= 10, count
+    assert count["UTCBAR"] >= 30, count
