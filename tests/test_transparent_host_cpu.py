@@ -117,3 +117,58 @@ def test_masked_pipeline_signature_matches_reference():
               ("image_embeds", None)]
     got = [(n, p.default) for n, p in sig.parameters.items() if n != "self"]
     assert got == expect
+
+
+def test_masked_pipeline_host_logic_end_to_end():
+    """`MaskedLatentToVideoPipeline.__call__` called UNBOUND on a base pipeline object (train_transparent_i2v_stage2.py:500-515) with
+    every kernel emulated: UNet3D loop -> one VAE decoder pass with both tails -> UNet384 -> RGBA bytes, against
+    `oracle_masked_sampling_loop` (pinned to the verbatim reference call by tests/test_oracle_golden.py)."""
+    import numpy as np
+    from oracle.composition import (AutoencoderKL as OVAE, DDIMScheduler as ODDIM, OracleUNet3D, OracleUNet384,
+                                    oracle_masked_sampling_loop)
+    from animate_anything_b200 import schedulers as S
+    from animate_anything_b200.autoencoder_kl import AutoencoderKL
+    from animate_anything_b200.layerdiffuse_VAE import UNet384
+    from animate_anything_b200.pipeline_stage2 import MaskedLatentToVideoPipeline, TextToVideoSDPipeline
+    from animate_anything_b200.unet_3d_condition_mask import UNet3DConditionModel
+    ucfg = dict(sample_size=16, block_out_channels=(64, 64, 128, 128), attention_head_dim=64, cross_attention_dim=64,
+                motion_mask=True, motion_strength=True)
+    vcfg = dict(block_out_channels=(64, 64, 64, 64), layers_per_block=1, sample_size=64)
+    sk = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False, set_alpha_to_one=False,
+              steps_offset=1)
+    ounet = fill_deterministic(OracleUNet3D(**{k: v for k, v in ucfg.items() if k != "sample_size"}).eval(), 0)
+    ovae = fill_deterministic(OVAE(**vcfg).eval(), 1)
+    odec = fill_deterministic(OracleUNet384().eval(), 7)
+    unet, vae, dec = UNet3DConditionModel(**ucfg).eval(), AutoencoderKL(**vcfg).eval(), UNet384().eval()
+    unet.load_state_dict(ounet.state_dict())
+    vae.load_state_dict(ovae.state_dict())
+    dec.load_state_dict(odec.state_dict())
+    g = torch.Generator().manual_seed(6)
+    lat = torch.randn(1, 4, 2, 8, 8, generator=g)
+    cond = torch.randn(1, 4, 1, 8, 8, generator=g)
+    pe, ne = torch.randn(1, 7, 64, generator=g), torch.randn(1, 7, 64, generator=g)
+    mask1 = (torch.rand(1, 1, 1, 8, 8, generator=g) > 0.5).float()
+    with torch.no_grad():
+        ref_vid, ref_lat, ref_png = oracle_masked_sampling_loop(ounet, ODDIM(**sk), ovae, odec, lat, pe, ne, cond, mask1, [5],
+                                                                guidance_scale=9.0, num_inference_steps=2)
+    pipeline = TextToVideoSDPipeline(vae=vae, text_encoder=None, tokenizer=None, unet=unet, scheduler=S.DDIMScheduler(**sk))
+    pipeline.use_cuda_graph = False
+    with emulated_ops():
+        for m in (unet, vae, dec):
+            _host_prepared(m)
+        video, latents, pngs, alpha_png, pngs_rgb = MaskedLatentToVideoPipeline.__call__(
+            pipeline, clean_latents=lat.clone(), vae_alpha_decoder=dec, prompt_embeds=pe, negative_prompt_embeds=ne, latents=lat,
+            width=64, height=64, num_frames=2, num_inference_steps=2, guidance_scale=9.0, motion=[5], return_dict=False,
+            condition_latent=cond, mask=mask1)
+        with pytest.raises(TypeError):
+            MaskedLatentToVideoPipeline.__call__(pipeline, vae_alpha_decoder=torch.nn.Identity(), prompt_embeds=pe,
+                                                 negative_prompt_embeds=ne, latents=lat, condition_latent=cond, mask=mask1)
+    assert float((latents - ref_lat).abs().max()) < 2e-3 * max(1.0, float(ref_lat.abs().mean()))
+    assert len(video) == 2 and video[0].shape == (64, 64, 3) and video[0].dtype == np.uint8
+    want_frames = ((ref_vid * 0.5 + 0.5).clamp(0, 1) * 255).to(torch.uint8)[0].permute(1, 2, 3, 0).numpy()
+    assert np.abs(np.stack(video).astype(int) - want_frames.astype(int)).max() <= 1
+    assert pngs.shape == ref_png.shape == (2, 64, 64, 4)
+    d = np.abs(pngs.astype(int) - ref_png.astype(int))
+    # the emulated RGBA tail rounds through fp16 like the 16-bit product does; the oracle here ran in fp32
+    assert d[..., :3].mean() < 0.6 and (d[..., 3] != 0).mean() < 5e-3
+    assert (alpha_png == pngs[..., 3]).all() and (pngs_rgb == pngs[..., :3]).all()
