@@ -314,7 +314,39 @@ def axpby(x, y, a, b):
     return a * x + b * y
 
 
-_EMULATED = dict(image_to_nhwc16=image_to_nhwc16, add_rowvec=add_rowvec, axpby=axpby, igemm=igemm, softmax_rows=softmax_rows, transpose_batched=transpose_batched, vae_enc_finalize=vae_enc_finalize,
+def svd_in_assemble_frames(x, cond, mask, sigma, cfg, zero_uncond):
+    """x [B, F, 4, h, w]; cond [Hc, B, F' in (1, F), 4, h, w]; mask [B, F, h, w] or None -> [(2)B*F, h, w, 16]:
+    channels (mask?, x / sqrt(sigma^2 + 1), cond); the unconditional half (first) sees zero cond when `zero_uncond`."""
+    b, f, _, h, w = x.shape
+    xs = (x / math.sqrt(sigma * sigma + 1.0)).reshape(b * f, 4, h, w)
+    halves = []
+    for half in ((0, 1) if cfg else (1,)):
+        c = cond[min(half, cond.shape[0] - 1)] if cfg else cond[cond.shape[0] - 1]
+        c = c.expand(b, f, 4, h, w).reshape(b * f, 4, h, w)
+        if half == 0 and zero_uncond:
+            c = torch.zeros_like(c)
+        parts = ([mask.reshape(b * f, 1, h, w)] if mask is not None else []) + [xs, c]
+        halves.append(torch.cat(parts, dim=1))
+    return image_to_nhwc16(torch.cat(halves, dim=0))
+
+
+def svd_in_assemble(x, img_lat, mask, sigma, cfg):
+    b, f, _, h, w = x.shape
+    return svd_in_assemble_frames(x, img_lat.reshape(1, b, 1, 4, h, w), mask.reshape(1, 1, h, w).expand(b, f, h, w), sigma, cfg, True)
+
+
+def svd_cfg_euler_step(pred, cfg, gs, x, sigma, sigma_next):
+    b, f, _, h, w = x.shape
+    p = pred[:, :4].float().reshape(-1, f, h, w, 4).permute(0, 1, 4, 2, 3)                 # [(2)B, F, 4, h, w]
+    v = p[:b] + gs.float().reshape(1, f, 1, 1, 1) * (p[b:] - p[:b]) if cfg else p
+    xs = x.float()
+    s2 = sigma * sigma + 1.0
+    x0 = v * (-sigma / math.sqrt(s2)) + xs / s2
+    return (xs + (xs - x0) / sigma * (sigma_next - sigma)).to(x.dtype)
+
+
+_EMULATED = dict(svd_in_assemble=svd_in_assemble, svd_in_assemble_frames=svd_in_assemble_frames,
+                 svd_cfg_euler_step=svd_cfg_euler_step, image_to_nhwc16=image_to_nhwc16, add_rowvec=add_rowvec, axpby=axpby, igemm=igemm, softmax_rows=softmax_rows, transpose_batched=transpose_batched, vae_enc_finalize=vae_enc_finalize,
                  vae_dec_in=vae_dec_in, vae_dec_finalize=vae_dec_finalize, vae_dec_finalize_u8=vae_dec_finalize_u8,
                  cfg_scheduler_step=cfg_scheduler_step, unet_in_assemble=unet_in_assemble, unet_out_finalize=unet_out_finalize, timestep_embed=timestep_embed,
                  layernorm=layernorm, temporal_attn_d64=temporal_attn_d64, tconv3=tconv3, dup_rows=dup_rows, geglu=geglu,

@@ -227,3 +227,54 @@ def test_svd_temporal_vae_mirror_wiring_matches_oracle():
     assert out.shape == ref.shape == (3, 3, 48, 64)
     assert float((out.float() - ref).abs().max()) < 5e-4 and float((mean - ref_mean).abs().max()) < 2e-4
     assert vid.shape == (1, 3, 3, 48, 64) and float((vid[0].permute(1, 0, 2, 3) - ref).abs().max()) < 5e-4
+
+
+def test_svd_pipelines_host_logic_match_oracle_loop():
+    """Config-4 callers: `MaskStableVideoDiffusionPipeline.__call__` and `TextStableVideoDiffusionPipeline.__call__` (image branch,
+    with the caller's per-frame condition latents and with the image's own) over the emulated kernels — input assembly, UNet, per-frame
+    guidance + Euler step, chunked temporal decode — against `oracle_svd_sampling_loop` (pinned to the verbatim reference pipelines)."""
+    from oracle.composition import (SVD_SCHED, AutoencoderKLTemporalDecoder as OVAE, EulerDiscreteScheduler as OEuler,
+                                    UNetSpatioTemporalConditionModel as OUNet, oracle_svd_sampling_loop)
+    from animate_anything_b200.autoencoder_kl_temporal_decoder import AutoencoderKLTemporalDecoder
+    from animate_anything_b200.pipeline_svd import MaskStableVideoDiffusionPipeline, TextStableVideoDiffusionPipeline
+    from animate_anything_b200.schedulers import EulerDiscreteScheduler
+    from animate_anything_b200.unet_spatio_temporal_condition import UNetSpatioTemporalConditionModel
+    ucfg = dict(in_channels=9, block_out_channels=(64, 128, 128, 128), num_attention_heads=(1, 2, 2, 2), cross_attention_dim=96,
+                addition_time_embed_dim=32, projection_class_embeddings_input_dim=96, num_frames=4, sample_size=8)
+    vcfg = dict(block_out_channels=(64, 64, 64, 64), layers_per_block=1)
+    ounet = fill_deterministic(OUNet(**ucfg).eval(), 0)
+    ovae = fill_deterministic(OVAE(**vcfg).eval(), 1)
+    unet, vae = UNetSpatioTemporalConditionModel(**ucfg).eval(), AutoencoderKLTemporalDecoder(**vcfg).eval()
+    unet.load_state_dict(ounet.state_dict())
+    vae.load_state_dict(ovae.state_dict())
+    g = torch.Generator().manual_seed(6)
+    nf, hh, ww = 4, 64, 128
+    img = torch.randn(1, 3, hh, ww, generator=g).clamp(-1, 1)
+    mask = (torch.rand(1, hh // 8, ww // 8, generator=g) > 0.5).float()
+    fmask = (torch.rand(1, nf, 1, hh // 8, ww // 8, generator=g) > 0.5).float()
+    lat0 = torch.randn(1, nf, 4, hh // 8, ww // 8, generator=g)
+    cl = torch.randn(1, nf, 4, hh // 8, ww // 8, generator=g)
+    emb = torch.randn(1, 1, 96, generator=g)
+    kw = dict(height=hh, width=ww, num_frames=nf, num_inference_steps=3, decode_chunk_size=3, noise_aug_strength=0.0, latents=lat0,
+              image_embeddings=emb, return_dict=False)
+    okw = dict(num_inference_steps=3, noise_aug_strength=0.0)
+    with torch.no_grad():
+        il = ovae.encode(img).latent_dist.mode()
+        rf, rl = oracle_svd_sampling_loop(ounet, OEuler(**SVD_SCHED), ovae, emb, il, mask, lat0, decode_chunk_size=3, **okw)
+        _, r_c = oracle_svd_sampling_loop(ounet, OEuler(**SVD_SCHED), ovae, emb, il, None, lat0, frame_mask=fmask,
+                                          condition_latent=cl, decode=False, **okw)
+        _, r_i = oracle_svd_sampling_loop(ounet, OEuler(**SVD_SCHED), ovae, emb, il, None, lat0, frame_mask=fmask, decode=False, **okw)
+    with emulated_ops():
+        _host_prepared(unet)
+        _host_prepared(vae)
+        pm = MaskStableVideoDiffusionPipeline(vae=vae, image_encoder=None, unet=unet, scheduler=EulerDiscreteScheduler(**SVD_SCHED))
+        lat = pm(img, output_type="latent", mask=mask, **kw)
+        frames = pm(img, output_type="pt", mask=mask, **kw)
+        pt = TextStableVideoDiffusionPipeline(vae=vae, image_encoder=None, unet=unet, scheduler=EulerDiscreteScheduler(**SVD_SCHED))
+        lat_c = pt(img, condition_type="image", condition_latent=cl, output_type="latent", mask=fmask, **kw)
+        lat_i = pt(img, condition_type="image", output_type="latent", mask=fmask, **kw)
+    tol = 2e-3 * max(1.0, float(rl.abs().mean()))
+    assert float((lat - rl).abs().max()) < tol and float((lat_c - r_c).abs().max()) < tol and float((lat_i - r_i).abs().max()) < tol
+    want = (rf[0].permute(1, 0, 2, 3) / 2 + 0.5).clamp(0, 1)
+    assert frames[0].shape == want.shape and float((frames[0] - want).abs().max()) < 2e-3
+    assert float((lat_c - lat_i).abs().mean()) > 1e-2
